@@ -1,0 +1,151 @@
+/*
+ * ualm.h -- C ABI of the B200-native batched MINCO / augmented-Lagrangian trajectory optimizer.
+ *
+ * Drop-in boundary for ONE hot path of ZJU-FAST-Lab/uneven_planner: the back-end
+ *   uneven_planner::ALMTrajOpt::optimizeSE2Traj(...)            back_end/include/back_end/alm_traj_opt.h:92-98
+ *   uneven_planner::ALMTrajOpt::getTraj()                        alm_traj_opt.h:165-168
+ * with its environment binding
+ *   ALMTrajOpt::setEnvironment(UnevenMap::Ptr)                   alm_traj_opt.h:127-130
+ *   ALMTrajOpt::init(nh)  (the alm_traj_opt/ * rosparams)        back_end/src/alm_traj_opt.cpp:5-45
+ * (paths relative to /root/reference/src/uneven_planner/).  Plain pointers and sizes only; no
+ * torch / Eigen / ROS types.  Every entry point returns 0 on success or a negative UALM_E* code
+ * and never falls back to a CPU implementation: without a CUDA device the compute calls fail.
+ *
+ * All matrices use the reference's (Eigen column-major) layouts:
+ *   init_xy / end_xy : 2x3  [px,py, vx,vy, ax,ay]       (alm_traj_opt.cpp:183-186, pm.cpp:80-94)
+ *   inner_xy         : 2x(N-1) [x1,y1, x2,y2, ...]      (alm_traj_opt.cpp:211,215)
+ *   c_xy             : 6N x 2  (x column then y column; per piece 6 coefficients low->high power,
+ *                      se2traj.hpp:585, 712-715);  c_yaw : 6M
+ */
+#ifndef UALM_H
+#define UALM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UALM_OK 0
+#define UALM_ENOCUDA (-1)   /* no usable CUDA device / CUDA runtime error (message via ualm_last_error) */
+#define UALM_EINVAL (-2)    /* bad argument */
+#define UALM_ESTATE (-3)    /* call order (no map / no params / nothing uploaded) */
+#define UALM_ELIMIT (-4)    /* problem exceeds compiled limits (N, M, int_K) */
+
+/* ---- parameters: the 21 alm_traj_opt/ * values (alm_traj_opt.cpp:7-27) + uneven_map/gravity ---- */
+typedef struct {
+    double rho_T, rho_ter, max_vel, max_acc_lon, max_acc_lat, max_kap, min_cxi, max_sig;
+    int    use_scaling;
+    double rho, beta, gamma, epsilon_con, max_iter;
+    double g_epsilon, min_step, inner_max_iter, delta;
+    int    mem_size, past, int_K;
+    double gravity;          /* UnevenMap::getGravity(), uneven_map.cpp:85 */
+} ualm_params_t;
+
+/* run_hill.yaml defaults (plan_manager/params/run_hill.yaml:30-55) */
+void ualm_default_params(ualm_params_t *p);
+
+/* ---- environment: what ALMTrajOpt reads of UnevenMap (uneven_map.h:258-377, 398-454) ---- */
+typedef struct {
+    int    voxel_num[3];     /* X, Y, Yaw cells (uneven_map.cpp:108-110) */
+    double origin[3];        /* map_origin = min_boundary (uneven_map.cpp:99-101) */
+    double max_boundary[3];
+    double xy_resolution, yaw_resolution;
+} ualm_map_geom_t;
+
+/* geometry for map_size_x/y and resolutions exactly as UnevenMap::init computes it (uneven_map.cpp:96-114) */
+void ualm_map_geometry(double map_size_x, double map_size_y, double xy_resolution, double yaw_resolution,
+                       ualm_map_geom_t *g);
+
+/* ---- per-problem result record (what the reference prints / returns: alm_traj_opt.cpp:176,252,267,272-273;
+ *      alm_traj_opt.h:142) ---- */
+typedef struct {
+    int32_t ret_code;        /* 0 converged / 1 L-BFGS hard error / 2 ALM max_iter */
+    int32_t outer_iters;
+    int32_t n_evals;         /* cost+gradient evaluations */
+    int32_t n_lbfgs_iters;   /* accepted line searches */
+    int32_t last_lbfgs_ret;
+    int32_t max_bound;
+    double  inner_cost, jerk_cost, total_T, res_h, res_g, scale_fx, rho_final;
+} ualm_result_t;
+
+typedef struct ualm_ctx ualm_ctx_t;
+
+/* precision: 64 = parity path (double), 32 = throughput path (float).  device = CUDA ordinal. */
+int ualm_create(ualm_ctx_t **ctx, int device, int precision);
+int ualm_destroy(ualm_ctx_t *ctx);
+const char *ualm_last_error(void);
+int ualm_set_params(ualm_ctx_t *ctx, const ualm_params_t *p);                    /* ALMTrajOpt::init */
+/* cells: host, [X][Y][Yaw][4] float {z, sigma, zbx, zby}, address x*Y*Yaw + y*Yaw + yaw (uneven_map.h:427-435).
+ * One-time upload (replaces setEnvironment; the reference's map_buffer is private, uneven_map.h:91). */
+int ualm_set_map(ualm_ctx_t *ctx, const ualm_map_geom_t *g, const float *cells);
+
+/* ---- batch solve = B independent optimizeSE2Traj calls ----
+ * Ragged inputs are packed back to back in problem order: inner_xy has sum 2(N_b-1) doubles,
+ * inner_yaw sum (M_b-1); outputs c_xy sum 12 N_b, c_yaw sum 6 M_b.  bnd is B x 18:
+ * [init_xy(6) | end_xy(6) | init_yaw(3) | end_yaw(3)].  Host pointers. */
+int ualm_solve_batch(ualm_ctx_t *ctx, int B, const int32_t *N, const int32_t *M, const double *bnd,
+                     const double *total_time, const double *inner_xy, const double *inner_yaw,
+                     ualm_result_t *results, double *c_xy, double *c_yaw);
+
+/* The same in three steps, so a caller can keep inputs resident in HBM (bench `value`):
+ *   upload (H2D) -> solve_resident (kernels only, asynchronous on the context stream) -> download (D2H). */
+int ualm_upload(ualm_ctx_t *ctx, int B, const int32_t *N, const int32_t *M, const double *bnd,
+                const double *total_time, const double *inner_xy, const double *inner_yaw);
+int ualm_solve_resident(ualm_ctx_t *ctx);
+int ualm_sync(ualm_ctx_t *ctx);
+int ualm_download(ualm_ctx_t *ctx, ualm_result_t *results, double *c_xy, double *c_yaw);
+/* elapsed GPU time of the last solve_resident in ms (CUDA events on the context stream) and the
+ * number of kernel launches it made */
+int ualm_last_solve_ms(ualm_ctx_t *ctx, float *ms, int *launches);
+
+/* Fixed-stride result records for the multi-GPU all-gather: writes B records of `stride` doubles into
+ * a DEVICE buffer (e.g. a torch tensor): [ret, outer, evals, iters, cost, jerk, T, res_h, res_g, N, M, pad,
+ * c_xy(12N) , c_yaw(6M), zero pad].  stride >= 12 + 12 Nmax + 6 Mmax. */
+int ualm_pack_records_device(ualm_ctx_t *ctx, double *d_records, int stride);
+
+/* ---- phase entry points (kernel-level parity) ----
+ * One innerCallback evaluation (alm_traj_opt.cpp:280-347) per problem of the uploaded batch at the given
+ * decision vectors x (packed, n_b = 1+2(N_b-1)+(M_b-1)) with duals lambda[S_b], mu[6 S_b], scale_cx[7 S_b]
+ * in the reference's index layout (alm_traj_opt.cpp:705-707, 832-946), S_b = N_b (int_K+1).
+ * Outputs (host): f[B], grad (packed n_b), hx (packed S_b), gx (packed 6 S_b). Any input dual may be
+ * NULL (zeros / ones).  scale_fx[B], rho scalar. */
+int ualm_eval_batch(ualm_ctx_t *ctx, const double *x, const double *lambda, const double *mu,
+                    const double *scale_cx, const double *scale_fx, double rho,
+                    double *f, double *grad, double *hx, double *gx, double *c_xy, double *c_yaw);
+/* initScaling (alm_traj_opt.cpp:349-661) at the uploaded initial guesses: scale_fx[B], scale_cx packed 7 S_b */
+int ualm_init_scaling_batch(ualm_ctx_t *ctx, double *scale_fx, double *scale_cx);
+/* time `reps` back-to-back launches of the penalty-sampling kernel alone over the uploaded batch
+ * (roofline of calConstrainCostGrad, alm_traj_opt.cpp:663-991): average ms per launch */
+int ualm_time_penalty_kernel(ualm_ctx_t *ctx, int reps, float *ms_per_launch, double *algorithmic_bytes);
+
+/* =====================  host-side input pipeline (no GPU needed)  ===================== */
+
+/* UnevenMap::init cloud preprocessing + constructMap (uneven_map.cpp:127-163, 317-398, 5-43) on host
+ * threads.  pts: npts x 3 float (x,y,z) as read from the .pcd.  cells out: [X][Y][Yaw][4] float.
+ * ellipsoid = {0.2,0.1,0.1}, iter_num = 2 in every reference yaml. */
+int ualm_map_build(const float *pts, int64_t npts, const ualm_map_geom_t *g, double ellipsoid_x,
+                   double ellipsoid_y, double ellipsoid_z, int iter_num, int nthreads, float *cells);
+/* occupancy (uneven_map.cpp:169-179): occ3[X*Y*Yaw], occ2[X*Y] (1 = occupied) */
+int ualm_map_occupancy(const float *cells, const ualm_map_geom_t *g, double min_cnormal, double max_rho,
+                       uint8_t *occ3, uint8_t *occ2);
+
+/* Initial-guess path (stands in for KinoAstar::plan, front_end/src/kino_astar.cpp:67-236, whose one-shot is
+ * the same Dubins curve family, kino_astar.h:242-258): shortest forward Dubins path start->goal with
+ * turning radius `radius`, sampled every `ds` metres as (x,y,yaw).  Returns the number of points written
+ * (<= max_pts) or a negative error. */
+int ualm_dubins_path(const double start[3], const double goal[3], double radius, double ds, double *path_xyyaw,
+                     int max_pts);
+
+/* PlanManager::rcvWpsCallBack input contract (plan_manager/src/plan_manager.cpp:62-122): yaw unwrap, boundary
+ * states, arc-length resampling into inner xy / yaw waypoints, total_time.  Outputs: bnd[18], inner_xy
+ * (2 x (N-1)), inner_yaw (M-1); returns 0 and sets *N, *M, *total_time. */
+int ualm_resample_path(const double *path_xyyaw, int npts, double piece_len, double yaw_piece_times,
+                       double mean_vel, double init_time_times, double init_sig_vel, double *bnd,
+                       double *inner_xy, int max_inner_xy, double *inner_yaw, int max_inner_yaw, int32_t *N,
+                       int32_t *M, double *total_time);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
