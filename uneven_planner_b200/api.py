@@ -1,0 +1,131 @@
+"""Python face of the C ABI (include/ualm.h) used by tests and bench.py.
+
+`BatchALMTrajOpt` mirrors the reference's ALMTrajOpt wiring for a batch of problems:
+    init(params)            <- ALMTrajOpt::init(nh)                 (alm_traj_opt.cpp:5-45)
+    set_environment(map)    <- ALMTrajOpt::setEnvironment(map)      (alm_traj_opt.h:127-130)
+    optimize(problems)      <- B x ALMTrajOpt::optimizeSE2Traj(...) (alm_traj_opt.h:92-98), then getTraj()
+All compute happens inside libualm.so on the GPU; this file only marshals numpy arrays.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import Params, Result
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int32)
+
+
+def _p(a, t=dp):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+class UalmError(RuntimeError):
+    pass
+
+
+def _check(rc):
+    if rc != 0:
+        msg = _lib.lib().ualm_last_error()
+        raise UalmError(f"libualm error {rc}: {msg.decode() if msg else ''}")
+
+
+class BatchALMTrajOpt:
+    def __init__(self, device=0, precision=64):
+        L = _lib.lib()
+        if not hasattr(L, "ualm_create"):
+            raise ImportError("libualm.so was built without the CUDA translation unit")
+        self.L = L
+        self.h = C.c_void_p()
+        _check(L.ualm_create(C.byref(self.h), device, precision))
+        self.params = None
+        self.pb = None
+
+    def close(self):
+        if self.h:
+            self.L.ualm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def init(self, params=None):
+        self.params = params or _lib.default_params()
+        _check(self.L.ualm_set_params(self.h, C.byref(self.params)))
+        return self
+
+    def set_environment(self, mapdata):
+        self.map = mapdata
+        _check(self.L.ualm_set_map(self.h, C.byref(mapdata.geom), mapdata.cells.ctypes.data_as(C.POINTER(C.c_float))))
+        return self
+
+    # ---- three-step path -------------------------------------------------------------
+    def upload(self, pb):
+        self.pb = pb
+        self._keep = [np.ascontiguousarray(a) for a in (pb.N.astype(np.int32), pb.M.astype(np.int32), pb.bnd.astype(np.float64),
+                                                        pb.total_time.astype(np.float64), pb.inner_xy.astype(np.float64),
+                                                        pb.inner_yaw.astype(np.float64))]
+        N, M, bnd, T, ixy, iyaw = self._keep
+        _check(self.L.ualm_upload(self.h, pb.B, _p(N, ip), _p(M, ip), _p(bnd), _p(T), _p(ixy), _p(iyaw)))
+
+    def solve_resident(self):
+        _check(self.L.ualm_solve_resident(self.h))
+
+    def sync(self):
+        _check(self.L.ualm_sync(self.h))
+
+    def last_solve_ms(self):
+        ms, n = C.c_float(), C.c_int()
+        _check(self.L.ualm_last_solve_ms(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def download(self):
+        pb = self.pb
+        res = (Result * pb.B)()
+        cxy = np.zeros(int(12 * pb.N.astype(np.int64).sum()))
+        cyaw = np.zeros(int(6 * pb.M.astype(np.int64).sum()))
+        _check(self.L.ualm_download(self.h, res, _p(cxy), _p(cyaw)))
+        return res, cxy, cyaw
+
+    # ---- one call, host buffers in / host buffers out (the drop-in call) ---------------
+    def optimize(self, pb):
+        self.pb = pb
+        N = np.ascontiguousarray(pb.N, np.int32); M = np.ascontiguousarray(pb.M, np.int32)
+        bnd = np.ascontiguousarray(pb.bnd, np.float64); T = np.ascontiguousarray(pb.total_time, np.float64)
+        ixy = np.ascontiguousarray(pb.inner_xy, np.float64); iyaw = np.ascontiguousarray(pb.inner_yaw, np.float64)
+        res = (Result * pb.B)()
+        cxy = np.zeros(int(12 * N.astype(np.int64).sum()))
+        cyaw = np.zeros(int(6 * M.astype(np.int64).sum()))
+        _check(self.L.ualm_solve_batch(self.h, pb.B, _p(N, ip), _p(M, ip), _p(bnd), _p(T), _p(ixy), _p(iyaw), res, _p(cxy), _p(cyaw)))
+        return res, cxy, cyaw
+
+    def pack_records(self, dev_ptr, stride):
+        _check(self.L.ualm_pack_records_device(self.h, C.c_void_p(dev_ptr), stride))
+
+    # ---- phase entry points ----------------------------------------------------------
+    def eval_batch(self, x=None, lam=None, mu=None, scale_cx=None, scale_fx=None, rho=None):
+        pb = self.pb
+        K = self.params.int_K
+        nx = int(pb.nvar().sum()); S = int(pb.nsamples(K).sum())
+        f = np.zeros(pb.B); grad = np.zeros(nx); hx = np.zeros(S); gx = np.zeros(6 * S)
+        cxy = np.zeros(int(12 * pb.N.astype(np.int64).sum())); cyaw = np.zeros(int(6 * pb.M.astype(np.int64).sum()))
+        arrs = [None if a is None else np.ascontiguousarray(a, np.float64) for a in (x, lam, mu, scale_cx, scale_fx)]
+        _check(self.L.ualm_eval_batch(self.h, _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(arrs[3]), _p(arrs[4]),
+                                      float(self.params.rho if rho is None else rho), _p(f), _p(grad), _p(hx), _p(gx), _p(cxy), _p(cyaw)))
+        return dict(f=f, grad=grad, hx=hx, gx=gx, c_xy=cxy, c_yaw=cyaw)
+
+    def init_scaling_batch(self):
+        pb = self.pb
+        S = int(pb.nsamples(self.params.int_K).sum())
+        sfx = np.zeros(pb.B); scx = np.zeros(7 * S)
+        _check(self.L.ualm_init_scaling_batch(self.h, _p(sfx), _p(scx)))
+        return sfx, scx
+
+    def time_penalty_kernel(self, reps=10):
+        ms, by = C.c_float(), C.c_double()
+        _check(self.L.ualm_time_penalty_kernel(self.h, reps, C.byref(ms), C.byref(by)))
+        return ms.value, by.value

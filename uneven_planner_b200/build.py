@@ -17,13 +17,14 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 CU_SOURCES = ["ualm_api.cu"]
 CXX_SOURCES = ["host_tools.cpp"]
-HEADERS = ["ualm_kernels.cuh", "ualm_device_math.cuh", "minco_tables.hpp"]
+HEADERS = ["ualm_kernels.cuh", "../../include/ualm_detmath.h"]
 
 
 
 def _flags():
-    # no fast-math: the fp64 path is the parity path; fp32 uses explicit intrinsics where wanted
-    return ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    # -fmad=false: no FMA contraction, so every double result is bit-identical to the CPU oracle's
+    # (gcc -ffp-contract=off); fp64 division and sqrt are IEEE by default (no fast-math anywhere)
+    return ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
             "-Xcompiler", "-fPIC,-O3", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
             "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -1,0 +1,358 @@
+// ualm_api.cu -- the extern "C" layer declared in include/ualm.h: context, uploads, kernel launches.
+// Host code is thin: it packs descriptors, sizes shared memory from the batch maxima and launches the
+// per-trajectory kernels of ualm_kernels.cuh.  There is NO CPU fallback: every compute entry point needs a CUDA
+// device and returns UALM_ENOCUDA otherwise.
+#include "ualm_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace ualm;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess) return fail(UALM_ENOCUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct ualm_ctx {
+    int device = 0, precision = 64;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool have_params = false, have_map = false, have_batch = false, solved = false;
+    ualm_params_t hp;
+    DevParams dp;
+    DevMap dm;
+    DevBuf<float4> cells;
+    // batch
+    int B = 0, Nmax = 0, Mmax = 0, nmax = 0, Smax = 0;
+    std::vector<ProbDesc> desc;
+    std::vector<int> order;
+    long long tot_x = 0, tot_s = 0, tot_cxy = 0, tot_cyaw = 0, tot_hist = 0, tot_scr = 0, ws_stride = 0;
+    DevBuf<ProbDesc> d_desc;
+    DevBuf<int> d_order;
+    DevBuf<double> d_x0, d_x, d_lambda, d_mu, d_scale_cx, d_hx, d_gx, d_lm_s, d_lm_y, d_scr, d_ws, d_cxy, d_cyaw, d_f, d_grad, d_sfx;
+    DevBuf<ualm_result_t> d_res;
+    float last_ms = 0.f;
+    int last_launches = 0;
+    SmemLayout L;
+    size_t smem_bytes = 0;
+};
+
+extern "C" const char *ualm_last_error(void) { return g_err.c_str(); }
+
+extern "C" int ualm_create(ualm_ctx_t **out, int device, int precision)
+{
+    if (!out) return fail(UALM_EINVAL, "ctx out pointer is NULL");
+    if (precision != 64) return fail(UALM_EINVAL, "only precision=64 (bit-reproducible double path) is built in this round");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) return fail(UALM_ENOCUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(UALM_EINVAL, "device ordinal out of range");
+    CK(cudaSetDevice(device));
+    ualm_ctx *c = new ualm_ctx();
+    c->device = device; c->precision = precision;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+    *out = c;
+    return UALM_OK;
+}
+
+extern "C" int ualm_destroy(ualm_ctx_t *c)
+{
+    if (!c) return UALM_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->cells.release(); c->d_desc.release(); c->d_order.release();
+    DevBuf<double> *bufs[] = {&c->d_x0, &c->d_x, &c->d_lambda, &c->d_mu, &c->d_scale_cx, &c->d_hx, &c->d_gx, &c->d_lm_s, &c->d_lm_y,
+                              &c->d_scr, &c->d_ws, &c->d_cxy, &c->d_cyaw, &c->d_f, &c->d_grad, &c->d_sfx};
+    for (auto *b : bufs) b->release();
+    c->d_res.release();
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return UALM_OK;
+}
+
+extern "C" int ualm_set_params(ualm_ctx_t *c, const ualm_params_t *p)
+{
+    if (!c || !p) return fail(UALM_EINVAL, "null argument");
+    if (p->int_K < 1 || p->int_K > 128) return fail(UALM_ELIMIT, "int_K out of range [1,128]");
+    if (p->mem_size < 1 || p->mem_size > 1024) return fail(UALM_ELIMIT, "mem_size out of range [1,1024]");
+    if (p->past < 0 || p->past > 16) return fail(UALM_ELIMIT, "past out of range [0,16]");
+    c->hp = *p;
+    DevParams &d = c->dp;
+    d.rho_T = p->rho_T; d.rho_ter = p->rho_ter; d.max_vel = p->max_vel; d.max_acc_lon = p->max_acc_lon; d.max_acc_lat = p->max_acc_lat;
+    d.max_kap = p->max_kap; d.min_cxi = p->min_cxi; d.max_sig = p->max_sig; d.use_scaling = p->use_scaling; d.rho = p->rho;
+    d.beta = p->beta; d.gamma = p->gamma; d.epsilon_con = p->epsilon_con; d.max_iter = p->max_iter; d.g_epsilon = p->g_epsilon;
+    d.min_step = p->min_step; d.delta = p->delta; d.inner_max_iter = (int)p->inner_max_iter; d.mem_size = p->mem_size; d.past = p->past;
+    d.int_K = p->int_K; d.gravity = p->gravity;
+    c->have_params = true;
+    return UALM_OK;
+}
+
+extern "C" int ualm_set_map(ualm_ctx_t *c, const ualm_map_geom_t *g, const float *cells)
+{
+    if (!c || !g || !cells) return fail(UALM_EINVAL, "null argument");
+    CK(cudaSetDevice(c->device));
+    const size_t ncell = (size_t)g->voxel_num[0] * g->voxel_num[1] * g->voxel_num[2];
+    CK(c->cells.ensure(ncell));
+    CK(cudaMemcpyAsync(c->cells.p, cells, ncell * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    DevMap &m = c->dm;
+    m.cells = c->cells.p;
+    for (int k = 0; k < 3; k++) { m.vn[k] = g->voxel_num[k]; m.origin[k] = g->origin[k]; m.maxb[k] = g->max_boundary[k]; }
+    m.xy_res = g->xy_resolution; m.yaw_res = g->yaw_resolution;
+    m.xy_inv = 1.0 / g->xy_resolution; m.yaw_inv = 1.0 / g->yaw_resolution; // uneven_map.cpp:104-105
+    c->have_map = true;
+    return UALM_OK;
+}
+
+static int prepare_launch(ualm_ctx *c)
+{
+    c->L = make_layout(c->Nmax, c->Mmax, c->nmax, c->dp.mem_size, c->dp.past, c->dp.int_K, c->Smax);
+    c->smem_bytes = (size_t)c->L.total_doubles * sizeof(double);
+    if (c->smem_bytes > 227 * 1024) return fail(UALM_ELIMIT, "problem too large for shared memory (N/M/int_K too big)");
+    CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    CK(cudaFuncSetAttribute(eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    CK(cudaFuncSetAttribute(scaling_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    CK(cudaFuncSetAttribute(penalty_only_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    return UALM_OK;
+}
+
+static BatchPtrs batch_ptrs(ualm_ctx *c)
+{
+    BatchPtrs b;
+    b.desc = c->d_desc.p; b.order = c->d_order.p; b.x0 = c->d_x0.p; b.x = c->d_x.p;
+    b.lambda = c->d_lambda.p; b.mu = c->d_mu.p; b.scale_cx = c->d_scale_cx.p; b.hx = c->d_hx.p; b.gx = c->d_gx.p;
+    b.lm_s = c->d_lm_s.p; b.lm_y = c->d_lm_y.p; b.scratch = c->d_scr.p; b.ws_scaling = c->d_ws.p; b.ws_stride = c->ws_stride;
+    b.c_xy = c->d_cxy.p; b.c_yaw = c->d_cyaw.p; b.results = c->d_res.p; b.f_out = c->d_f.p; b.grad_out = c->d_grad.p;
+    b.scale_fx_io = c->d_sfx.p;
+    return b;
+}
+
+extern "C" int ualm_upload(ualm_ctx_t *c, int B, const int32_t *N, const int32_t *M, const double *bnd, const double *total_time,
+                           const double *inner_xy, const double *inner_yaw)
+{
+    if (!c || B < 0 || (B > 0 && (!N || !M || !bnd || !total_time))) return fail(UALM_EINVAL, "bad argument");
+    if (!c->have_params) return fail(UALM_ESTATE, "ualm_set_params must be called before ualm_upload");
+    CK(cudaSetDevice(c->device));
+    const int K = c->dp.int_K, m = c->dp.mem_size;
+    c->B = B; c->desc.resize(B); c->order.resize(B);
+    c->Nmax = c->Mmax = c->nmax = c->Smax = 1;
+    long long ox = 0, os = 0, ocx = 0, ocy = 0, oh = 0, oscr = 0, oixy = 0, oiyaw = 0;
+    std::vector<double> x0;
+    for (int b = 0; b < B; b++) {
+        ProbDesc &d = c->desc[b];
+        if (N[b] < 1 || M[b] < 1 || N[b] > 64 || M[b] > 128) return fail(UALM_ELIMIT, "piece count outside [1,64] x [1,128]");
+        d.N = N[b]; d.M = M[b]; d.n = 1 + 2 * (N[b] - 1) + (M[b] - 1); d.S = N[b] * (K + 1);
+        d.off_x = ox; d.off_s = os; d.off_cxy = ocx; d.off_cyaw = ocy; d.off_hist = oh; d.off_scr = oscr;
+        for (int k = 0; k < 18; k++) d.bnd[k] = bnd[(size_t)b * 18 + k];
+        d.total_time = total_time[b];
+        // x = [tau | Pxy | Pyaw]  (alm_traj_opt.cpp:205-216); logC2 (alm_traj_opt.h:238-241) is two IEEE ops + sqrt
+        const double T = total_time[b];
+        x0.push_back(T > 1.0 ? (std::sqrt(2.0 * T - 1.0) - 1.0) : (1.0 - std::sqrt(2.0 / T - 1.0)));
+        for (int q = 0; q < 2 * (d.N - 1); q++) x0.push_back(inner_xy[oixy + q]);
+        for (int q = 0; q < d.M - 1; q++) x0.push_back(inner_yaw[oiyaw + q]);
+        oixy += 2 * (d.N - 1); oiyaw += d.M - 1;
+        ox += d.n; os += d.S; ocx += 12 * d.N; ocy += 6 * d.M; oh += (long long)m * d.n; oscr += (long long)UALM_NFIELD * d.S;
+        c->Nmax = std::max(c->Nmax, d.N); c->Mmax = std::max(c->Mmax, d.M); c->nmax = std::max(c->nmax, d.n); c->Smax = std::max(c->Smax, d.S);
+    }
+    c->tot_x = ox; c->tot_s = os; c->tot_cxy = ocx; c->tot_cyaw = ocy; c->tot_hist = oh; c->tot_scr = oscr;
+    // launch order: most samples first (longest-processing-time-first keeps the tail short)
+    std::iota(c->order.begin(), c->order.end(), 0);
+    std::stable_sort(c->order.begin(), c->order.end(), [&](int a, int b2) { return c->desc[a].S > c->desc[b2].S; });
+    c->ws_stride = (long long)(12 * c->Nmax + 6 * c->Mmax) * UALM_THREADS;
+    CK(c->d_desc.ensure(B)); CK(c->d_order.ensure(B)); CK(c->d_x0.ensure(ox)); CK(c->d_x.ensure(ox)); CK(c->d_grad.ensure(ox));
+    CK(c->d_lambda.ensure(os)); CK(c->d_hx.ensure(os)); CK(c->d_mu.ensure(6 * os)); CK(c->d_gx.ensure(6 * os)); CK(c->d_scale_cx.ensure(7 * os));
+    CK(c->d_lm_s.ensure(oh)); CK(c->d_lm_y.ensure(oh)); CK(c->d_scr.ensure(oscr));
+    CK(c->d_ws.ensure(c->hp.use_scaling ? (size_t)c->ws_stride * B : 1));
+    CK(c->d_cxy.ensure(ocx)); CK(c->d_cyaw.ensure(ocy)); CK(c->d_res.ensure(B)); CK(c->d_f.ensure(B)); CK(c->d_sfx.ensure(B));
+    if (B > 0) {
+        CK(cudaMemcpyAsync(c->d_desc.p, c->desc.data(), sizeof(ProbDesc) * B, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_order.p, c->order.data(), sizeof(int) * B, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_x0.p, x0.data(), sizeof(double) * ox, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream)); // x0 is a stack-local staging vector
+    }
+    c->have_batch = true; c->solved = false;
+    return prepare_launch(c);
+}
+
+extern "C" int ualm_solve_resident(ualm_ctx_t *c)
+{
+    if (!c) return fail(UALM_EINVAL, "null ctx");
+    if (!c->have_map || !c->have_params || !c->have_batch) return fail(UALM_ESTATE, "set_params, set_map and upload must precede solve");
+    CK(cudaSetDevice(c->device));
+    c->last_launches = 0;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    if (c->B > 0) {
+        solve_kernel<<<c->B, UALM_THREADS, c->smem_bytes, c->stream>>>(batch_ptrs(c), c->dp, c->dm, c->L);
+        CK(cudaGetLastError());
+        c->last_launches = 1;
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    c->solved = true;
+    return UALM_OK;
+}
+
+extern "C" int ualm_sync(ualm_ctx_t *c)
+{
+    if (!c) return fail(UALM_EINVAL, "null ctx");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return UALM_OK;
+}
+
+extern "C" int ualm_last_solve_ms(ualm_ctx_t *c, float *ms, int *launches)
+{
+    if (!c || !c->solved) return fail(UALM_ESTATE, "no solve to time");
+    CK(cudaEventSynchronize(c->ev1));
+    CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    if (ms) *ms = c->last_ms;
+    if (launches) *launches = c->last_launches;
+    return UALM_OK;
+}
+
+extern "C" int ualm_download(ualm_ctx_t *c, ualm_result_t *results, double *c_xy, double *c_yaw)
+{
+    if (!c || !c->solved) return fail(UALM_ESTATE, "nothing solved");
+    CK(cudaSetDevice(c->device));
+    if (c->B > 0) {
+        if (results) CK(cudaMemcpyAsync(results, c->d_res.p, sizeof(ualm_result_t) * c->B, cudaMemcpyDeviceToHost, c->stream));
+        if (c_xy) CK(cudaMemcpyAsync(c_xy, c->d_cxy.p, sizeof(double) * c->tot_cxy, cudaMemcpyDeviceToHost, c->stream));
+        if (c_yaw) CK(cudaMemcpyAsync(c_yaw, c->d_cyaw.p, sizeof(double) * c->tot_cyaw, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return UALM_OK;
+}
+
+extern "C" int ualm_solve_batch(ualm_ctx_t *c, int B, const int32_t *N, const int32_t *M, const double *bnd, const double *total_time,
+                                const double *inner_xy, const double *inner_yaw, ualm_result_t *results, double *c_xy, double *c_yaw)
+{
+    int rc = ualm_upload(c, B, N, M, bnd, total_time, inner_xy, inner_yaw);
+    if (rc) return rc;
+    rc = ualm_solve_resident(c);
+    if (rc) return rc;
+    return ualm_download(c, results, c_xy, c_yaw);
+}
+
+extern "C" int ualm_pack_records_device(ualm_ctx_t *c, double *d_records, int stride)
+{
+    if (!c || !c->solved || !d_records) return fail(UALM_ESTATE, "nothing solved / null buffer");
+    if (stride < 12 + 12 * c->Nmax + 6 * c->Mmax) return fail(UALM_EINVAL, "record stride too small");
+    CK(cudaSetDevice(c->device));
+    if (c->B > 0) {
+        pack_records_kernel<<<c->B, 128, 0, c->stream>>>(batch_ptrs(c), c->B, d_records, stride);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return UALM_OK;
+}
+
+// upload an optional host array (or a constant fill) into a device buffer
+static int put(ualm_ctx *c, double *dst, const double *src, size_t n, double fill)
+{
+    if (n == 0) return UALM_OK;
+    if (src) { CK(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, c->stream)); }
+    else {
+        std::vector<double> tmp(n, fill);
+        CK(cudaMemcpyAsync(dst, tmp.data(), n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return UALM_OK;
+}
+
+extern "C" int ualm_eval_batch(ualm_ctx_t *c, const double *x, const double *lambda, const double *mu, const double *scale_cx,
+                               const double *scale_fx, double rho, double *f, double *grad, double *hx, double *gx, double *c_xy,
+                               double *c_yaw)
+{
+    if (!c || !c->have_batch || !c->have_map) return fail(UALM_ESTATE, "upload and set_map first");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if (x) { if ((rc = put(c, c->d_x0.p, x, c->tot_x, 0.0))) return rc; }
+    if ((rc = put(c, c->d_lambda.p, lambda, c->tot_s, 0.0))) return rc;
+    if ((rc = put(c, c->d_mu.p, mu, 6 * c->tot_s, 0.0))) return rc;
+    if ((rc = put(c, c->d_scale_cx.p, scale_cx, 7 * c->tot_s, 1.0))) return rc;
+    if ((rc = put(c, c->d_sfx.p, scale_fx, c->B, 1.0))) return rc;
+    if (c->B > 0) {
+        eval_kernel<<<c->B, UALM_THREADS, c->smem_bytes, c->stream>>>(batch_ptrs(c), c->dp, c->dm, c->L, rho);
+        CK(cudaGetLastError());
+        if (f) CK(cudaMemcpyAsync(f, c->d_f.p, sizeof(double) * c->B, cudaMemcpyDeviceToHost, c->stream));
+        if (grad) CK(cudaMemcpyAsync(grad, c->d_grad.p, sizeof(double) * c->tot_x, cudaMemcpyDeviceToHost, c->stream));
+        if (hx) CK(cudaMemcpyAsync(hx, c->d_hx.p, sizeof(double) * c->tot_s, cudaMemcpyDeviceToHost, c->stream));
+        if (gx) CK(cudaMemcpyAsync(gx, c->d_gx.p, sizeof(double) * 6 * c->tot_s, cudaMemcpyDeviceToHost, c->stream));
+        if (c_xy) CK(cudaMemcpyAsync(c_xy, c->d_cxy.p, sizeof(double) * c->tot_cxy, cudaMemcpyDeviceToHost, c->stream));
+        if (c_yaw) CK(cudaMemcpyAsync(c_yaw, c->d_cyaw.p, sizeof(double) * c->tot_cyaw, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return UALM_OK;
+}
+
+extern "C" int ualm_init_scaling_batch(ualm_ctx_t *c, double *scale_fx, double *scale_cx)
+{
+    if (!c || !c->have_batch || !c->have_map) return fail(UALM_ESTATE, "upload and set_map first");
+    CK(cudaSetDevice(c->device));
+    CK(c->d_ws.ensure((size_t)c->ws_stride * std::max(c->B, 1)));
+    if (c->B > 0) {
+        scaling_kernel<<<c->B, UALM_THREADS, c->smem_bytes, c->stream>>>(batch_ptrs(c), c->dp, c->dm, c->L);
+        CK(cudaGetLastError());
+        if (scale_fx) CK(cudaMemcpyAsync(scale_fx, c->d_sfx.p, sizeof(double) * c->B, cudaMemcpyDeviceToHost, c->stream));
+        if (scale_cx) CK(cudaMemcpyAsync(scale_cx, c->d_scale_cx.p, sizeof(double) * 7 * c->tot_s, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return UALM_OK;
+}
+
+extern "C" int ualm_time_penalty_kernel(ualm_ctx_t *c, int reps, float *ms_per_launch, double *algorithmic_bytes)
+{
+    if (!c || !c->have_batch || !c->have_map) return fail(UALM_ESTATE, "upload and set_map first");
+    if (reps < 1) return fail(UALM_EINVAL, "reps < 1");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = put(c, c->d_lambda.p, nullptr, c->tot_s, 0.0))) return rc;
+    if ((rc = put(c, c->d_mu.p, nullptr, 6 * c->tot_s, 0.0))) return rc;
+    if ((rc = put(c, c->d_scale_cx.p, nullptr, 7 * c->tot_s, 1.0))) return rc;
+    penalty_only_kernel<<<c->B, UALM_THREADS, c->smem_bytes, c->stream>>>(batch_ptrs(c), c->dp, c->dm, c->L, 1); // warm-up
+    CK(cudaEventRecord(c->ev0, c->stream));
+    penalty_only_kernel<<<c->B, UALM_THREADS, c->smem_bytes, c->stream>>>(batch_ptrs(c), c->dp, c->dm, c->L, reps);
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaGetLastError());
+    CK(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    if (ms_per_launch) *ms_per_launch = ms / reps;
+    if (algorithmic_bytes) {
+        // per trajectory per evaluation S*45e + (25N + 13M)e
+        double bytes = 0;
+        for (auto &d : c->desc) bytes += (double)d.S * 45 * 8 + (25.0 * d.N + 13.0 * d.M) * 8;
+        *algorithmic_bytes = bytes;
+    }
+    return UALM_OK;
+}

@@ -1,0 +1,1516 @@
+// ualm_kernels.cuh -- sm_100a device code of the batched MINCO / PHR-ALM / L-BFGS trajectory optimizer.
+//
+// One CTA (UALM_THREADS threads) owns one optimizeSE2Traj problem from the first evaluation to the last
+// dual update (no host round trips).  The arithmetic is IEEE double with contraction OFF (-fmad=false) and is
+// ordered so that every floating-point result is bit-identical to the CPU oracle (oracle/oracle.cpp):
+//   * work that is independent per element (band-matrix entries inside one pivot step, constraint samples,
+//     coefficient-gradient entries, history vectors) is spread over threads;
+//   * every reduction whose order is visible in the reference source is evaluated in that order by one thread
+//     (cost accumulation alm_traj_opt.cpp:825-943, gdC/gdT accumulation :969-985, triangular sweeps
+//     banded_system.hpp:96-145);
+//   * dot products / norms of the L-BFGS driver (order left to Eigen in the reference) use the canonical
+//     32-lane order: lane-strided partial sums + xor-butterfly 16,8,4,2,1 (warp shuffles).
+// Reference citations are relative to /root/reference/src/uneven_planner/.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ualm.h"
+#include "ualm_detmath.h"
+
+#define UALM_THREADS 128
+#define UALM_NFIELD 26          // per-sample scratch fields (see SF_* below)
+
+namespace ualm {
+
+typedef double R;
+
+// ---- compile-time constants of the reference (alm_traj_opt.h:16-19) ----
+#define UALM_DELTA_SIGL 0.01
+#define UALM_CUR_SCALE 10.0
+#define UALM_SIG_SCALE 1000.0
+#define UALM_SCALE_TRICK_JERK 1000.0
+
+// lbfgs return codes (lbfgs.hpp:135-184)
+enum {
+    LBFGS_CONVERGENCE = 0, LBFGS_STOP, LBFGS_CANCELED,
+    LBFGSERR_UNKNOWNERROR = -1024, LBFGSERR_INVALID_N, LBFGSERR_INVALID_MEMSIZE, LBFGSERR_INVALID_GEPSILON,
+    LBFGSERR_INVALID_TESTPERIOD, LBFGSERR_INVALID_DELTA, LBFGSERR_INVALID_MINSTEP, LBFGSERR_INVALID_MAXSTEP,
+    LBFGSERR_INVALID_FDECCOEFF, LBFGSERR_INVALID_SCURVCOEFF, LBFGSERR_INVALID_MACHINEPREC,
+    LBFGSERR_INVALID_MAXLINESEARCH, LBFGSERR_INVALID_FUNCVAL, LBFGSERR_MINIMUMSTEP, LBFGSERR_MAXIMUMSTEP,
+    LBFGSERR_MAXIMUMLINESEARCH, LBFGSERR_MAXIMUMITERATION, LBFGSERR_WIDTHTOOSMALL, LBFGSERR_INVALIDPARAMETERS,
+    LBFGSERR_INCREASEGRADIENT,
+};
+
+struct DevParams {
+    R rho_T, rho_ter, max_vel, max_acc_lon, max_acc_lat, max_kap, min_cxi, max_sig;
+    int use_scaling;
+    R rho, beta, gamma, epsilon_con, max_iter;
+    R g_epsilon, min_step, delta;
+    int inner_max_iter;
+    int mem_size, past, int_K;
+    R gravity;
+};
+
+struct DevMap {
+    const float4 *cells;   // {z, sigma, zbx, zby}
+    int vn[3];
+    R origin[3], maxb[3], xy_res, yaw_res, xy_inv, yaw_inv;
+};
+
+// one problem; offsets index the packed batch arrays
+struct ProbDesc {
+    int N, M, n, S;
+    long long off_x;      // n-sized vectors (x0, x_out, grad)
+    long long off_s;      // S-sized (lambda, hx); 6*off_s for mu/gx; 7*off_s for scale_cx
+    long long off_cxy;    // 12 N
+    long long off_cyaw;   // 6 M
+    long long off_hist;   // mem_size * n  (lm_s, lm_y)
+    long long off_scr;    // UALM_NFIELD * S per-sample scratch
+    R bnd[18];
+    R total_time;
+};
+
+struct BatchPtrs {
+    const ProbDesc *desc;
+    const int *order;        // launch order (largest first); blockIdx.x -> problem index
+    const R *x0;             // packed initial decision vectors
+    R *x;                    // packed final decision vectors
+    R *lambda, *mu, *scale_cx, *hx, *gx;
+    R *lm_s, *lm_y;
+    R *scratch;
+    R *ws_scaling;           // initScaling adjoint workspace: per CTA  (6N*2 + 6M) * UALM_THREADS
+    long long ws_stride;     // elements per CTA
+    R *c_xy, *c_yaw;
+    ualm_result_t *results;
+    // eval entry
+    R *f_out, *grad_out, *scale_fx_io;
+};
+
+// per-sample scratch fields (SoA: scratch[field * S + s])
+enum {
+    SF_COST0 = 0,              // 8 cost terms in accumulation order: user, nonhol, vx, ax, ay, curv, att, sig
+    SF_GP = 8, SF_GV = 10, SF_GA = 12, SF_GYAW = 14, SF_GDYAW = 15,
+    SF_VEL = 16, SF_ACC = 18, SF_JER = 20, SF_DYAW = 22, SF_D2YAW = 23, SF_S1YAW = 24, SF_USER = 25
+};
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory layout (doubles), sized on the host from the batch maxima
+// ---------------------------------------------------------------------------------------------
+struct SmemLayout {
+    int Axy, Ayaw, cxy, cyaw, gCxy, gCyaw, gCxy_j, gCyaw_j, gTxy, gTyaw, gTxy_j, gTyaw_j, pcost_xy, pcost_yaw;
+    int x, g, xp, gp, d, lm_alpha, lm_ys, pf, s1tab, base, sc, yawidx /* shorts */, total_doubles;
+};
+
+__host__ __device__ inline SmemLayout make_layout(int Nmax, int Mmax, int nmax, int m, int past, int K, int Smax)
+{
+    SmemLayout L;
+    int o = 0;
+    L.Axy = o; o += 13 * 6 * Nmax;
+    L.Ayaw = o; o += 13 * 6 * Mmax;
+    L.cxy = o; o += 12 * Nmax;
+    L.cyaw = o; o += 6 * Mmax;
+    L.gCxy = o; o += 12 * Nmax;
+    L.gCyaw = o; o += 6 * Mmax;
+    L.gCxy_j = o; o += 12 * Nmax;
+    L.gCyaw_j = o; o += 6 * Mmax;
+    L.gTxy = o; o += Nmax;
+    L.gTyaw = o; o += Mmax;
+    L.gTxy_j = o; o += Nmax;
+    L.gTyaw_j = o; o += Mmax;
+    L.pcost_xy = o; o += Nmax;
+    L.pcost_yaw = o; o += Mmax;
+    L.x = o; o += nmax;
+    L.g = o; o += nmax;
+    L.xp = o; o += nmax;
+    L.gp = o; o += nmax;
+    L.d = o; o += nmax;
+    L.lm_alpha = o; o += m;
+    L.lm_ys = o; o += m;
+    L.pf = o; o += (past > 1 ? past : 1);
+    L.s1tab = o; o += K + 1;
+    L.base = o; o += Nmax;
+    L.sc = o; o += 64;               // scalars
+    L.yawidx = o; o += (Smax + 3) / 4; // shorts packed
+    L.total_doubles = o;
+    return L;
+}
+
+// scalar slots in sm[L.sc + ...]
+enum {
+    SC_TX1 = 0, SC_TX2, SC_TX3, SC_TX4, SC_TX5, SC_TY1, SC_TY2, SC_TY3, SC_TY4, SC_TY5,
+    SC_SCALE_FX, SC_RHO, SC_F, SC_JERK, SC_CONSTR, SC_TAUCOST, SC_RED0, SC_RED1, SC_RED2, SC_RED3,
+    SC_STEP, SC_FX, SC_FINIT, SC_DGINIT, SC_DGTEST, SC_DSTEST, SC_MU, SC_NU, SC_YS, SC_YY, SC_TMP0, SC_TMP1,
+    SC_RESH, SC_RESG, SC_JERKRAW
+};
+
+struct Traj {
+    // problem
+    int N, M, n, S, K;
+    const ProbDesc *pd;
+    // smem
+    R *sm;
+    SmemLayout L;
+    R *Axy, *Ayaw, *cxy, *cyaw, *gCxy, *gCyaw, *gCxy_j, *gCyaw_j, *gTxy, *gTyaw, *gTxy_j, *gTyaw_j, *pcx, *pcy;
+    R *x, *g, *xp, *gp, *d, *lm_alpha, *lm_ys, *pf, *s1tab, *base, *sc;
+    unsigned short *yawidx;
+    // global
+    R *lambda, *mu, *scale_cx, *hx, *gx, *lm_s, *lm_y, *scr;
+    int n_evals;
+};
+
+__device__ __forceinline__ R expC2(R tau) // alm_traj_opt.h:232-235
+{
+    return tau > 0.0 ? ((0.5 * tau + 1.0) * tau + 1.0) : 1.0 / ((0.5 * tau - 1.0) * tau + 1.0);
+}
+__device__ __forceinline__ R logC2(R T) // alm_traj_opt.h:238-241
+{
+    return T > 1.0 ? (sqrt(2.0 * T - 1.0) - 1.0) : (1.0 - sqrt(2.0 / T - 1.0));
+}
+__device__ __forceinline__ R getTtoTauGrad(R tau) // alm_traj_opt.h:244-253
+{
+    if (tau > 0) return tau + 1.0;
+    R denSqrt = (0.5 * tau - 1.0) * tau + 1.0;
+    return (1.0 - tau) / (denSqrt * denSqrt);
+}
+__device__ __forceinline__ void normSO2(R &yaw) // uneven_map.cpp:64-71
+{
+    while (yaw < -M_PI) yaw += 2 * M_PI;
+    while (yaw > M_PI) yaw -= 2 * M_PI;
+}
+
+// band accessor: ptr[(i - j + 6) * n6 + j]   (banded_system.hpp:55-62)
+#define BAND(A, n6, i, j) (A)[((i) - (j) + 6) * (n6) + (j)]
+
+// ---------------------------------------------------------------------------------------------
+// MINCO: fill A and b (se2traj.hpp:609-674).  All threads; ends with __syncthreads.
+// ---------------------------------------------------------------------------------------------
+__device__ void minco_fill(Traj &t, int tid)
+{
+    const int N = t.N, M = t.M, nx = 6 * N, ny = 6 * M;
+    for (int q = tid; q < 13 * nx; q += UALM_THREADS) t.Axy[q] = 0.0;
+    for (int q = tid; q < 13 * ny; q += UALM_THREADS) t.Ayaw[q] = 0.0;
+    for (int q = tid; q < 2 * nx; q += UALM_THREADS) t.cxy[q] = 0.0;
+    for (int q = tid; q < ny; q += UALM_THREADS) t.cyaw[q] = 0.0;
+    __syncthreads();
+    // two systems: sys 0 = xy (Dim 2), sys 1 = yaw (Dim 1)
+    for (int sys = 0; sys < 2; sys++) {
+        R *A = sys ? t.Ayaw : t.Axy;
+        const int P = sys ? M : N, n6 = 6 * P;
+        const R T1 = t.sc[sys ? SC_TY1 : SC_TX1], T2 = t.sc[sys ? SC_TY2 : SC_TX2], T3 = t.sc[sys ? SC_TY3 : SC_TX3],
+                T4 = t.sc[sys ? SC_TY4 : SC_TX4], T5 = t.sc[sys ? SC_TY5 : SC_TX5];
+        for (int i = tid; i < P - 1; i += UALM_THREADS) {
+            BAND(A, n6, 6 * i + 3, 6 * i + 3) = 6.0;
+            BAND(A, n6, 6 * i + 3, 6 * i + 4) = 24.0 * T1;
+            BAND(A, n6, 6 * i + 3, 6 * i + 5) = 60.0 * T2;
+            BAND(A, n6, 6 * i + 3, 6 * i + 9) = -6.0;
+            BAND(A, n6, 6 * i + 4, 6 * i + 4) = 24.0;
+            BAND(A, n6, 6 * i + 4, 6 * i + 5) = 120.0 * T1;
+            BAND(A, n6, 6 * i + 4, 6 * i + 10) = -24.0;
+            BAND(A, n6, 6 * i + 5, 6 * i) = 1.0;
+            BAND(A, n6, 6 * i + 5, 6 * i + 1) = T1;
+            BAND(A, n6, 6 * i + 5, 6 * i + 2) = T2;
+            BAND(A, n6, 6 * i + 5, 6 * i + 3) = T3;
+            BAND(A, n6, 6 * i + 5, 6 * i + 4) = T4;
+            BAND(A, n6, 6 * i + 5, 6 * i + 5) = T5;
+            BAND(A, n6, 6 * i + 6, 6 * i) = 1.0;
+            BAND(A, n6, 6 * i + 6, 6 * i + 1) = T1;
+            BAND(A, n6, 6 * i + 6, 6 * i + 2) = T2;
+            BAND(A, n6, 6 * i + 6, 6 * i + 3) = T3;
+            BAND(A, n6, 6 * i + 6, 6 * i + 4) = T4;
+            BAND(A, n6, 6 * i + 6, 6 * i + 5) = T5;
+            BAND(A, n6, 6 * i + 6, 6 * i + 6) = -1.0;
+            BAND(A, n6, 6 * i + 7, 6 * i + 1) = 1.0;
+            BAND(A, n6, 6 * i + 7, 6 * i + 2) = 2.0 * T1;
+            BAND(A, n6, 6 * i + 7, 6 * i + 3) = 3.0 * T2;
+            BAND(A, n6, 6 * i + 7, 6 * i + 4) = 4.0 * T3;
+            BAND(A, n6, 6 * i + 7, 6 * i + 5) = 5.0 * T4;
+            BAND(A, n6, 6 * i + 7, 6 * i + 7) = -1.0;
+            BAND(A, n6, 6 * i + 8, 6 * i + 2) = 2.0;
+            BAND(A, n6, 6 * i + 8, 6 * i + 3) = 6.0 * T1;
+            BAND(A, n6, 6 * i + 8, 6 * i + 4) = 12.0 * T2;
+            BAND(A, n6, 6 * i + 8, 6 * i + 5) = 20.0 * T3;
+            BAND(A, n6, 6 * i + 8, 6 * i + 8) = -2.0;
+        }
+        if (tid == 0) {
+            BAND(A, n6, 0, 0) = 1.0;
+            BAND(A, n6, 1, 1) = 1.0;
+            BAND(A, n6, 2, 2) = 2.0;
+            BAND(A, n6, n6 - 3, n6 - 6) = 1.0;
+            BAND(A, n6, n6 - 3, n6 - 5) = T1;
+            BAND(A, n6, n6 - 3, n6 - 4) = T2;
+            BAND(A, n6, n6 - 3, n6 - 3) = T3;
+            BAND(A, n6, n6 - 3, n6 - 2) = T4;
+            BAND(A, n6, n6 - 3, n6 - 1) = T5;
+            BAND(A, n6, n6 - 2, n6 - 5) = 1.0;
+            BAND(A, n6, n6 - 2, n6 - 4) = 2.0 * T1;
+            BAND(A, n6, n6 - 2, n6 - 3) = 3.0 * T2;
+            BAND(A, n6, n6 - 2, n6 - 2) = 4.0 * T3;
+            BAND(A, n6, n6 - 2, n6 - 1) = 5.0 * T4;
+            BAND(A, n6, n6 - 1, n6 - 4) = 2.0;
+            BAND(A, n6, n6 - 1, n6 - 3) = 6.0 * T1;
+            BAND(A, n6, n6 - 1, n6 - 2) = 12.0 * T2;
+            BAND(A, n6, n6 - 1, n6 - 1) = 20.0 * T3;
+        }
+    }
+    // right-hand sides
+    const R *bnd = t.pd->bnd;
+    const R *Pxy = t.x + 1, *Pyaw = t.x + 1 + 2 * (N - 1);
+    if (tid < 2) { // dim d = tid: head PVA rows 0..2, tail rows
+        const int d = tid;
+        t.cxy[0 + d * nx] = bnd[d + 0]; t.cxy[1 + d * nx] = bnd[d + 2]; t.cxy[2 + d * nx] = bnd[d + 4];
+        t.cxy[nx - 3 + d * nx] = bnd[6 + d + 0]; t.cxy[nx - 2 + d * nx] = bnd[6 + d + 2]; t.cxy[nx - 1 + d * nx] = bnd[6 + d + 4];
+    }
+    if (tid == 2) {
+        t.cyaw[0] = bnd[12]; t.cyaw[1] = bnd[13]; t.cyaw[2] = bnd[14];
+        t.cyaw[ny - 3] = bnd[15]; t.cyaw[ny - 2] = bnd[16]; t.cyaw[ny - 1] = bnd[17];
+    }
+    for (int i = tid; i < N - 1; i += UALM_THREADS) {
+        t.cxy[6 * i + 5] = Pxy[2 * i];
+        t.cxy[6 * i + 5 + nx] = Pxy[2 * i + 1];
+    }
+    for (int i = tid; i < M - 1; i += UALM_THREADS) t.cyaw[6 * i + 5] = Pyaw[i];
+    __syncthreads();
+}
+
+// banded LU without pivoting, one warp per system (banded_system.hpp:66-91).  Element-wise the update
+// sequence is that of the reference; the 6 multipliers / 36 updates of one pivot step run on different lanes.
+__device__ void banded_lu_warp(R *A, int n6, int lane)
+{
+    for (int k = 0; k <= n6 - 2; k++) {
+        const int iM = min(k + 6, n6 - 1);
+        const R cVl = BAND(A, n6, k, k);
+        if (lane < 6) {
+            const int i = k + 1 + lane;
+            if (i <= iM) {
+                R v = BAND(A, n6, i, k);
+                if (v != 0.0) BAND(A, n6, i, k) = v / cVl;
+            }
+        }
+        __syncwarp();
+        const int jM = min(k + 6, n6 - 1);
+        for (int e = lane; e < 36; e += 32) {
+            const int i = k + 1 + e / 6, j = k + 1 + e % 6;
+            if (i <= iM && j <= jM) {
+                const R c = BAND(A, n6, k, j);
+                if (c != 0.0) {
+                    const R l = BAND(A, n6, i, k);
+                    if (l != 0.0) BAND(A, n6, i, j) = BAND(A, n6, i, j) - l * c;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// forward + backward substitution of ONE right-hand-side column by one thread, row-oriented but with the
+// per-element update order of banded_system.hpp:96-118 (ascending j, then descending j, then the division).
+__device__ void banded_solve_col(const R *A, int n6, R *b)
+{
+    for (int i = 0; i < n6; i++) {
+        R v = b[i];
+        for (int j = max(0, i - 6); j < i; j++) {
+            const R l = BAND(A, n6, i, j);
+            if (l != 0.0) v = v - l * b[j];
+        }
+        b[i] = v;
+    }
+    for (int i = n6 - 1; i >= 0; i--) {
+        R v = b[i];
+        for (int j = min(n6 - 1, i + 6); j > i; j--) {
+            const R u = BAND(A, n6, i, j);
+            if (u != 0.0) v = v - u * b[j];
+        }
+        b[i] = v / BAND(A, n6, i, i);
+    }
+}
+
+// A^T x = b, same conventions (banded_system.hpp:123-145).  b has element stride `st` (1 = smem vector;
+// UALM_THREADS = the interleaved per-thread workspace of initScaling).
+__device__ void banded_solve_adj_col(const R *A, int n6, R *b, int st)
+{
+    for (int i = 0; i < n6; i++) {
+        R v = b[(size_t)i * st];
+        for (int j = max(0, i - 6); j < i; j++) {
+            const R u = BAND(A, n6, j, i);
+            if (u != 0.0) v = v - u * b[(size_t)j * st];
+        }
+        b[(size_t)i * st] = v / BAND(A, n6, i, i);
+    }
+    for (int i = n6 - 1; i >= 0; i--) {
+        R v = b[(size_t)i * st];
+        for (int j = min(n6 - 1, i + 6); j > i; j--) {
+            const R l = BAND(A, n6, j, i);
+            if (l != 0.0) v = v - l * b[(size_t)j * st];
+        }
+        b[(size_t)i * st] = v;
+    }
+}
+
+// x -> T powers, A, LU, c   (alm_traj_opt.cpp:293-299 + se2traj.hpp:595-680)
+__device__ void minco_generate(Traj &t, int tid)
+{
+    if (tid == 0) {
+        const R tau = t.x[0];
+        const R T = expC2(tau);
+        const R Tx = T / (R)t.N, Ty = T / (R)t.M; // calTfromTau alm_traj_opt.h:257-261
+        t.sc[SC_TX1] = Tx; t.sc[SC_TX2] = Tx * Tx; t.sc[SC_TX3] = t.sc[SC_TX2] * Tx; t.sc[SC_TX4] = t.sc[SC_TX2] * t.sc[SC_TX2];
+        t.sc[SC_TX5] = t.sc[SC_TX4] * Tx;
+        t.sc[SC_TY1] = Ty; t.sc[SC_TY2] = Ty * Ty; t.sc[SC_TY3] = t.sc[SC_TY2] * Ty; t.sc[SC_TY4] = t.sc[SC_TY2] * t.sc[SC_TY2];
+        t.sc[SC_TY5] = t.sc[SC_TY4] * Ty;
+    }
+    __syncthreads();
+    minco_fill(t, tid);
+    const int warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) banded_lu_warp(t.Axy, 6 * t.N, lane);
+    else if (warp == 1) banded_lu_warp(t.Ayaw, 6 * t.M, lane);
+    __syncthreads();
+    if (tid == 0) banded_solve_col(t.Axy, 6 * t.N, t.cxy);
+    else if (tid == 32) banded_solve_col(t.Axy, 6 * t.N, t.cxy + 6 * t.N);
+    else if (tid == 64) banded_solve_col(t.Ayaw, 6 * t.M, t.cyaw);
+    __syncthreads();
+}
+
+// jerk cost and its (C,T) gradient (se2traj.hpp:697-747).  Per-piece values in parallel, the sum over pieces
+// sequentially by thread 0 (same order as the reference's `energy +=` loop).  Leaves sc[SC_JERKRAW].
+__device__ void jerk_cost_grad(Traj &t, int tid)
+{
+    const int N = t.N, M = t.M, nx = 6 * N;
+    for (int q = tid; q < N + M; q += UALM_THREADS) {
+        const bool isy = q >= N;
+        const int i = isy ? q - N : q;
+        const R T1 = t.sc[isy ? SC_TY1 : SC_TX1], T2 = t.sc[isy ? SC_TY2 : SC_TX2], T3 = t.sc[isy ? SC_TY3 : SC_TX3],
+                T4 = t.sc[isy ? SC_TY4 : SC_TX4], T5 = t.sc[isy ? SC_TY5 : SC_TX5];
+        R d33, d43, d44, d53, d54, d55;
+        if (!isy) {
+            const R a3 = t.cxy[6 * i + 3], a4 = t.cxy[6 * i + 4], a5 = t.cxy[6 * i + 5];
+            const R b3 = t.cxy[6 * i + 3 + nx], b4 = t.cxy[6 * i + 4 + nx], b5 = t.cxy[6 * i + 5 + nx];
+            d33 = a3 * a3 + b3 * b3; d43 = a4 * a3 + b4 * b3; d44 = a4 * a4 + b4 * b4;
+            d53 = a5 * a3 + b5 * b3; d54 = a5 * a4 + b5 * b4; d55 = a5 * a5 + b5 * b5;
+            for (int dd = 0; dd < 2; dd++) {
+                const R c3 = t.cxy[6 * i + 3 + dd * nx], c4 = t.cxy[6 * i + 4 + dd * nx], c5 = t.cxy[6 * i + 5 + dd * nx];
+                R *G = t.gCxy_j + dd * nx + 6 * i;
+                G[5] = 240.0 * c3 * T3 + 720.0 * c4 * T4 + 1440.0 * c5 * T5;
+                G[4] = 144.0 * c3 * T2 + 384.0 * c4 * T3 + 720.0 * c5 * T4;
+                G[3] = 72.0 * c3 * T1 + 144.0 * c4 * T2 + 240.0 * c5 * T3;
+                G[0] = 0.0; G[1] = 0.0; G[2] = 0.0;
+            }
+        } else {
+            const R c3 = t.cyaw[6 * i + 3], c4 = t.cyaw[6 * i + 4], c5 = t.cyaw[6 * i + 5];
+            d33 = c3 * c3; d43 = c4 * c3; d44 = c4 * c4; d53 = c5 * c3; d54 = c5 * c4; d55 = c5 * c5;
+            R *G = t.gCyaw_j + 6 * i;
+            G[5] = 240.0 * c3 * T3 + 720.0 * c4 * T4 + 1440.0 * c5 * T5;
+            G[4] = 144.0 * c3 * T2 + 384.0 * c4 * T3 + 720.0 * c5 * T4;
+            G[3] = 72.0 * c3 * T1 + 144.0 * c4 * T2 + 240.0 * c5 * T3;
+            G[0] = 0.0; G[1] = 0.0; G[2] = 0.0;
+        }
+        const R e = 36.0 * d33 * T1 + 144.0 * d43 * T2 + 192.0 * d44 * T3 + 240.0 * d53 * T3 + 720.0 * d54 * T4 + 720.0 * d55 * T5;
+        const R gt = 36.0 * d33 + 288.0 * d43 * T1 + 576.0 * d44 * T2 + 720.0 * d53 * T2 + 2880.0 * d54 * T3 + 3600.0 * d55 * T4;
+        if (!isy) { t.pcx[i] = e; t.gTxy_j[i] = gt; }
+        else { t.pcy[i] = e; t.gTyaw_j[i] = gt; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        R ex = 0.0, ey = 0.0;
+        for (int i = 0; i < N; i++) ex += t.pcx[i];
+        for (int i = 0; i < M; i++) ey += t.pcy[i];
+        t.sc[SC_JERKRAW] = ex + ey; // MINCO_SE2::getTrajJerkCost se2traj.hpp:852-855
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// UnevenMap::getAllWithGrad  (uneven_map.h:258-377)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool map_in(const DevMap &m, const R pos[3]) // uneven_map.h:437-454
+{
+    if (pos[0] < m.origin[0] + 1e-4 || pos[1] < m.origin[1] + 1e-4 || pos[2] < m.origin[2] + 1e-4) return false;
+    if (pos[0] > m.maxb[0] - 1e-4 || pos[1] > m.maxb[1] - 1e-4 || pos[2] > m.maxb[2] - 1e-4) return false;
+    return true;
+}
+
+__device__ void map_get_all_with_grad(const DevMap &m, const R pos[3], R values[7], R grads[7][3])
+{
+    R rs[3], rg[4][3];
+    if (!map_in(m, pos)) {
+        for (int r = 0; r < 4; r++) for (int k = 0; k < 3; k++) rg[r][k] = 0.0;
+        rs[0] = rs[1] = rs[2] = 0.0;
+    } else {
+        R pos_m[3] = {pos[0] - 0.5 * m.xy_res, pos[1] - 0.5 * m.xy_res, pos[2] - 0.5 * m.yaw_res};
+        normSO2(pos_m[2]);
+        int idx[3];
+        idx[0] = (int)floor((pos_m[0] - m.origin[0]) * m.xy_inv);
+        idx[1] = (int)floor((pos_m[1] - m.origin[1]) * m.xy_inv);
+        idx[2] = (int)floor((pos_m[2] - m.origin[2]) * m.yaw_inv);
+        R idx_pos[3];
+        idx_pos[0] = ((R)idx[0] + 0.5) * m.xy_res + m.origin[0];
+        idx_pos[1] = ((R)idx[1] + 0.5) * m.xy_res + m.origin[1];
+        idx_pos[2] = ((R)idx[2] + 0.5) * m.yaw_res + m.origin[2];
+        R diff[3];
+        diff[0] = (pos[0] - idx_pos[0]) * m.xy_inv;
+        diff[1] = (pos[1] - idx_pos[1]) * m.xy_inv;
+        {
+            R sd, cd;
+            ualm_sincos(pos[2] - idx_pos[2], &sd, &cd);
+            diff[2] = ualm_atan2(sd, cd) * m.yaw_inv;
+        }
+        R v[2][2][2][3];
+#pragma unroll
+        for (int x = 0; x < 2; x++)
+#pragma unroll
+            for (int y = 0; y < 2; y++)
+#pragma unroll
+                for (int w = 0; w < 2; w++) {
+                    int c0 = idx[0] + x, c1 = idx[1] + y, c2 = idx[2] + w;
+                    c0 = max(min(c0, m.vn[0] - 1), 0);
+                    c1 = max(min(c1, m.vn[1] - 1), 0);
+                    while (c2 > m.vn[2] - 1) c2 -= m.vn[2];
+                    while (c2 < 0) c2 += m.vn[2];
+                    const float4 cell = __ldg(&m.cells[(size_t)c0 * m.vn[1] * m.vn[2] + (size_t)c1 * m.vn[2] + c2]);
+                    v[x][y][w][0] = (R)cell.y; v[x][y][w][1] = (R)cell.z; v[x][y][w][2] = (R)cell.w;
+                }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const R v00 = v[0][0][0][k] * (1 - diff[0]) + v[1][0][0][k] * diff[0];
+            const R v01 = v[0][0][1][k] * (1 - diff[0]) + v[1][0][1][k] * diff[0];
+            const R v10 = v[0][1][0][k] * (1 - diff[0]) + v[1][1][0][k] * diff[0];
+            const R v11 = v[0][1][1][k] * (1 - diff[0]) + v[1][1][1][k] * diff[0];
+            const R v0 = v00 * (1 - diff[1]) + v10 * diff[1];
+            const R v1 = v01 * (1 - diff[1]) + v11 * diff[1];
+            rs[k] = v0 * (1 - diff[2]) + v1 * diff[2];
+            rg[k][2] = (v1 - v0) * m.yaw_inv;
+            rg[k][1] = ((v10 - v00) * (1 - diff[2]) + (v11 - v01) * diff[2]) * m.xy_inv;
+            R g0 = (1 - diff[2]) * (1 - diff[1]) * (v[1][0][0][k] - v[0][0][0][k]);
+            g0 += (1 - diff[2]) * diff[1] * (v[1][1][0][k] - v[0][1][0][k]);
+            g0 += diff[2] * (1 - diff[1]) * (v[1][0][1][k] - v[0][0][1][k]);
+            g0 += diff[2] * diff[1] * (v[1][1][1][k] - v[0][1][1][k]);
+            g0 *= m.xy_inv;
+            rg[k][0] = g0;
+        }
+        const R cc = sqrt(1.0 - rs[1] * rs[1] - rs[2] * rs[2]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) rg[3][k] = -(rg[1][k] * rs[1] + rg[2][k] * rs[2]) / cc;
+    }
+    const R c = sqrt(1.0 - rs[1] * rs[1] - rs[2] * rs[2]);
+    const R inv_c = 1.0 / c;
+    R syaw, cyaw;
+    ualm_sincos(pos[2], &syaw, &cyaw);
+    const R xyaw[2] = {cyaw, syaw};
+    const R yyaw[2] = {-syaw, cyaw};
+    const R tt = xyaw[0] * rs[1] + xyaw[1] * rs[2];
+    const R s = -(yyaw[0] * rs[1] + yyaw[1] * rs[2]);
+    const R sqrt_1_t2 = sqrt(1.0 - tt * tt);
+    const R inv_sqrt_1_t2 = 1.0 / sqrt_1_t2;
+    const R inv_sqrt_1_t2_3 = inv_sqrt_1_t2 * inv_sqrt_1_t2 * inv_sqrt_1_t2;
+    R dt[3], ds[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        dt[k] = rg[1][k] * xyaw[0] + rg[2][k] * xyaw[1];
+        ds[k] = -(rg[1][k] * yyaw[0] + rg[2][k] * yyaw[1]);
+    }
+    dt[2] -= s;
+    ds[2] += tt;
+    values[0] = inv_sqrt_1_t2;
+    values[1] = -c * tt * inv_sqrt_1_t2;
+    values[2] = sqrt_1_t2 * inv_c;
+    values[3] = s * inv_sqrt_1_t2;
+    values[4] = c;
+    values[5] = inv_c;
+    values[6] = rs[0];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        grads[0][k] = tt * inv_sqrt_1_t2_3 * dt[k];
+        grads[1][k] = -(tt * inv_sqrt_1_t2 * rg[3][k] + inv_sqrt_1_t2_3 * c * dt[k]);
+        grads[2][k] = -inv_c * (tt * inv_sqrt_1_t2 * dt[k] + sqrt_1_t2 * inv_c * rg[3][k]);
+        grads[3][k] = inv_sqrt_1_t2 * ds[k] + tt * inv_sqrt_1_t2_3 * s * dt[k];
+        grads[4][k] = rg[3][k];
+        grads[5][k] = -inv_c * inv_c * rg[3][k];
+        grads[6][k] = rg[0][k];
+    }
+}
+
+// kinematics of one constraint sample (alm_traj_opt.cpp:733-817)
+struct SampleK {
+    R b0[6], b1[6], b2[6], b3[6], y0[6], y1[6], y2[6];
+    R pos[2], vel[2], acc[2], jer[2];
+    R yaw, dyaw, d2yaw, syaw, cyaw, v_norm, lon_acc, lat_acc;
+    R tv[7], tg[7][3];
+    R vx, wz, ax, ay, curv_snorm;
+    int yaw_idx;
+};
+
+__device__ void sample_kin(const Traj &t, const DevMap &map, R gravity, int i, R s1, R base_time, SampleK &S)
+{
+    const int nx = 6 * t.N;
+    const R s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
+    S.b0[0] = 1.0; S.b0[1] = s1; S.b0[2] = s2; S.b0[3] = s3; S.b0[4] = s4; S.b0[5] = s5;
+    S.b1[0] = 0.0; S.b1[1] = 1.0; S.b1[2] = 2.0 * s1; S.b1[3] = 3.0 * s2; S.b1[4] = 4.0 * s3; S.b1[5] = 5.0 * s4;
+    S.b2[0] = 0.0; S.b2[1] = 0.0; S.b2[2] = 2.0; S.b2[3] = 6.0 * s1; S.b2[4] = 12.0 * s2; S.b2[5] = 20.0 * s3;
+    S.b3[0] = 0.0; S.b3[1] = 0.0; S.b3[2] = 0.0; S.b3[3] = 6.0; S.b3[4] = 24.0 * s1; S.b3[5] = 60.0 * s2;
+#pragma unroll
+    for (int d = 0; d < 2; d++) {
+        R p = 0, v = 0, a = 0, j = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const R c = t.cxy[6 * i + k + d * nx];
+            p += c * S.b0[k]; v += c * S.b1[k]; a += c * S.b2[k]; j += c * S.b3[k];
+        }
+        S.pos[d] = p; S.vel[d] = v; S.acc[d] = a; S.jer[d] = j;
+    }
+    const R Ty = t.sc[SC_TY1];
+    const R now_time = s1 + base_time;
+    int yaw_idx = (int)(now_time / Ty);
+    if (yaw_idx >= t.M) yaw_idx = t.M - 1;
+    S.yaw_idx = yaw_idx;
+    const R sy1 = now_time - (R)yaw_idx * Ty;
+    const R sy2 = sy1 * sy1, sy3 = sy2 * sy1, sy4 = sy2 * sy2, sy5 = sy4 * sy1;
+    S.y0[0] = 1.0; S.y0[1] = sy1; S.y0[2] = sy2; S.y0[3] = sy3; S.y0[4] = sy4; S.y0[5] = sy5;
+    S.y1[0] = 0.0; S.y1[1] = 1.0; S.y1[2] = 2.0 * sy1; S.y1[3] = 3.0 * sy2; S.y1[4] = 4.0 * sy3; S.y1[5] = 5.0 * sy4;
+    S.y2[0] = 0.0; S.y2[1] = 0.0; S.y2[2] = 2.0; S.y2[3] = 6.0 * sy1; S.y2[4] = 12.0 * sy2; S.y2[5] = 20.0 * sy3;
+    R yaw = 0, dyaw = 0, d2yaw = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const R c = t.cyaw[6 * yaw_idx + k];
+        yaw += c * S.y0[k]; dyaw += c * S.y1[k]; d2yaw += c * S.y2[k];
+    }
+    S.yaw = yaw; S.dyaw = dyaw; S.d2yaw = d2yaw;
+    R se2[3] = {S.pos[0], S.pos[1], yaw};
+    normSO2(se2[2]);
+    ualm_sincos(yaw, &S.syaw, &S.cyaw);
+    S.v_norm = sqrt(S.vel[0] * S.vel[0] + S.vel[1] * S.vel[1]);
+    S.lon_acc = S.acc[0] * S.cyaw + S.acc[1] * S.syaw;
+    S.lat_acc = S.acc[0] * (-S.syaw) + S.acc[1] * S.cyaw;
+    map_get_all_with_grad(map, se2, S.tv, S.tg);
+    S.vx = S.v_norm * S.tv[0];
+    S.wz = dyaw * S.tv[5];
+    S.ax = S.lon_acc * S.tv[0] + gravity * S.tv[1];
+    S.ay = S.lat_acc * S.tv[2] + gravity * S.tv[3];
+    S.curv_snorm = S.wz * S.wz / (S.vx * S.vx + UALM_DELTA_SIGL);
+}
+
+// sample-time tables: s1tab[j] = j-fold accumulated step, base[i] = i-fold accumulated T (alm_traj_opt.cpp:713-714, 987-989)
+__device__ void sample_tables(Traj &t, int tid)
+{
+    if (tid == 0) {
+        const R step = t.sc[SC_TX1] / (R)t.K;
+        R s1 = 0.0;
+        for (int j = 0; j <= t.K; j++) { t.s1tab[j] = s1; s1 += step; }
+    }
+    if (tid == 32) {
+        R b = 0.0;
+        for (int i = 0; i < t.N; i++) { t.base[i] = b; b += t.sc[SC_TX1]; }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// calConstrainCostGrad, phase A: one thread per sample (alm_traj_opt.cpp:710-964).  Writes hx/gx, the 8 cost
+// terms and the per-sample gradients to the scratch; phase B accumulates them in the reference's order.
+// ---------------------------------------------------------------------------------------------
+__device__ void penalty_samples(Traj &t, const DevMap &map, const DevParams &p, int tid)
+{
+    const int S = t.S, K = t.K;
+    const R rho = t.sc[SC_RHO], scale_fx = t.sc[SC_SCALE_FX];
+    const R step = t.sc[SC_TX1] / (R)K;
+    R *scr = t.scr;
+    for (int s = tid; s < S; s += UALM_THREADS) {
+        const int i = s / (K + 1), j = s - i * (K + 1);
+        SampleK q;
+        sample_kin(t, map, p.gravity, i, t.s1tab[j], t.base[i], q);
+        t.yawidx[s] = (unsigned short)q.yaw_idx;
+        R grad_p[2] = {0, 0}, grad_v[2] = {0, 0}, grad_a[2] = {0, 0}, grad_se2[3] = {0, 0, 0};
+        R grad_yaw = 0, grad_dyaw = 0, grad_vx2 = 0, grad_wz = 0, grad_ax = 0, grad_ay = 0, aug_grad = 0;
+        const R inv_cos_vphix = q.tv[0], inv_cos_vphiy = q.tv[2], cos_xi = q.tv[4], inv_cos_xi = q.tv[5], sigma = q.tv[6];
+        const R vx = q.vx, wz = q.wz, ax = q.ax, ay = q.ay, curv_snorm = q.curv_snorm;
+        const R *sc7 = t.scale_cx + 7 * (size_t)s;
+        const R *mu6 = t.mu + 6 * (size_t)s;
+        R *gx6 = t.gx + 6 * (size_t)s;
+
+        R omega;
+        if (j == 0 || j == K) omega = 0.5 * p.rho_ter * step * scale_fx;
+        else omega = p.rho_ter * step * scale_fx;
+        const R user_cost = omega * sigma * sigma;
+        scr[(SF_COST0 + 0) * S + s] = user_cost;
+        scr[SF_USER * S + s] = user_cost;
+#pragma unroll
+        for (int k = 0; k < 3; k++) grad_se2[k] += omega * q.tg[6][k] * sigma * 2.0;
+
+        { // non-holonomic
+            const R nonh_lambda = t.lambda[s];
+            const R nhy0 = q.syaw, nhy1 = -q.cyaw;
+            const R h = (q.vel[0] * nhy0 + q.vel[1] * nhy1) * sc7[0];
+            t.hx[s] = h;
+            scr[(SF_COST0 + 1) * S + s] = h * (nonh_lambda + 0.5 * rho * h);
+            const R nonh_grad = (rho * h + nonh_lambda) * sc7[0];
+            grad_v[0] += nonh_grad * nhy0; grad_v[1] += nonh_grad * nhy1;
+            grad_yaw += nonh_grad * (q.vel[0] * q.cyaw + q.vel[1] * q.syaw);
+        }
+        { // longitude velocity
+            const R m_ = mu6[0];
+            const R gv = (vx * vx - p.max_vel * p.max_vel) * sc7[1];
+            gx6[0] = gv;
+            if (rho * gv + m_ > 0) {
+                scr[(SF_COST0 + 2) * S + s] = gv * (m_ + 0.5 * rho * gv);
+                aug_grad = (rho * gv + m_) * sc7[1];
+                grad_vx2 += aug_grad;
+            } else scr[(SF_COST0 + 2) * S + s] = -0.5 * m_ * m_ / rho;
+        }
+        { // longitude acceleration
+            const R m_ = mu6[1];
+            const R gv = (ax * ax - p.max_acc_lon * p.max_acc_lon) * sc7[2];
+            gx6[1] = gv;
+            if (rho * gv + m_ > 0) {
+                scr[(SF_COST0 + 3) * S + s] = gv * (m_ + 0.5 * rho * gv);
+                aug_grad = (rho * gv + m_) * sc7[2];
+                grad_ax += aug_grad * 2.0 * ax;
+            } else scr[(SF_COST0 + 3) * S + s] = -0.5 * m_ * m_ / rho;
+        }
+        { // latitude acceleration
+            const R m_ = mu6[2];
+            const R gv = (ay * ay - p.max_acc_lat * p.max_acc_lat) * sc7[3];
+            gx6[2] = gv;
+            if (rho * gv + m_ > 0) {
+                scr[(SF_COST0 + 4) * S + s] = gv * (m_ + 0.5 * rho * gv);
+                aug_grad = (rho * gv + m_) * sc7[3];
+                grad_ay += aug_grad * 2.0 * ay;
+            } else scr[(SF_COST0 + 4) * S + s] = -0.5 * m_ * m_ / rho;
+        }
+        { // curvature
+            const R m_ = mu6[3];
+            R gv;
+            if (p.use_scaling) gv = (curv_snorm - p.max_kap * p.max_kap) * sc7[4];
+            else gv = (curv_snorm - p.max_kap * p.max_kap) * UALM_CUR_SCALE;
+            gx6[3] = gv;
+            if (rho * gv + m_ > 0) {
+                const R denominator = 1.0 / (vx * vx + UALM_DELTA_SIGL);
+                scr[(SF_COST0 + 5) * S + s] = gv * (m_ + 0.5 * rho * gv);
+                if (p.use_scaling) aug_grad = (rho * gv + m_) * sc7[4];
+                else aug_grad = (rho * gv + m_) * UALM_CUR_SCALE;
+                grad_wz += aug_grad * denominator * 2.0 * wz;
+                grad_vx2 -= aug_grad * curv_snorm * denominator;
+            } else scr[(SF_COST0 + 5) * S + s] = -0.5 * m_ * m_ / rho;
+        }
+        { // attitude
+            const R m_ = mu6[4];
+            const R gv = (p.min_cxi - cos_xi) * sc7[5];
+            gx6[4] = gv;
+            if (rho * gv + m_ > 0) {
+                scr[(SF_COST0 + 6) * S + s] = gv * (m_ + 0.5 * rho * gv);
+                const R ag = rho * gv + m_;
+#pragma unroll
+                for (int k = 0; k < 3; k++) grad_se2[k] -= ag * q.tg[4][k] * sc7[5];
+            } else scr[(SF_COST0 + 6) * S + s] = -0.5 * m_ * m_ / rho;
+        }
+        { // surface variation
+            const R m_ = mu6[5];
+            R gv;
+            if (p.use_scaling) gv = (sigma - p.max_sig) * sc7[6];
+            else gv = (sigma - p.max_sig) * UALM_SIG_SCALE;
+            gx6[5] = gv;
+            if (rho * gv + m_ > 0) {
+                scr[(SF_COST0 + 7) * S + s] = gv * (m_ + 0.5 * rho * gv);
+                const R ag = rho * gv + m_;
+                if (p.use_scaling) {
+#pragma unroll
+                    for (int k = 0; k < 3; k++) grad_se2[k] += ag * q.tg[6][k] * sc7[6];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 3; k++) grad_se2[k] += ag * q.tg[6][k] * UALM_SIG_SCALE;
+                }
+            } else scr[(SF_COST0 + 7) * S + s] = -0.5 * m_ * m_ / rho;
+        }
+        // process with vx, wz, ax (alm_traj_opt.cpp:948-964)
+#pragma unroll
+        for (int d = 0; d < 2; d++) grad_v[d] += grad_vx2 * inv_cos_vphix * inv_cos_vphix * 2.0 * q.vel[d];
+#pragma unroll
+        for (int k = 0; k < 3; k++) grad_se2[k] += grad_vx2 * q.v_norm * q.v_norm * 2.0 * inv_cos_vphix * q.tg[0][k];
+        grad_dyaw += grad_wz * inv_cos_xi;
+#pragma unroll
+        for (int k = 0; k < 3; k++) grad_se2[k] += grad_wz * q.dyaw * q.tg[5][k];
+        grad_a[0] += grad_ax * inv_cos_vphix * q.cyaw; grad_a[1] += grad_ax * inv_cos_vphix * q.syaw;
+        grad_yaw += grad_ax * inv_cos_vphix * q.lat_acc;
+#pragma unroll
+        for (int k = 0; k < 3; k++) grad_se2[k] += grad_ax * (p.gravity * q.tg[1][k] + q.tg[0][k] * q.lon_acc);
+        grad_a[0] += grad_ay * inv_cos_vphiy * (-q.syaw); grad_a[1] += grad_ay * inv_cos_vphiy * q.cyaw;
+        grad_yaw -= grad_ay * inv_cos_vphiy * q.lon_acc;
+#pragma unroll
+        for (int k = 0; k < 3; k++) grad_se2[k] += grad_ay * (p.gravity * q.tg[3][k] + q.tg[2][k] * q.lat_acc);
+        grad_p[0] += grad_se2[0]; grad_p[1] += grad_se2[1];
+        grad_yaw += grad_se2[2];
+
+        scr[(SF_GP + 0) * S + s] = grad_p[0]; scr[(SF_GP + 1) * S + s] = grad_p[1];
+        scr[(SF_GV + 0) * S + s] = grad_v[0]; scr[(SF_GV + 1) * S + s] = grad_v[1];
+        scr[(SF_GA + 0) * S + s] = grad_a[0]; scr[(SF_GA + 1) * S + s] = grad_a[1];
+        scr[SF_GYAW * S + s] = grad_yaw; scr[SF_GDYAW * S + s] = grad_dyaw;
+        scr[(SF_VEL + 0) * S + s] = q.vel[0]; scr[(SF_VEL + 1) * S + s] = q.vel[1];
+        scr[(SF_ACC + 0) * S + s] = q.acc[0]; scr[(SF_ACC + 1) * S + s] = q.acc[1];
+        scr[(SF_JER + 0) * S + s] = q.jer[0]; scr[(SF_JER + 1) * S + s] = q.jer[1];
+        scr[SF_DYAW * S + s] = q.dyaw; scr[SF_D2YAW * S + s] = q.d2yaw;
+        scr[SF_S1YAW * S + s] = q.y0[1];
+    }
+    __syncthreads();
+}
+
+// phase B: accumulate in the reference's order (alm_traj_opt.cpp:825-946 cost; :969-985 gradients).
+// warp 3 lane 0 runs the sequential cost chain while the other threads do the per-entry gradient sums.
+__device__ void penalty_accumulate(Traj &t, int tid)
+{
+    const int N = t.N, M = t.M, S = t.S, K = t.K, nx = 6 * N;
+    const R *scr = t.scr;
+    if (tid == UALM_THREADS - 32) {
+        R cost = 0.0;
+        for (int s = 0; s < S; s++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) cost += scr[(SF_COST0 + k) * S + s];
+        }
+        t.sc[SC_CONSTR] = cost;
+    } else if (tid < UALM_THREADS - 32) {
+        const int nt = UALM_THREADS - 32;
+        // gdCxy: one thread per (piece, dim): 6 accumulators
+        for (int q = tid; q < 2 * N + N + M; q += nt) {
+            if (q < 2 * N) {
+                const int i = q >> 1, d = q & 1;
+                R acc[6] = {0, 0, 0, 0, 0, 0};
+                for (int j = 0; j <= K; j++) {
+                    const int s = i * (K + 1) + j;
+                    const R s1 = t.s1tab[j];
+                    const R s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
+                    const R gp = scr[(SF_GP + d) * S + s], gv = scr[(SF_GV + d) * S + s], ga = scr[(SF_GA + d) * S + s];
+                    acc[0] += (1.0 * gp + 0.0 * gv + 0.0 * ga);
+                    acc[1] += (s1 * gp + 1.0 * gv + 0.0 * ga);
+                    acc[2] += (s2 * gp + (2.0 * s1) * gv + 2.0 * ga);
+                    acc[3] += (s3 * gp + (3.0 * s2) * gv + (6.0 * s1) * ga);
+                    acc[4] += (s4 * gp + (4.0 * s3) * gv + (12.0 * s2) * ga);
+                    acc[5] += (s5 * gp + (5.0 * s4) * gv + (20.0 * s3) * ga);
+                }
+#pragma unroll
+                for (int k = 0; k < 6; k++) t.gCxy[6 * i + k + d * nx] = acc[k];
+            } else if (q < 3 * N) {
+                // gdTxy(i): three += per sample (alm_traj_opt.cpp:827, 973-975, 984-985)
+                const int i = q - 2 * N;
+                R acc = 0.0;
+                for (int j = 0; j <= K; j++) {
+                    const int s = i * (K + 1) + j;
+                    const R alpha = 1.0 / (R)K * (R)j;
+                    acc += scr[SF_USER * S + s] / (R)K;
+                    const R gp0 = scr[(SF_GP + 0) * S + s], gp1 = scr[(SF_GP + 1) * S + s];
+                    const R gv0 = scr[(SF_GV + 0) * S + s], gv1 = scr[(SF_GV + 1) * S + s];
+                    const R ga0 = scr[(SF_GA + 0) * S + s], ga1 = scr[(SF_GA + 1) * S + s];
+                    const R ve0 = scr[(SF_VEL + 0) * S + s], ve1 = scr[(SF_VEL + 1) * S + s];
+                    const R ac0 = scr[(SF_ACC + 0) * S + s], ac1 = scr[(SF_ACC + 1) * S + s];
+                    const R je0 = scr[(SF_JER + 0) * S + s], je1 = scr[(SF_JER + 1) * S + s];
+                    acc += ((gp0 * ve0 + gp1 * ve1) + (gv0 * ac0 + gv1 * ac1) + (ga0 * je0 + ga1 * je1)) * alpha;
+                    const R gy = scr[SF_GYAW * S + s], gdy = scr[SF_GDYAW * S + s];
+                    acc += (gy * scr[SF_DYAW * S + s] + gdy * scr[SF_D2YAW * S + s]) * (alpha + (R)i);
+                }
+                t.gTxy[i] = acc;
+            } else {
+                // gdCyaw block m and gdTyaw(m): samples with yaw_idx == m in ascending sample order
+                const int m = q - 3 * N;
+                R acc[6] = {0, 0, 0, 0, 0, 0};
+                R accT = 0.0;
+                for (int s = 0; s < S; s++) {
+                    if (t.yawidx[s] != m) continue;
+                    const R sy1 = scr[SF_S1YAW * S + s];
+                    const R sy2 = sy1 * sy1, sy3 = sy2 * sy1, sy4 = sy2 * sy2, sy5 = sy4 * sy1;
+                    const R gy = scr[SF_GYAW * S + s], gdy = scr[SF_GDYAW * S + s];
+                    const R gd2 = 0.0;
+                    acc[0] += (1.0 * gy + 0.0 * gdy + 0.0 * gd2);
+                    acc[1] += (sy1 * gy + 1.0 * gdy + 0.0 * gd2);
+                    acc[2] += (sy2 * gy + (2.0 * sy1) * gdy + 2.0 * gd2);
+                    acc[3] += (sy3 * gy + (3.0 * sy2) * gdy + (6.0 * sy1) * gd2);
+                    acc[4] += (sy4 * gy + (4.0 * sy3) * gdy + (12.0 * sy2) * gd2);
+                    acc[5] += (sy5 * gy + (5.0 * sy4) * gdy + (20.0 * sy3) * gd2);
+                    accT += -(gy * scr[SF_DYAW * S + s] + gdy * scr[SF_D2YAW * S + s]) * (R)m;
+                }
+#pragma unroll
+                for (int k = 0; k < 6; k++) t.gCyaw[6 * m + k] = acc[k];
+                t.gTyaw[m] = accT;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// gdT(i) += B1 . adj  (se2traj.hpp:763-814); adj = solved adjoint vector (element stride st), Dim columns
+__device__ R adj_time_term(const R *c, int cst /*col stride of c*/, const R *adj, int ast /*col stride*/, int st, int Dim,
+                           int i, int P, R T1, R T2, R T3, R T4)
+{
+    R s = 0.0;
+    if (i < P - 1) {
+        for (int d = 0; d < Dim; d++) {
+            const R *cc = c + d * cst + 6 * i;
+            const R nv = -(cc[1] + 2.0 * T1 * cc[2] + 3.0 * T2 * cc[3] + 4.0 * T3 * cc[4] + 5.0 * T4 * cc[5]);
+            const R na = -(2.0 * cc[2] + 6.0 * T1 * cc[3] + 12.0 * T2 * cc[4] + 20.0 * T3 * cc[5]);
+            const R nj = -(6.0 * cc[3] + 24.0 * T1 * cc[4] + 60.0 * T2 * cc[5]);
+            const R ns = -(24.0 * cc[4] + 120.0 * T1 * cc[5]);
+            const R nc = -120.0 * cc[5];
+            const R B1[6] = {ns, nc, nv, nv, na, nj};
+            const R *a = adj + (size_t)d * ast;
+            for (int r = 0; r < 6; r++) s += B1[r] * a[(size_t)(6 * i + 3 + r) * st];
+        }
+    } else {
+        for (int d = 0; d < Dim; d++) {
+            const R *cc = c + d * cst + 6 * (P - 1);
+            const R nv = -(cc[1] + 2.0 * T1 * cc[2] + 3.0 * T2 * cc[3] + 4.0 * T3 * cc[4] + 5.0 * T4 * cc[5]);
+            const R na = -(2.0 * cc[2] + 6.0 * T1 * cc[3] + 12.0 * T2 * cc[4] + 20.0 * T3 * cc[5]);
+            const R nj = -(6.0 * cc[3] + 24.0 * T1 * cc[4] + 60.0 * T2 * cc[5]);
+            const R B2[3] = {nv, na, nj};
+            const R *a = adj + (size_t)d * ast;
+            for (int r = 0; r < 3; r++) s += B2[r] * a[(size_t)(6 * P - 3 + r) * st];
+        }
+    }
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// innerCallback (alm_traj_opt.cpp:280-347): x (smem t.x) -> f (sc[SC_F]) and g (smem t.g)
+// ---------------------------------------------------------------------------------------------
+__device__ void evaluate(Traj &t, const DevMap &map, const DevParams &p, int tid)
+{
+    const int N = t.N, M = t.M, nx = 6 * N, ny = 6 * M;
+    t.n_evals++;
+    minco_generate(t, tid);
+    jerk_cost_grad(t, tid);
+    sample_tables(t, tid);
+    penalty_samples(t, map, p, tid);
+    penalty_accumulate(t, tid);
+    // combine jerk and constraint gradients (alm_traj_opt.cpp:322-332)
+    const R scale_fx = t.sc[SC_SCALE_FX];
+    for (int q = tid; q < 2 * nx; q += UALM_THREADS) {
+        R gj = t.gCxy_j[q];
+        if (p.use_scaling) gj *= UALM_SCALE_TRICK_JERK;
+        t.gCxy[q] = gj * scale_fx + t.gCxy[q];
+    }
+    for (int q = tid; q < ny; q += UALM_THREADS) {
+        R gj = t.gCyaw_j[q];
+        if (p.use_scaling) gj *= UALM_SCALE_TRICK_JERK;
+        t.gCyaw[q] = gj * scale_fx + t.gCyaw[q];
+    }
+    for (int q = tid; q < N; q += UALM_THREADS) {
+        R gj = t.gTxy_j[q];
+        if (p.use_scaling) gj *= UALM_SCALE_TRICK_JERK;
+        t.gTxy[q] = gj * scale_fx + t.gTxy[q];
+    }
+    for (int q = tid; q < M; q += UALM_THREADS) {
+        R gj = t.gTyaw_j[q];
+        if (p.use_scaling) gj *= UALM_SCALE_TRICK_JERK;
+        t.gTyaw[q] = gj * scale_fx + t.gTyaw[q];
+    }
+    __syncthreads();
+    // calGradCTtoQT (se2traj.hpp:751-816): adjoint solves in place in gCxy / gCyaw
+    if (tid == 0) banded_solve_adj_col(t.Axy, nx, t.gCxy, 1);
+    else if (tid == 32) banded_solve_adj_col(t.Axy, nx, t.gCxy + nx, 1);
+    else if (tid == 64) banded_solve_adj_col(t.Ayaw, ny, t.gCyaw, 1);
+    __syncthreads();
+    for (int q = tid; q < N + M; q += UALM_THREADS) {
+        if (q < N) t.gTxy[q] += adj_time_term(t.cxy, nx, t.gCxy, nx, 1, 2, q, N, t.sc[SC_TX1], t.sc[SC_TX2], t.sc[SC_TX3], t.sc[SC_TX4]);
+        else t.gTyaw[q - N] += adj_time_term(t.cyaw, ny, t.gCyaw, ny, 1, 1, q - N, M, t.sc[SC_TY1], t.sc[SC_TY2], t.sc[SC_TY3], t.sc[SC_TY4]);
+    }
+    for (int i = tid; i < N - 1; i += UALM_THREADS) {
+        t.g[1 + 2 * i] = t.gCxy[6 * i + 5];
+        t.g[1 + 2 * i + 1] = t.gCxy[6 * i + 5 + nx];
+    }
+    for (int i = tid; i < M - 1; i += UALM_THREADS) t.g[1 + 2 * (N - 1) + i] = t.gCyaw[6 * i + 5];
+    __syncthreads();
+    if (tid == 0) {
+        const R tau = t.x[0];
+        R jerk_cost = t.sc[SC_JERKRAW] * scale_fx;
+        if (p.use_scaling) jerk_cost *= UALM_SCALE_TRICK_JERK;
+        const R tau_cost = p.rho_T * expC2(tau) * scale_fx;
+        R sx = 0.0, sy = 0.0;
+        for (int i = 0; i < N; i++) sx += t.gTxy[i];
+        for (int i = 0; i < M; i++) sy += t.gTyaw[i];
+        const R grad_Tsum = p.rho_T * scale_fx + sx / (R)N + sy / (R)M;
+        t.g[0] = grad_Tsum * getTtoTauGrad(tau);
+        t.sc[SC_JERK] = jerk_cost; t.sc[SC_TAUCOST] = tau_cost;
+        t.sc[SC_F] = jerk_cost + t.sc[SC_CONSTR] + tau_cost;
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// canonical 32-lane dot product (warp 0 only); result on every lane of the calling warp
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ R lane_dot(const R *a, const R *b, int n, int lane)
+{
+    R pacc = 0.0;
+    for (int i = lane; i < n; i += 32) pacc += a[i] * b[i];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) pacc = pacc + __shfl_xor_sync(0xffffffffu, pacc, off);
+    return pacc;
+}
+__device__ __forceinline__ R lane_absmax(const R *a, int n, int lane)
+{
+    R m = 0.0;
+    for (int i = lane; i < n; i += 32) m = fmax(m, fabs(a[i]));
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+    return m;
+}
+
+struct LbfgsOut { int ret; R f; int iters; int max_bound; };
+
+// lbfgs_optimize + line_search_lewisoverton (lbfgs.hpp:276-389, 439-722).  Control flow is uniform over the
+// CTA: every decision is computed identically by all lanes of warp 0 and broadcast through shared memory.
+__device__ LbfgsOut lbfgs_optimize(Traj &t, const DevMap &map, const DevParams &p, int tid, int *s_flag)
+{
+    const int n = t.n, m = p.mem_size, lane = tid & 31, warp = tid >> 5;
+    const R f_dec_coeff = 1.0e-4, s_curv_coeff = 0.9, cautious_factor = 1.0e-6, machine_prec = 1.0e-16;
+    const R max_step = 1.0e+20, min_step = p.min_step;
+    const int max_linesearch = 64;
+    LbfgsOut out; out.ret = 0; out.iters = 0; out.max_bound = 0;
+
+    for (int q = tid; q < m; q += UALM_THREADS) { t.lm_alpha[q] = 0.0; t.lm_ys[q] = 0.0; }
+    evaluate(t, map, p, tid);
+    R fx = t.sc[SC_F];
+    if (tid == 0) t.pf[0] = fx;
+    for (int q = tid; q < n; q += UALM_THREADS) t.d[q] = -t.g[q];
+    __syncthreads();
+    if (warp == 0) {
+        const R gn = lane_absmax(t.g, n, lane), xn = lane_absmax(t.x, n, lane);
+        const R dn = lane_dot(t.d, t.d, n, lane);
+        if (lane == 0) {
+            s_flag[0] = (gn / fmax(1.0, xn) < p.g_epsilon) ? 1 : 0;
+            t.sc[SC_STEP] = 1.0 / sqrt(dn);
+        }
+    }
+    __syncthreads();
+    if (s_flag[0]) { out.ret = LBFGS_CONVERGENCE; out.f = fx; return out; }
+    R step = t.sc[SC_STEP];
+    int k = 1, end = 0, bound = 0, ret = 0;
+    while (true) {
+        for (int q = tid; q < n; q += UALM_THREADS) { t.xp[q] = t.x[q]; t.gp[q] = t.g[q]; }
+        __syncthreads();
+        // ---- line search (lbfgs.hpp:276-389) ----
+        int ls;
+        {
+            int count = 0;
+            bool brackt = false, touched = false;
+            R stp = step, mu = 0.0, nu = max_step;
+            if (warp == 0) {
+                const R dg = lane_dot(t.gp, t.d, n, lane);
+                if (lane == 0) t.sc[SC_DGINIT] = dg;
+            }
+            __syncthreads();
+            const R dginit = t.sc[SC_DGINIT];
+            const R finit = fx;
+            if (!(stp > 0.0)) ls = LBFGSERR_INVALIDPARAMETERS;
+            else if (0.0 < dginit) ls = LBFGSERR_INCREASEGRADIENT;
+            else {
+                const R dgtest = f_dec_coeff * dginit, dstest = s_curv_coeff * dginit;
+                while (true) {
+                    for (int q = tid; q < n; q += UALM_THREADS) t.x[q] = t.xp[q] + stp * t.d[q];
+                    __syncthreads();
+                    evaluate(t, map, p, tid);
+                    fx = t.sc[SC_F];
+                    ++count;
+                    if (isinf(fx) || isnan(fx)) { ls = LBFGSERR_INVALID_FUNCVAL; break; }
+                    if (p.past > 0 && fabs(finit - fx) / (fabs(finit) + 1.0) < p.delta / (R)p.past) { ls = count; break; }
+                    if (fx > finit + stp * dgtest) {
+                        nu = stp;
+                        brackt = true;
+                    } else {
+                        if (warp == 0) {
+                            const R dg = lane_dot(t.g, t.d, n, lane);
+                            if (lane == 0) t.sc[SC_TMP0] = dg;
+                        }
+                        __syncthreads();
+                        const R dg = t.sc[SC_TMP0];
+                        __syncthreads();
+                        if (dg < dstest) mu = stp;
+                        else { ls = count; break; }
+                    }
+                    if (max_linesearch <= count) { ls = LBFGSERR_MAXIMUMLINESEARCH; break; }
+                    if (brackt && (nu - mu) < machine_prec * nu) { ls = LBFGSERR_WIDTHTOOSMALL; break; }
+                    if (brackt) stp = 0.5 * (mu + nu);
+                    else stp *= 2.0;
+                    if (stp < min_step) { ls = LBFGSERR_MINIMUMSTEP; break; }
+                    if (stp > max_step) {
+                        if (touched) { ls = LBFGSERR_MAXIMUMSTEP; break; }
+                        touched = true;
+                        stp = max_step;
+                    }
+                }
+            }
+            step = stp;
+        }
+        if (ls < 0) {
+            for (int q = tid; q < n; q += UALM_THREADS) { t.x[q] = t.xp[q]; t.g[q] = t.gp[q]; }
+            __syncthreads();
+            ret = ls;
+            break;
+        }
+        out.iters++;
+        if (k > 1000) { ret = LBFGS_CANCELED; break; } // earlyExit alm_traj_opt.cpp:1016 (k > 1e3)
+        if (warp == 0) {
+            const R gn = lane_absmax(t.g, n, lane), xn = lane_absmax(t.x, n, lane);
+            if (lane == 0) s_flag[0] = (gn / fmax(1.0, xn) < p.g_epsilon) ? 1 : 0;
+        }
+        __syncthreads();
+        const int conv = s_flag[0];
+        __syncthreads();
+        if (conv) { ret = LBFGS_CONVERGENCE; break; }
+        if (0 < p.past) {
+            if (p.past <= k) {
+                const R rate = fabs(t.pf[k % p.past] - fx) / fmax(1.0, fabs(fx));
+                if (rate < p.delta) { ret = LBFGS_STOP; break; }
+            }
+            __syncthreads();
+            if (tid == 0) t.pf[k % p.past] = fx;
+            __syncthreads();
+        }
+        if (p.inner_max_iter != 0 && p.inner_max_iter <= k) { ret = LBFGSERR_MAXIMUMITERATION; break; }
+        ++k;
+        R *sE = t.lm_s + (size_t)end * n, *yE = t.lm_y + (size_t)end * n;
+        for (int q = tid; q < n; q += UALM_THREADS) {
+            sE[q] = t.x[q] - t.xp[q];
+            yE[q] = t.g[q] - t.gp[q];
+            t.d[q] = -t.g[q];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const R ys = lane_dot(yE, sE, n, lane);
+            const R yy = lane_dot(yE, yE, n, lane);
+            const R ss = lane_dot(sE, sE, n, lane);
+            const R gpn = lane_dot(t.gp, t.gp, n, lane);
+            const R cau = ss * sqrt(gpn) * cautious_factor;
+            if (lane == 0) {
+                t.lm_ys[end] = ys;
+                t.sc[SC_YS] = ys; t.sc[SC_YY] = yy;
+                s_flag[0] = (ys > cau) ? 1 : 0;
+            }
+        }
+        __syncthreads();
+        const int upd = s_flag[0];
+        if (upd) {
+            ++bound;
+            bound = m < bound ? m : bound;
+            if (bound > out.max_bound) out.max_bound = bound;
+            end = (end + 1) % m;
+            if (warp == 0) { // two-loop recursion (lbfgs.hpp:691-710) on warp 0; d lives in shared memory
+                const R ys = t.sc[SC_YS], yy = t.sc[SC_YY];
+                int j = end;
+                for (int i = 0; i < bound; ++i) {
+                    j = (j + m - 1) % m;
+                    const R *sj = t.lm_s + (size_t)j * n, *yj = t.lm_y + (size_t)j * n;
+                    const R a = lane_dot(sj, t.d, n, lane) / t.lm_ys[j];
+                    if (lane == 0) t.lm_alpha[j] = a;
+                    const R na = -a;
+                    for (int q = lane; q < n; q += 32) t.d[q] = t.d[q] + na * yj[q];
+                    __syncwarp();
+                }
+                const R scl = ys / yy;
+                for (int q = lane; q < n; q += 32) t.d[q] = t.d[q] * scl;
+                __syncwarp();
+                for (int i = 0; i < bound; ++i) {
+                    const R *sj = t.lm_s + (size_t)j * n, *yj = t.lm_y + (size_t)j * n;
+                    const R beta = lane_dot(yj, t.d, n, lane) / t.lm_ys[j];
+                    const R cf = t.lm_alpha[j] - beta;
+                    for (int q = lane; q < n; q += 32) t.d[q] = t.d[q] + cf * sj[q];
+                    __syncwarp();
+                    j = (j + 1) % m;
+                }
+            }
+        }
+        __syncthreads();
+        step = 1.0;
+    }
+    out.ret = ret;
+    out.f = fx;
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// initScaling (alm_traj_opt.cpp:349-661): one task per constraint, each task runs the reference's adjoint
+// solves on its own (interleaved) workspace column.  Requires c / LU at x0 (calls minco_generate).
+// ---------------------------------------------------------------------------------------------
+__device__ void init_scaling(Traj &t, const DevMap &map, const DevParams &p, int tid, R *ws /* per CTA */)
+{
+    const int N = t.N, M = t.M, S = t.S, K = t.K, nx = 6 * N, ny = 6 * M;
+    minco_generate(t, tid);
+    jerk_cost_grad(t, tid); // gdC*_j, gdT*_j = jerk gradient (alm_traj_opt.cpp:370)
+    sample_tables(t, tid);
+    const R tau = t.x[0];
+    const R dTdtau = getTtoTauGrad(tau);
+    const R step = t.sc[SC_TX1] / (R)K;
+    const R Tx1 = t.sc[SC_TX1], Tx2 = t.sc[SC_TX2], Tx3 = t.sc[SC_TX3], Tx4 = t.sc[SC_TX4];
+    const R Ty1 = t.sc[SC_TY1], Ty2 = t.sc[SC_TY2], Ty3 = t.sc[SC_TY3], Ty4 = t.sc[SC_TY4];
+    const int st = UALM_THREADS;
+    R *wx = ws + tid;                       // x column: rows 0..nx-1 at stride st
+    R *wy = ws + (size_t)nx * st + tid;     // y column
+    R *ww = ws + (size_t)2 * nx * st + tid; // yaw
+    R *scr = t.scr;
+    // ---- per-sample pass: f-gradient contributions to the scratch, and the 7 constraint tasks ----
+    for (int s0 = 0; s0 < S; s0 += UALM_THREADS) {
+        const int s = s0 + tid;
+        const bool act = s < S;
+        SampleK q;
+        int i = 0, j = 0;
+        R alpha = 0.0;
+        if (act) {
+            i = s / (K + 1); j = s - i * (K + 1);
+            alpha = 1.0 / (R)K * (R)j;
+            sample_kin(t, map, p.gravity, i, t.s1tab[j], t.base[i], q);
+            t.yawidx[s] = (unsigned short)q.yaw_idx;
+            // user-defined cost -> f gradient pieces (alm_traj_opt.cpp:507-519): stored like a penalty sample
+            const R omega = (j == 0 || j == K) ? 0.5 * p.rho_ter * step : p.rho_ter * step;
+            const R sigma = q.tv[6];
+            const R user_cost = omega * sigma * sigma;
+            R gs[3];
+            for (int k = 0; k < 3; k++) gs[k] = omega * q.tg[6][k] * sigma * 2.0;
+            scr[SF_USER * S + s] = user_cost;
+            scr[(SF_GP + 0) * S + s] = gs[0]; scr[(SF_GP + 1) * S + s] = gs[1];
+            scr[SF_GYAW * S + s] = gs[2];
+            scr[(SF_VEL + 0) * S + s] = q.vel[0]; scr[(SF_VEL + 1) * S + s] = q.vel[1];
+            scr[SF_DYAW * S + s] = q.dyaw;
+            scr[SF_S1YAW * S + s] = q.y0[1];
+        }
+        for (int ct = 0; ct < 7; ct++) {
+            R m1 = 0.0, m2 = 0.0, gdTau = 0.0;
+            if (act) {
+                R grad_p[2] = {0, 0}, grad_v[2] = {0, 0}, grad_a[2] = {0, 0}, grad_se2[3];
+                R grad_yaw = 0.0, grad_dyaw = 0.0;
+                int usep = 0, usev = 0, usea = 0, usedy = 0;
+                const R inv_cos_vphix = q.tv[0], inv_cos_vphiy = q.tv[2], inv_cos_xi = q.tv[5];
+                if (ct == 0) { // non-holonomic (521-529)
+                    grad_v[0] = q.syaw; grad_v[1] = -q.cyaw;
+                    grad_yaw = q.vel[0] * q.cyaw + q.vel[1] * q.syaw;
+                    usev = 1;
+                } else if (ct == 1) { // longitude velocity (531-544)
+                    const R grad_vx2 = 1.0;
+                    for (int d = 0; d < 2; d++) grad_v[d] = grad_vx2 * inv_cos_vphix * inv_cos_vphix * 2.0 * q.vel[d];
+                    for (int k = 0; k < 3; k++) grad_se2[k] = grad_vx2 * q.v_norm * q.v_norm * 2.0 * inv_cos_vphix * q.tg[0][k];
+                    grad_p[0] = grad_se2[0]; grad_p[1] = grad_se2[1]; grad_yaw = grad_se2[2];
+                    usep = 1; usev = 1;
+                } else if (ct == 2) { // longitude acceleration (546-560)
+                    const R grad_ax = 2.0 * q.ax;
+                    grad_a[0] = grad_ax * inv_cos_vphix * q.cyaw; grad_a[1] = grad_ax * inv_cos_vphix * q.syaw;
+                    grad_yaw = grad_ax * inv_cos_vphix * q.lat_acc;
+                    for (int k = 0; k < 3; k++) grad_se2[k] = grad_ax * (p.gravity * q.tg[1][k] + q.tg[0][k] * q.lon_acc);
+                    grad_p[0] = grad_se2[0]; grad_p[1] = grad_se2[1]; grad_yaw += grad_se2[2];
+                    usep = 1; usea = 1;
+                } else if (ct == 3) { // latitude acceleration (562-576)
+                    const R grad_ay = 2.0 * q.ay;
+                    grad_a[0] = grad_ay * inv_cos_vphiy * (-q.syaw); grad_a[1] = grad_ay * inv_cos_vphiy * q.cyaw;
+                    grad_yaw = -grad_ay * inv_cos_vphiy * q.lon_acc;
+                    for (int k = 0; k < 3; k++) grad_se2[k] = grad_ay * (p.gravity * q.tg[3][k] + q.tg[2][k] * q.lat_acc);
+                    grad_p[0] = grad_se2[0]; grad_p[1] = grad_se2[1]; grad_yaw += grad_se2[2];
+                    usep = 1; usea = 1;
+                } else if (ct == 4) { // curvature (578-598)
+                    const R denominator = 1.0 / (q.vx * q.vx + UALM_DELTA_SIGL);
+                    const R grad_wz = denominator * 2.0 * q.wz;
+                    const R grad_vx2 = -q.curv_snorm * denominator;
+                    grad_dyaw = grad_wz * inv_cos_xi;
+                    for (int k = 0; k < 3; k++) grad_se2[k] = grad_wz * q.dyaw * q.tg[5][k];
+                    for (int d = 0; d < 2; d++) grad_v[d] = grad_vx2 * inv_cos_vphix * inv_cos_vphix * 2.0 * q.vel[d];
+                    for (int k = 0; k < 3; k++) grad_se2[k] += grad_vx2 * q.v_norm * q.v_norm * 2.0 * inv_cos_vphix * q.tg[0][k];
+                    grad_p[0] = grad_se2[0]; grad_p[1] = grad_se2[1]; grad_yaw = grad_se2[2];
+                    usep = 1; usev = 1; usedy = 1;
+                } else if (ct == 5) { // attitude (600-609)
+                    for (int k = 0; k < 3; k++) grad_se2[k] = -q.tg[4][k];
+                    grad_p[0] = grad_se2[0]; grad_p[1] = grad_se2[1]; grad_yaw = grad_se2[2];
+                    usep = 1;
+                } else { // surface variation (611-620)
+                    for (int k = 0; k < 3; k++) grad_se2[k] = q.tg[6][k];
+                    grad_p[0] = grad_se2[0]; grad_p[1] = grad_se2[1]; grad_yaw = grad_se2[2];
+                    usep = 1;
+                }
+                // build this constraint's gdC (only block i / block yaw_idx are non-zero)
+                for (int r = 0; r < nx; r++) { wx[(size_t)r * st] = 0.0; wy[(size_t)r * st] = 0.0; }
+                for (int r = 0; r < ny; r++) ww[(size_t)r * st] = 0.0;
+                for (int k = 0; k < 6; k++) {
+                    R vx_, vy_;
+                    if (usep && usev) { vx_ = (q.b0[k] * grad_p[0] + q.b1[k] * grad_v[0]); vy_ = (q.b0[k] * grad_p[1] + q.b1[k] * grad_v[1]); }
+                    else if (usep && usea) { vx_ = (q.b0[k] * grad_p[0] + q.b2[k] * grad_a[0]); vy_ = (q.b0[k] * grad_p[1] + q.b2[k] * grad_a[1]); }
+                    else if (usep) { vx_ = (q.b0[k] * grad_p[0]); vy_ = (q.b0[k] * grad_p[1]); }
+                    else { vx_ = q.b1[k] * grad_v[0]; vy_ = q.b1[k] * grad_v[1]; }
+                    wx[(size_t)(6 * i + k) * st] = 0.0 + vx_;
+                    wy[(size_t)(6 * i + k) * st] = 0.0 + vy_;
+                    R vw;
+                    if (usedy) vw = (q.y0[k] * grad_yaw + q.y1[k] * grad_dyaw);
+                    else vw = q.y0[k] * grad_yaw;
+                    ww[(size_t)(6 * q.yaw_idx + k) * st] = 0.0 + vw;
+                }
+                // direct time-gradient terms of this constraint
+                R dTx = 0.0, dTy = 0.0;
+                if (usep && usev) dTx += ((grad_p[0] * q.vel[0] + grad_p[1] * q.vel[1]) + (grad_v[0] * q.acc[0] + grad_v[1] * q.acc[1])) * alpha;
+                else if (usep && usea) dTx += ((grad_p[0] * q.vel[0] + grad_p[1] * q.vel[1]) + (grad_a[0] * q.jer[0] + grad_a[1] * q.jer[1])) * alpha;
+                else if (usep) dTx += (grad_p[0] * q.vel[0] + grad_p[1] * q.vel[1]) * alpha;
+                else dTx += (grad_v[0] * q.acc[0] + grad_v[1] * q.acc[1]) * alpha;
+                if (usedy) {
+                    dTy += -(grad_yaw * q.dyaw + grad_dyaw * q.d2yaw) * (R)q.yaw_idx;
+                    dTx += (grad_yaw * q.dyaw + grad_dyaw * q.d2yaw) * (alpha + (R)i);
+                } else {
+                    dTy += -(grad_yaw * q.dyaw) * (R)q.yaw_idx;
+                    dTx += (grad_yaw * q.dyaw) * (alpha + (R)i);
+                }
+                // adjoint solves (calGradCTtoQT, se2traj.hpp:751-816)
+                banded_solve_adj_col(t.Axy, nx, wx, st);
+                banded_solve_adj_col(t.Axy, nx, wy, st);
+                banded_solve_adj_col(t.Ayaw, ny, ww, st);
+                for (int r = 0; r < N - 1; r++) {
+                    m1 = fmax(m1, fabs(wx[(size_t)(6 * r + 5) * st]));
+                    m1 = fmax(m1, fabs(wy[(size_t)(6 * r + 5) * st]));
+                }
+                for (int r = 0; r < M - 1; r++) m2 = fmax(m2, fabs(ww[(size_t)(6 * r + 5) * st]));
+                R sx = 0.0, sy = 0.0;
+                for (int r = 0; r < N; r++) {
+                    R gT = (r == i) ? dTx : 0.0;
+                    gT += adj_time_term(t.cxy, nx, ws + tid, nx * st, st, 2, r, N, Tx1, Tx2, Tx3, Tx4);
+                    sx += gT;
+                }
+                for (int r = 0; r < M; r++) {
+                    R gT = (r == q.yaw_idx) ? dTy : 0.0;
+                    gT += adj_time_term(t.cyaw, ny, ww, 0, st, 1, r, M, Ty1, Ty2, Ty3, Ty4);
+                    sy += gT;
+                }
+                gdTau = (sx / (R)N + sy / (R)M) * dTdtau;
+                t.scale_cx[7 * (size_t)s + ct] = 1.0 / fmax(1.0, fmax(fmax(m1, m2), fabs(gdTau)));
+            }
+        }
+    }
+    __syncthreads();
+    // ---- f gradient: jerk (already in gC*_j / gT*_j) + user cost (alm_traj_opt.cpp:507-519), then adjoint ----
+    {
+        const int nt = UALM_THREADS;
+        for (int qq = tid; qq < 2 * N + N + M; qq += nt) {
+            if (qq < 2 * N) {
+                const int i = qq >> 1, d = qq & 1;
+                R acc[6];
+                for (int k = 0; k < 6; k++) acc[k] = t.gCxy_j[6 * i + k + d * nx];
+                for (int j = 0; j <= K; j++) {
+                    const int s = i * (K + 1) + j;
+                    const R s1 = t.s1tab[j];
+                    const R s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
+                    const R gp = scr[(SF_GP + d) * S + s];
+                    acc[0] += 1.0 * gp; acc[1] += s1 * gp; acc[2] += s2 * gp; acc[3] += s3 * gp; acc[4] += s4 * gp; acc[5] += s5 * gp;
+                }
+                for (int k = 0; k < 6; k++) t.gCxy[6 * i + k + d * nx] = acc[k];
+            } else if (qq < 3 * N) {
+                const int i = qq - 2 * N;
+                R acc = t.gTxy_j[i];
+                for (int j = 0; j <= K; j++) {
+                    const int s = i * (K + 1) + j;
+                    const R alpha = 1.0 / (R)K * (R)j;
+                    acc += scr[SF_USER * S + s] / (R)K;
+                    acc += (scr[(SF_GP + 0) * S + s] * scr[(SF_VEL + 0) * S + s] + scr[(SF_GP + 1) * S + s] * scr[(SF_VEL + 1) * S + s]) * alpha;
+                    acc += (scr[SF_GYAW * S + s] * scr[SF_DYAW * S + s]) * (alpha + (R)i);
+                }
+                t.gTxy[i] = acc;
+            } else {
+                const int m = qq - 3 * N;
+                R acc[6];
+                for (int k = 0; k < 6; k++) acc[k] = t.gCyaw_j[6 * m + k];
+                R accT = t.gTyaw_j[m];
+                for (int s = 0; s < S; s++) {
+                    if (t.yawidx[s] != m) continue;
+                    const R sy1 = scr[SF_S1YAW * S + s];
+                    const R sy2 = sy1 * sy1, sy3 = sy2 * sy1, sy4 = sy2 * sy2, sy5 = sy4 * sy1;
+                    const R gy = scr[SF_GYAW * S + s];
+                    acc[0] += (1.0 * gy); acc[1] += (sy1 * gy); acc[2] += (sy2 * gy); acc[3] += (sy3 * gy); acc[4] += (sy4 * gy); acc[5] += (sy5 * gy);
+                    accT += -(gy * scr[SF_DYAW * S + s]) * (R)m;
+                }
+                for (int k = 0; k < 6; k++) t.gCyaw[6 * m + k] = acc[k];
+                t.gTyaw[m] = accT;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) banded_solve_adj_col(t.Axy, nx, t.gCxy, 1);
+    else if (tid == 32) banded_solve_adj_col(t.Axy, nx, t.gCxy + nx, 1);
+    else if (tid == 64) banded_solve_adj_col(t.Ayaw, ny, t.gCyaw, 1);
+    __syncthreads();
+    for (int q = tid; q < N + M; q += UALM_THREADS) {
+        if (q < N) t.gTxy[q] += adj_time_term(t.cxy, nx, t.gCxy, nx, 1, 2, q, N, Tx1, Tx2, Tx3, Tx4);
+        else t.gTyaw[q - N] += adj_time_term(t.cyaw, ny, t.gCyaw, ny, 1, 1, q - N, M, Ty1, Ty2, Ty3, Ty4);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        R sx = 0.0, sy = 0.0, m1 = 0.0, m2 = 0.0;
+        for (int i = 0; i < N; i++) sx += t.gTxy[i];
+        for (int i = 0; i < M; i++) sy += t.gTyaw[i];
+        const R grad_Tsum_fx = p.rho_T + sx / (R)N + sy / (R)M;
+        const R gdTau_fx = grad_Tsum_fx * dTdtau;
+        for (int i = 0; i < N - 1; i++) { m1 = fmax(m1, fabs(t.gCxy[6 * i + 5])); m1 = fmax(m1, fabs(t.gCxy[6 * i + 5 + nx])); }
+        for (int i = 0; i < M - 1; i++) m2 = fmax(m2, fabs(t.gCyaw[6 * i + 5]));
+        t.sc[SC_SCALE_FX] = 1.0 / fmax(1.0, fmax(fmax(m1, m2), fabs(gdTau_fx)));
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// set up the Traj view of one problem
+// ---------------------------------------------------------------------------------------------
+__device__ void traj_setup(Traj &t, const BatchPtrs &bp, const DevParams &p, const SmemLayout &L, R *sm, int prob)
+{
+    const ProbDesc *pd = bp.desc + prob;
+    t.pd = pd; t.N = pd->N; t.M = pd->M; t.n = pd->n; t.S = pd->S; t.K = p.int_K;
+    t.sm = sm; t.L = L;
+    t.Axy = sm + L.Axy; t.Ayaw = sm + L.Ayaw; t.cxy = sm + L.cxy; t.cyaw = sm + L.cyaw; t.gCxy = sm + L.gCxy; t.gCyaw = sm + L.gCyaw;
+    t.gCxy_j = sm + L.gCxy_j; t.gCyaw_j = sm + L.gCyaw_j; t.gTxy = sm + L.gTxy; t.gTyaw = sm + L.gTyaw; t.gTxy_j = sm + L.gTxy_j;
+    t.gTyaw_j = sm + L.gTyaw_j; t.pcx = sm + L.pcost_xy; t.pcy = sm + L.pcost_yaw;
+    t.x = sm + L.x; t.g = sm + L.g; t.xp = sm + L.xp; t.gp = sm + L.gp; t.d = sm + L.d; t.lm_alpha = sm + L.lm_alpha; t.lm_ys = sm + L.lm_ys;
+    t.pf = sm + L.pf; t.s1tab = sm + L.s1tab; t.base = sm + L.base; t.sc = sm + L.sc;
+    t.yawidx = reinterpret_cast<unsigned short *>(sm + L.yawidx);
+    t.lambda = bp.lambda + pd->off_s; t.hx = bp.hx + pd->off_s;
+    t.mu = bp.mu + 6 * pd->off_s; t.gx = bp.gx + 6 * pd->off_s;
+    t.scale_cx = bp.scale_cx + 7 * pd->off_s;
+    t.lm_s = bp.lm_s ? bp.lm_s + pd->off_hist : nullptr;
+    t.lm_y = bp.lm_y ? bp.lm_y + pd->off_hist : nullptr;
+    t.scr = bp.scratch + pd->off_scr;
+    t.n_evals = 0;
+}
+
+// =============================================================================================
+// kernels
+// =============================================================================================
+
+// full solve: optimizeSE2Traj (alm_traj_opt.cpp:168-278)
+__global__ void __launch_bounds__(UALM_THREADS) solve_kernel(BatchPtrs bp, DevParams p, DevMap map, SmemLayout L)
+{
+    extern __shared__ double sm[];
+    __shared__ int s_flag[4];
+    const int tid = threadIdx.x;
+    const int prob = bp.order[blockIdx.x];
+    Traj t;
+    traj_setup(t, bp, p, L, sm, prob);
+    const int N = t.N, M = t.M, n = t.n, S = t.S;
+    // duals and scales (alm_traj_opt.cpp:193-203)
+    for (int q = tid; q < S; q += UALM_THREADS) { t.lambda[q] = 0.0; t.hx[q] = 0.0; }
+    for (int q = tid; q < 6 * S; q += UALM_THREADS) { t.mu[q] = 0.0; t.gx[q] = 0.0; }
+    for (int q = tid; q < 7 * S; q += UALM_THREADS) t.scale_cx[q] = 1.0;
+    for (int q = tid; q < n; q += UALM_THREADS) t.x[q] = bp.x0[t.pd->off_x + q];
+    if (tid == 0) { t.sc[SC_SCALE_FX] = 1.0; t.sc[SC_RHO] = p.rho; }
+    __syncthreads();
+    if (p.use_scaling) init_scaling(t, map, p, tid, bp.ws_scaling + (size_t)blockIdx.x * bp.ws_stride);
+
+    int ret_code = 0, iter = 0, last = 0, iters_total = 0, max_bound = 0;
+    R inner_cost = 0.0, rh = 0.0, rg = 0.0;
+    while (true) {
+        LbfgsOut lo = lbfgs_optimize(t, map, p, tid, s_flag);
+        inner_cost = lo.f; last = lo.ret; iters_total += lo.iters;
+        if (lo.max_bound > max_bound) max_bound = lo.max_bound;
+        __syncthreads();
+        if (lo.ret == LBFGS_CONVERGENCE || lo.ret == LBFGS_CANCELED || lo.ret == LBFGS_STOP || lo.ret == LBFGSERR_MAXIMUMITERATION) {
+        } else if (lo.ret == LBFGSERR_MAXIMUMLINESEARCH) {
+        } else { ret_code = 1; break; }
+        // updateDualVars (alm_traj_opt.h:132-138) with hx/gx of the LAST evaluation (Q1)
+        const R rho = t.sc[SC_RHO];
+        for (int q = tid; q < S; q += UALM_THREADS) t.lambda[q] += rho * t.hx[q];
+        for (int q = tid; q < 6 * S; q += UALM_THREADS) t.mu[q] = fmax(t.mu[q] + rho * t.gx[q], 0.0);
+        __syncthreads();
+        const R rho_new = fmin((1 + p.gamma) * rho, p.beta);
+        // judgeConvergence (alm_traj_opt.h:140-151): max-norms are order independent
+        R mh = 0.0, mg = 0.0;
+        for (int q = tid; q < S; q += UALM_THREADS) mh = fmax(mh, fabs(t.hx[q]));
+        for (int q = tid; q < 6 * S; q += UALM_THREADS) mg = fmax(mg, fabs(fmax(t.gx[q], -t.mu[q] / rho_new)));
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            mh = fmax(mh, __shfl_xor_sync(0xffffffffu, mh, off));
+            mg = fmax(mg, __shfl_xor_sync(0xffffffffu, mg, off));
+        }
+        __shared__ R s_red[2 * (UALM_THREADS / 32)];
+        if ((tid & 31) == 0) { s_red[2 * (tid >> 5)] = mh; s_red[2 * (tid >> 5) + 1] = mg; }
+        __syncthreads();
+        rh = 0.0; rg = 0.0;
+        for (int w = 0; w < UALM_THREADS / 32; w++) { rh = fmax(rh, s_red[2 * w]); rg = fmax(rg, s_red[2 * w + 1]); }
+        if (tid == 0) t.sc[SC_RHO] = rho_new;
+        __syncthreads();
+        if (fmax(rh, rg) < p.epsilon_con) break;
+        if ((R)(++iter) > p.max_iter) { ret_code = 2; break; }
+    }
+    // outputs: coefficients / decision vector of the LAST evaluation's MINCO state (Q1), result record
+    const int nx = 6 * N, ny = 6 * M;
+    for (int q = tid; q < 2 * nx; q += UALM_THREADS) bp.c_xy[t.pd->off_cxy + q] = t.cxy[q];
+    for (int q = tid; q < ny; q += UALM_THREADS) bp.c_yaw[t.pd->off_cyaw + q] = t.cyaw[q];
+    for (int q = tid; q < n; q += UALM_THREADS) bp.x[t.pd->off_x + q] = t.x[q];
+    if (tid == 0) {
+        ualm_result_t r;
+        r.ret_code = ret_code; r.outer_iters = iter; r.n_evals = t.n_evals; r.n_lbfgs_iters = iters_total; r.last_lbfgs_ret = last;
+        r.max_bound = max_bound; r.inner_cost = inner_cost; r.jerk_cost = t.sc[SC_JERKRAW];
+        R tt = 0.0;
+        for (int i = 0; i < N; i++) tt += t.sc[SC_TX1];
+        r.total_T = tt; r.res_h = rh; r.res_g = rg; r.scale_fx = t.sc[SC_SCALE_FX]; r.rho_final = t.sc[SC_RHO];
+        bp.results[prob] = r;
+    }
+}
+
+// one innerCallback evaluation per problem at caller-provided x / duals (kernel-level parity)
+__global__ void __launch_bounds__(UALM_THREADS) eval_kernel(BatchPtrs bp, DevParams p, DevMap map, SmemLayout L, R rho)
+{
+    extern __shared__ double sm[];
+    const int tid = threadIdx.x;
+    const int prob = bp.order[blockIdx.x];
+    Traj t;
+    traj_setup(t, bp, p, L, sm, prob);
+    for (int q = tid; q < t.n; q += UALM_THREADS) t.x[q] = bp.x0[t.pd->off_x + q];
+    if (tid == 0) { t.sc[SC_SCALE_FX] = bp.scale_fx_io[prob]; t.sc[SC_RHO] = rho; }
+    __syncthreads();
+    evaluate(t, map, p, tid);
+    const int nx = 6 * t.N, ny = 6 * t.M;
+    for (int q = tid; q < t.n; q += UALM_THREADS) bp.grad_out[t.pd->off_x + q] = t.g[q];
+    for (int q = tid; q < 2 * nx; q += UALM_THREADS) bp.c_xy[t.pd->off_cxy + q] = t.cxy[q];
+    for (int q = tid; q < ny; q += UALM_THREADS) bp.c_yaw[t.pd->off_cyaw + q] = t.cyaw[q];
+    if (tid == 0) bp.f_out[prob] = t.sc[SC_F];
+}
+
+// initScaling per problem at x0
+__global__ void __launch_bounds__(UALM_THREADS) scaling_kernel(BatchPtrs bp, DevParams p, DevMap map, SmemLayout L)
+{
+    extern __shared__ double sm[];
+    const int tid = threadIdx.x;
+    const int prob = bp.order[blockIdx.x];
+    Traj t;
+    traj_setup(t, bp, p, L, sm, prob);
+    for (int q = tid; q < t.n; q += UALM_THREADS) t.x[q] = bp.x0[t.pd->off_x + q];
+    if (tid == 0) { t.sc[SC_SCALE_FX] = 1.0; t.sc[SC_RHO] = p.rho; }
+    __syncthreads();
+    init_scaling(t, map, p, tid, bp.ws_scaling + (size_t)blockIdx.x * bp.ws_stride);
+    if (tid == 0) bp.scale_fx_io[prob] = t.sc[SC_SCALE_FX];
+}
+
+// the penalty-sampling phase alone (calConstrainCostGrad samples, alm_traj_opt.cpp:710-964) for roofline timing:
+// MINCO state is generated once, then `reps` sampling passes are run.
+__global__ void __launch_bounds__(UALM_THREADS) penalty_only_kernel(BatchPtrs bp, DevParams p, DevMap map, SmemLayout L, int reps)
+{
+    extern __shared__ double sm[];
+    const int tid = threadIdx.x;
+    const int prob = bp.order[blockIdx.x];
+    Traj t;
+    traj_setup(t, bp, p, L, sm, prob);
+    for (int q = tid; q < t.n; q += UALM_THREADS) t.x[q] = bp.x0[t.pd->off_x + q];
+    if (tid == 0) { t.sc[SC_SCALE_FX] = 1.0; t.sc[SC_RHO] = p.rho; }
+    __syncthreads();
+    minco_generate(t, tid);
+    sample_tables(t, tid);
+    for (int r = 0; r < reps; r++) {
+        penalty_samples(t, map, p, tid);
+        penalty_accumulate(t, tid);
+    }
+    if (tid == 0) bp.f_out[prob] = t.sc[SC_CONSTR];
+}
+
+// fixed-stride result records for the multi-GPU all-gather
+__global__ void pack_records_kernel(BatchPtrs bp, int B, R *rec, int stride)
+{
+    const int b = blockIdx.x;
+    if (b >= B) return;
+    const ProbDesc *pd = bp.desc + b;
+    R *o = rec + (size_t)b * stride;
+    const ualm_result_t r = bp.results[b];
+    if (threadIdx.x == 0) {
+        o[0] = r.ret_code; o[1] = r.outer_iters; o[2] = r.n_evals; o[3] = r.n_lbfgs_iters; o[4] = r.inner_cost; o[5] = r.jerk_cost;
+        o[6] = r.total_T; o[7] = r.res_h; o[8] = r.res_g; o[9] = pd->N; o[10] = pd->M; o[11] = 0.0;
+    }
+    const int ncx = 12 * pd->N, ncy = 6 * pd->M;
+    for (int q = threadIdx.x; q < stride - 12; q += blockDim.x) {
+        R v = 0.0;
+        if (q < ncx) v = bp.c_xy[pd->off_cxy + q];
+        else if (q < ncx + ncy) v = bp.c_yaw[pd->off_cyaw + q - ncx];
+        o[12 + q] = v;
+    }
+}
+
+} // namespace ualm
