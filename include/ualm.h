@@ -66,6 +66,8 @@ typedef struct {
     int32_t n_lbfgs_iters;   /* accepted line searches */
     int32_t last_lbfgs_ret;
     int32_t max_bound;
+    int32_t sum_bound;       /* sum over L-BFGS iterations of the history depth used (bytes accounting) */
+    int32_t reserved;
     double  inner_cost, jerk_cost, total_T, res_h, res_g, scale_fx, rho_final;
 } ualm_result_t;
 
@@ -75,6 +77,9 @@ typedef struct ualm_ctx ualm_ctx_t;
 int ualm_create(ualm_ctx_t **ctx, int device, int precision);
 int ualm_destroy(ualm_ctx_t *ctx);
 const char *ualm_last_error(void);
+/* run all work of this context on a caller-owned CUDA stream (e.g. torch's current stream); NULL restores the
+ * context's own stream */
+int ualm_set_stream(ualm_ctx_t *ctx, void *cuda_stream);
 int ualm_set_params(ualm_ctx_t *ctx, const ualm_params_t *p);                    /* ALMTrajOpt::init */
 /* cells: host, [X][Y][Yaw][4] float {z, sigma, zbx, zby}, address x*Y*Yaw + y*Yaw + yaw (uneven_map.h:427-435).
  * One-time upload (replaces setEnvironment; the reference's map_buffer is private, uneven_map.h:91). */
@@ -118,6 +123,11 @@ int ualm_init_scaling_batch(ualm_ctx_t *ctx, double *scale_fx, double *scale_cx)
 /* time `reps` back-to-back launches of the penalty-sampling kernel alone over the uploaded batch
  * (roofline of calConstrainCostGrad, alm_traj_opt.cpp:663-991): average ms per launch */
 int ualm_time_penalty_kernel(ualm_ctx_t *ctx, int reps, float *ms_per_launch, double *algorithmic_bytes);
+
+/* developer aid: per-phase SM-cycle counters of the last solve (thread 0 of every CTA) summed over the batch into out16[16]
+ * (order: fill, LU, solve, jerk, tables, samples, accumulate, combine, adjoint, tail, two-loop, line-search, initScaling,
+ * dual-update, other, total).  enable != 0 switches collection on for the following solves. */
+int ualm_profile(ualm_ctx_t *ctx, int enable, long long *out16);
 
 /* =====================  host-side input pipeline (no GPU needed)  ===================== */
 

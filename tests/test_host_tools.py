@@ -1,0 +1,141 @@
+"""Host side of the boundary: input contract (PlanManager resampler), initial path generator, map geometry/builder,
+and the C ABI surface (every symbol of include/ualm.h is exported; compute calls fail loudly without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from uneven_planner_b200 import _lib, maps, problems
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_every_declared_symbol_is_exported(built):
+    hdr = open(os.path.join(ROOT, "include", "ualm.h")).read()
+    names = sorted(set(re.findall(r"\b(ualm_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 20
+    L = C.CDLL(_lib.LIB_PATH)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_compute_calls_fail_loudly_without_gpu(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    L = _lib.lib()
+    h = C.c_void_p()
+    rc = L.ualm_create(C.byref(h), 0, 64)
+    assert rc == _lib.UALM_ENOCUDA
+    assert b"CUDA" in L.ualm_last_error()
+
+
+def test_unsupported_precision_is_rejected(built):
+    L = _lib.lib()
+    h = C.c_void_p()
+    assert L.ualm_create(C.byref(h), 0, 16) == _lib.UALM_EINVAL
+
+
+def test_map_geometry_matches_reference_rule(built):
+    g = _lib.map_geometry()  # run_hill.yaml: 10 x 10 m, 0.05 m, 0.1 rad
+    assert tuple(g.voxel_num) == (200, 200, 64)  # SURVEY 8a a8 / uneven_map.cpp:108-110
+    assert g.origin[0] == -5.0 and abs(g.origin[2] + (np.pi + 0.025)) < 1e-15
+
+
+def py_resample(path, piece_len=0.3, ypt=2.0, mean_vel=0.5, itt=1.2, isv=0.05):
+    """independent Python restatement of plan_manager.cpp:62-122"""
+    p = np.array(path, dtype=np.float64)
+    for i in range(len(p) - 1):
+        while p[i + 1, 2] - p[i, 2] >= np.pi / 2: p[i + 1, 2] -= 2 * np.pi
+        while p[i + 1, 2] - p[i, 2] <= -np.pi / 2: p[i + 1, 2] += 2 * np.pi
+    tly = tlp = tot = 0.0
+    ply = piece_len / ypt
+    xy, yaw = [], []
+    for k in range(len(p) - 1):
+        seg = np.hypot(*(p[k + 1, :2] - p[k, :2]))
+        tly += seg; tlp += seg; tot += seg
+        while tly > ply:
+            yaw.append(p[k, 2] + (1.0 - (tly - ply) / seg) * (p[k + 1, 2] - p[k, 2])); tly -= ply
+        while tlp > piece_len:
+            xy.append(p[k, :2] + (1.0 - (tlp - piece_len) / seg) * (p[k + 1, :2] - p[k, :2])); tlp -= piece_len
+    return len(xy) + 1, len(yaw) + 1, np.array(xy).ravel(), np.array(yaw), tot / mean_vel * itt, p
+
+
+def test_resampler_matches_python_restatement(built):
+    rng = np.random.default_rng(0)
+    for trial in range(20):
+        s = np.array([rng.uniform(-4, 4), rng.uniform(-4, 4), rng.uniform(-np.pi, np.pi)])
+        e = np.array([rng.uniform(-4, 4), rng.uniform(-4, 4), rng.uniform(-np.pi, np.pi)])
+        path = problems.dubins(s, e)
+        N, M, bnd, T, ixy, iyaw = problems.resample(path)
+        N2, M2, ixy2, iyaw2, T2, p = py_resample(path)
+        assert (N, M) == (N2, M2)
+        assert np.allclose(ixy, ixy2, atol=1e-14) and np.allclose(iyaw, iyaw2, atol=1e-14) and abs(T - T2) < 1e-12
+        # boundary states: 0.05 m/s along the heading, zero acceleration (pm.cpp:80-94)
+        assert np.allclose(bnd[:6], [p[0, 0], p[0, 1], 0.05 * np.cos(p[0, 2]), 0.05 * np.sin(p[0, 2]), 0, 0])
+        assert np.allclose(bnd[12:15], [p[0, 2], 0, 0]) and np.allclose(bnd[15:18], [p[-1, 2], 0, 0])
+        # derived sizes of SURVEY section 3.1
+        L = np.hypot(np.diff(path[:, 0]), np.diff(path[:, 1])).sum()
+        assert abs(N - (int(L / 0.3) + 1)) <= 1 and abs(M - (int(L / 0.15) + 1)) <= 1
+
+
+def test_dubins_reaches_goal_with_bounded_curvature(built):
+    rng = np.random.default_rng(3)
+    for trial in range(50):
+        s = np.array([rng.uniform(-4, 4), rng.uniform(-4, 4), rng.uniform(-np.pi, np.pi)])
+        e = np.array([rng.uniform(-4, 4), rng.uniform(-4, 4), rng.uniform(-np.pi, np.pi)])
+        path = problems.dubins(s, e, radius=0.6, ds=0.02)
+        assert np.allclose(path[0, :2], s[:2]) and np.allclose(path[-1, :2], e[:2], atol=1e-9)
+        d = np.hypot(np.diff(path[:-1, 0]), np.diff(path[:-1, 1]))
+        assert np.all(d < 0.0201)
+        dyaw = np.abs(np.angle(np.exp(1j * np.diff(path[:-1, 2]))))
+        assert np.all(dyaw <= 0.02 / 0.6 + 1e-9)  # |kappa| <= 1/radius
+        # heading is the path tangent (forward motion)
+        mid = len(path) // 2
+        tang = np.arctan2(path[mid + 1, 1] - path[mid, 1], path[mid + 1, 0] - path[mid, 0])
+        assert abs(np.angle(np.exp(1j * (tang - path[mid, 2])))) < 0.03
+        # the last sampled heading meets the goal heading
+        assert abs(np.angle(np.exp(1j * (path[-2, 2] - e[2])))) < 0.05
+
+
+def test_map_builder_on_analytic_cloud(built):
+    """constructMap restatement: a cloud sampled from a tilted plane must give its normal, sigma ~ 0 and z on the plane."""
+    rng = np.random.default_rng(0)
+    a, b = 0.15, -0.1
+    xy = rng.uniform(-5, 5, (300000, 2))
+    pts = np.column_stack([xy, 1.0 + a * xy[:, 0] + b * xy[:, 1]]).astype(np.float32)
+    m = maps.build_from_cloud(pts, nthreads=8)
+    nrm = np.array([-a, -b, 1.0]) / np.sqrt(1 + a * a + b * b)
+    inner = m.cells[20:180, 20:180]
+    assert np.abs(inner[..., 2] - nrm[0]).max() < 2e-3 and np.abs(inner[..., 3] - nrm[1]).max() < 2e-3
+    assert inner[..., 1].max() < 1e-6  # surface variation of an exact plane (float32 cloud -> ~1e-9)
+    g = m.geom
+    xs = (np.arange(200) + 0.5) * g.xy_resolution + g.origin[0]
+    yaws = (np.arange(64) + 0.5) * g.yaw_resolution + g.origin[2]
+    # z is the mean height of the points in the ellipsoid centred 0.12 m ahead of the cell (uneven_map.cpp:341-342)
+    X, Y, W = np.meshgrid(xs, xs, yaws, indexing="ij")
+    zexp = 1.0 + a * (X + 0.12 * np.cos(W)) + b * (Y + 0.12 * np.sin(W))
+    err = np.abs(m.cells[20:180, 20:180, :, 0] - zexp[20:180, 20:180])  # sample mean of ~190 random points per footprint
+    assert err.mean() < 2e-3 and err.max() < 3e-2
+    occ3, occ2 = m.occupancy()
+    assert occ2[20:180, 20:180].sum() == 0
+
+
+def test_umap_file_roundtrip(built, tmp_path):
+    m = maps.synthetic_terrain("bumps", seed=1)
+    p = str(tmp_path / "t.umap")
+    m.save(p)
+    m2 = maps.UnevenMapData.load(p)
+    assert np.array_equal(m.cells, m2.cells) and tuple(m2.geom.voxel_num) == (200, 200, 64)
+
+
+def test_problem_generator_is_deterministic_and_valid(bumps_map):
+    a = problems.generate(bumps_map, 16, seed=7)
+    b = problems.generate(bumps_map, 16, seed=7)
+    assert np.array_equal(a.N, b.N) and np.array_equal(a.inner_xy, b.inner_xy) and np.array_equal(a.bnd, b.bnd)
+    assert a.N.min() >= 5 and a.N.max() <= 56 and np.all(a.M >= a.N)
+    assert np.all(np.hypot(*(a.starts[:, :2] - a.goals[:, :2]).T) >= 1.5)
+    sub = a.select([3, 5])
+    assert np.array_equal(sub.x0(1), a.x0(5))

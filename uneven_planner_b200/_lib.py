@@ -29,7 +29,7 @@ class MapGeom(C.Structure):
 
 class Result(C.Structure):
     _fields_ = [("ret_code", C.c_int32), ("outer_iters", C.c_int32), ("n_evals", C.c_int32),
-                ("n_lbfgs_iters", C.c_int32), ("last_lbfgs_ret", C.c_int32), ("max_bound", C.c_int32),
+                ("n_lbfgs_iters", C.c_int32), ("last_lbfgs_ret", C.c_int32), ("max_bound", C.c_int32), ("sum_bound", C.c_int32), ("reserved", C.c_int32),
                 ("inner_cost", C.c_double), ("jerk_cost", C.c_double), ("total_T", C.c_double),
                 ("res_h", C.c_double), ("res_g", C.c_double), ("scale_fx", C.c_double), ("rho_final", C.c_double)]
 
@@ -65,6 +65,8 @@ def lib():
         L.ualm_destroy.argtypes = [vp]
         L.ualm_last_error.argtypes = []
         L.ualm_last_error.restype = C.c_char_p
+        L.ualm_set_stream.argtypes = [vp, vp]
+        L.ualm_set_stream.restype = C.c_int
         L.ualm_set_params.argtypes = [vp, C.POINTER(Params)]
         L.ualm_set_map.argtypes = [vp, C.POINTER(MapGeom), fp]
         L.ualm_solve_batch.argtypes = [vp, C.c_int, ip, ip, dp, dp, dp, dp, C.POINTER(Result), dp, dp]
@@ -77,6 +79,8 @@ def lib():
         L.ualm_eval_batch.argtypes = [vp, dp, dp, dp, dp, dp, C.c_double, dp, dp, dp, dp, dp, dp]
         L.ualm_init_scaling_batch.argtypes = [vp, dp, dp]
         L.ualm_time_penalty_kernel.argtypes = [vp, C.c_int, C.POINTER(C.c_float), dp]
+        L.ualm_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong)]
+        L.ualm_profile.restype = C.c_int
         for name in ("ualm_create", "ualm_destroy", "ualm_set_params", "ualm_set_map", "ualm_solve_batch",
                      "ualm_upload", "ualm_solve_resident", "ualm_sync", "ualm_download", "ualm_last_solve_ms",
                      "ualm_pack_records_device", "ualm_eval_batch", "ualm_init_scaling_batch",

@@ -58,6 +58,10 @@ class BatchALMTrajOpt:
         _check(self.L.ualm_set_params(self.h, C.byref(self.params)))
         return self
 
+    def set_stream(self, cuda_stream_ptr):
+        _check(self.L.ualm_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+        return self
+
     def set_environment(self, mapdata):
         self.map = mapdata
         _check(self.L.ualm_set_map(self.h, C.byref(mapdata.geom), mapdata.cells.ctypes.data_as(C.POINTER(C.c_float))))
@@ -129,3 +133,11 @@ class BatchALMTrajOpt:
         ms, by = C.c_float(), C.c_double()
         _check(self.L.ualm_time_penalty_kernel(self.h, reps, C.byref(ms), C.byref(by)))
         return ms.value, by.value
+
+    PHASES = ("fill", "lu", "solve", "jerk", "tables", "samples", "accumulate", "combine", "adjoint", "tail", "twoloop", "linesearch",
+              "scaling", "dual", "other", "total")
+
+    def profile(self, enable=True, read=False):
+        out = (C.c_longlong * 16)()
+        _check(self.L.ualm_profile(self.h, 1 if enable else 0, out if read else None))
+        return dict(zip(self.PHASES, list(out))) if read else None

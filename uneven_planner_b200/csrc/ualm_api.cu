@@ -43,7 +43,7 @@ struct DevBuf {
 
 struct ualm_ctx {
     int device = 0, precision = 64;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool have_params = false, have_map = false, have_batch = false, solved = false;
     ualm_params_t hp;
@@ -59,6 +59,8 @@ struct ualm_ctx {
     DevBuf<int> d_order;
     DevBuf<double> d_x0, d_x, d_lambda, d_mu, d_scale_cx, d_hx, d_gx, d_lm_s, d_lm_y, d_scr, d_ws, d_cxy, d_cyaw, d_f, d_grad, d_sfx;
     DevBuf<ualm_result_t> d_res;
+    DevBuf<long long> d_prof;
+    bool profile = false;
     float last_ms = 0.f;
     int last_launches = 0;
     SmemLayout L;
@@ -78,7 +80,8 @@ extern "C" int ualm_create(ualm_ctx_t **out, int device, int precision)
     CK(cudaSetDevice(device));
     ualm_ctx *c = new ualm_ctx();
     c->device = device; c->precision = precision;
-    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
     *out = c;
@@ -94,10 +97,19 @@ extern "C" int ualm_destroy(ualm_ctx_t *c)
     DevBuf<double> *bufs[] = {&c->d_x0, &c->d_x, &c->d_lambda, &c->d_mu, &c->d_scale_cx, &c->d_hx, &c->d_gx, &c->d_lm_s, &c->d_lm_y,
                               &c->d_scr, &c->d_ws, &c->d_cxy, &c->d_cyaw, &c->d_f, &c->d_grad, &c->d_sfx};
     for (auto *b : bufs) b->release();
-    c->d_res.release();
+    c->d_res.release(); c->d_prof.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
-    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->own_stream);
     delete c;
+    return UALM_OK;
+}
+
+extern "C" int ualm_set_stream(ualm_ctx_t *c, void *s)
+{
+    if (!c) return fail(UALM_EINVAL, "null ctx");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
     return UALM_OK;
 }
 
@@ -155,6 +167,7 @@ static BatchPtrs batch_ptrs(ualm_ctx *c)
     b.lm_s = c->d_lm_s.p; b.lm_y = c->d_lm_y.p; b.scratch = c->d_scr.p; b.ws_scaling = c->d_ws.p; b.ws_stride = c->ws_stride;
     b.c_xy = c->d_cxy.p; b.c_yaw = c->d_cyaw.p; b.results = c->d_res.p; b.f_out = c->d_f.p; b.grad_out = c->d_grad.p;
     b.scale_fx_io = c->d_sfx.p;
+    b.prof = c->profile ? c->d_prof.p : nullptr;
     return b;
 }
 
@@ -194,6 +207,7 @@ extern "C" int ualm_upload(ualm_ctx_t *c, int B, const int32_t *N, const int32_t
     CK(c->d_lambda.ensure(os)); CK(c->d_hx.ensure(os)); CK(c->d_mu.ensure(6 * os)); CK(c->d_gx.ensure(6 * os)); CK(c->d_scale_cx.ensure(7 * os));
     CK(c->d_lm_s.ensure(oh)); CK(c->d_lm_y.ensure(oh)); CK(c->d_scr.ensure(oscr));
     CK(c->d_ws.ensure(c->hp.use_scaling ? (size_t)c->ws_stride * B : 1));
+    CK(c->d_prof.ensure((size_t)std::max(B, 1) * UALM_NPROF));
     CK(c->d_cxy.ensure(ocx)); CK(c->d_cyaw.ensure(ocy)); CK(c->d_res.ensure(B)); CK(c->d_f.ensure(B)); CK(c->d_sfx.ensure(B));
     if (B > 0) {
         CK(cudaMemcpyAsync(c->d_desc.p, c->desc.data(), sizeof(ProbDesc) * B, cudaMemcpyHostToDevice, c->stream));
@@ -354,5 +368,22 @@ extern "C" int ualm_time_penalty_kernel(ualm_ctx_t *c, int reps, float *ms_per_l
         for (auto &d : c->desc) bytes += (double)d.S * 45 * 8 + (25.0 * d.N + 13.0 * d.M) * 8;
         *algorithmic_bytes = bytes;
     }
+    return UALM_OK;
+}
+
+// developer aid: per-phase SM cycle counters of the last solve (thread 0 of every CTA), summed over the batch.
+// enable != 0 turns collection on for subsequent solves; out16 (may be NULL) receives the sums of the last solve.
+extern "C" int ualm_profile(ualm_ctx_t *c, int enable, long long *out16)
+{
+    if (!c) return fail(UALM_EINVAL, "null ctx");
+    CK(cudaSetDevice(c->device));
+    if (out16 && c->profile && c->solved && c->B > 0) {
+        std::vector<long long> h((size_t)c->B * UALM_NPROF);
+        CK(cudaMemcpyAsync(h.data(), c->d_prof.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (int q = 0; q < UALM_NPROF; q++) out16[q] = 0;
+        for (int b = 0; b < c->B; b++) for (int q = 0; q < UALM_NPROF; q++) out16[q] += h[(size_t)b * UALM_NPROF + q];
+    }
+    c->profile = enable != 0;
     return UALM_OK;
 }

@@ -21,6 +21,7 @@
 
 #define UALM_THREADS 128
 #define UALM_NFIELD 26          // per-sample scratch fields (see SF_* below)
+#define UALM_NPROF 16
 
 namespace ualm {
 
@@ -86,6 +87,7 @@ struct BatchPtrs {
     ualm_result_t *results;
     // eval entry
     R *f_out, *grad_out, *scale_fx_io;
+    long long *prof;         // optional [grid][UALM_NPROF] phase cycle counters (thread 0 of each CTA)
 };
 
 // per-sample scratch fields (SoA: scratch[field * S + s])
@@ -158,7 +160,21 @@ struct Traj {
     // global
     R *lambda, *mu, *scale_cx, *hx, *gx, *lm_s, *lm_y, *scr;
     int n_evals;
+    long long *prof;   // shared-memory phase counters (thread 0 only)
+    long long *plast;
 };
+
+// phase ids of the in-kernel profiler
+enum { PF_FILL = 0, PF_LU, PF_SOLVE, PF_JERK, PF_TABLES, PF_SAMPLES, PF_ACCUM, PF_COMBINE, PF_ADJ, PF_TAIL, PF_TWOLOOP, PF_LS, PF_SCALING,
+       PF_DUAL, PF_OTHER, PF_TOTAL };
+__device__ __forceinline__ void prof_mark(const Traj &t, int tid, int phase)
+{
+    if (tid == 0) {
+        const long long c = clock64();
+        t.prof[phase] += c - *t.plast;
+        *t.plast = c;
+    }
+}
 
 __device__ __forceinline__ R expC2(R tau) // alm_traj_opt.h:232-235
 {
@@ -362,14 +378,17 @@ __device__ void minco_generate(Traj &t, int tid)
     }
     __syncthreads();
     minco_fill(t, tid);
+    prof_mark(t, tid, PF_FILL);
     const int warp = tid >> 5, lane = tid & 31;
     if (warp == 0) banded_lu_warp(t.Axy, 6 * t.N, lane);
     else if (warp == 1) banded_lu_warp(t.Ayaw, 6 * t.M, lane);
     __syncthreads();
+    prof_mark(t, tid, PF_LU);
     if (tid == 0) banded_solve_col(t.Axy, 6 * t.N, t.cxy);
     else if (tid == 32) banded_solve_col(t.Axy, 6 * t.N, t.cxy + 6 * t.N);
     else if (tid == 64) banded_solve_col(t.Ayaw, 6 * t.M, t.cyaw);
     __syncthreads();
+    prof_mark(t, tid, PF_SOLVE);
 }
 
 // jerk cost and its (C,T) gradient (se2traj.hpp:697-747).  Per-piece values in parallel, the sum over pieces
@@ -871,11 +890,16 @@ __device__ void evaluate(Traj &t, const DevMap &map, const DevParams &p, int tid
 {
     const int N = t.N, M = t.M, nx = 6 * N, ny = 6 * M;
     t.n_evals++;
+    prof_mark(t, tid, PF_OTHER);
     minco_generate(t, tid);
     jerk_cost_grad(t, tid);
+    prof_mark(t, tid, PF_JERK);
     sample_tables(t, tid);
+    prof_mark(t, tid, PF_TABLES);
     penalty_samples(t, map, p, tid);
+    prof_mark(t, tid, PF_SAMPLES);
     penalty_accumulate(t, tid);
+    prof_mark(t, tid, PF_ACCUM);
     // combine jerk and constraint gradients (alm_traj_opt.cpp:322-332)
     const R scale_fx = t.sc[SC_SCALE_FX];
     for (int q = tid; q < 2 * nx; q += UALM_THREADS) {
@@ -899,11 +923,13 @@ __device__ void evaluate(Traj &t, const DevMap &map, const DevParams &p, int tid
         t.gTyaw[q] = gj * scale_fx + t.gTyaw[q];
     }
     __syncthreads();
+    prof_mark(t, tid, PF_COMBINE);
     // calGradCTtoQT (se2traj.hpp:751-816): adjoint solves in place in gCxy / gCyaw
     if (tid == 0) banded_solve_adj_col(t.Axy, nx, t.gCxy, 1);
     else if (tid == 32) banded_solve_adj_col(t.Axy, nx, t.gCxy + nx, 1);
     else if (tid == 64) banded_solve_adj_col(t.Ayaw, ny, t.gCyaw, 1);
     __syncthreads();
+    prof_mark(t, tid, PF_ADJ);
     for (int q = tid; q < N + M; q += UALM_THREADS) {
         if (q < N) t.gTxy[q] += adj_time_term(t.cxy, nx, t.gCxy, nx, 1, 2, q, N, t.sc[SC_TX1], t.sc[SC_TX2], t.sc[SC_TX3], t.sc[SC_TX4]);
         else t.gTyaw[q - N] += adj_time_term(t.cyaw, ny, t.gCyaw, ny, 1, 1, q - N, M, t.sc[SC_TY1], t.sc[SC_TY2], t.sc[SC_TY3], t.sc[SC_TY4]);
@@ -928,6 +954,7 @@ __device__ void evaluate(Traj &t, const DevMap &map, const DevParams &p, int tid
         t.sc[SC_F] = jerk_cost + t.sc[SC_CONSTR] + tau_cost;
     }
     __syncthreads();
+    prof_mark(t, tid, PF_TAIL);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -950,7 +977,7 @@ __device__ __forceinline__ R lane_absmax(const R *a, int n, int lane)
     return m;
 }
 
-struct LbfgsOut { int ret; R f; int iters; int max_bound; };
+struct LbfgsOut { int ret; R f; int iters; int max_bound; int sum_bound; };
 
 // lbfgs_optimize + line_search_lewisoverton (lbfgs.hpp:276-389, 439-722).  Control flow is uniform over the
 // CTA: every decision is computed identically by all lanes of warp 0 and broadcast through shared memory.
@@ -960,7 +987,7 @@ __device__ LbfgsOut lbfgs_optimize(Traj &t, const DevMap &map, const DevParams &
     const R f_dec_coeff = 1.0e-4, s_curv_coeff = 0.9, cautious_factor = 1.0e-6, machine_prec = 1.0e-16;
     const R max_step = 1.0e+20, min_step = p.min_step;
     const int max_linesearch = 64;
-    LbfgsOut out; out.ret = 0; out.iters = 0; out.max_bound = 0;
+    LbfgsOut out; out.ret = 0; out.iters = 0; out.max_bound = 0; out.sum_bound = 0;
 
     for (int q = tid; q < m; q += UALM_THREADS) { t.lm_alpha[q] = 0.0; t.lm_ys[q] = 0.0; }
     evaluate(t, map, p, tid);
@@ -1084,10 +1111,12 @@ __device__ LbfgsOut lbfgs_optimize(Traj &t, const DevMap &map, const DevParams &
         }
         __syncthreads();
         const int upd = s_flag[0];
+        prof_mark(t, tid, PF_LS);
         if (upd) {
             ++bound;
             bound = m < bound ? m : bound;
             if (bound > out.max_bound) out.max_bound = bound;
+            out.sum_bound += bound;
             end = (end + 1) % m;
             if (warp == 0) { // two-loop recursion (lbfgs.hpp:691-710) on warp 0; d lives in shared memory
                 const R ys = t.sc[SC_YS], yy = t.sc[SC_YY];
@@ -1115,6 +1144,7 @@ __device__ LbfgsOut lbfgs_optimize(Traj &t, const DevMap &map, const DevParams &
             }
         }
         __syncthreads();
+        prof_mark(t, tid, PF_TWOLOOP);
         step = 1.0;
     }
     out.ret = ret;
@@ -1361,6 +1391,11 @@ __device__ void traj_setup(Traj &t, const BatchPtrs &bp, const DevParams &p, con
     t.lm_y = bp.lm_y ? bp.lm_y + pd->off_hist : nullptr;
     t.scr = bp.scratch + pd->off_scr;
     t.n_evals = 0;
+    __shared__ long long s_prof[UALM_NPROF + 1];
+    if (threadIdx.x < UALM_NPROF + 1) s_prof[threadIdx.x] = 0;
+    t.prof = s_prof; t.plast = s_prof + UALM_NPROF;
+    __syncthreads();
+    if (threadIdx.x == 0) { *t.plast = clock64(); s_prof[PF_TOTAL] = -clock64(); }
 }
 
 // =============================================================================================
@@ -1385,13 +1420,15 @@ __global__ void __launch_bounds__(UALM_THREADS) solve_kernel(BatchPtrs bp, DevPa
     if (tid == 0) { t.sc[SC_SCALE_FX] = 1.0; t.sc[SC_RHO] = p.rho; }
     __syncthreads();
     if (p.use_scaling) init_scaling(t, map, p, tid, bp.ws_scaling + (size_t)blockIdx.x * bp.ws_stride);
+    prof_mark(t, tid, PF_SCALING);
 
-    int ret_code = 0, iter = 0, last = 0, iters_total = 0, max_bound = 0;
+    int ret_code = 0, iter = 0, last = 0, iters_total = 0, max_bound = 0, sum_bound = 0;
     R inner_cost = 0.0, rh = 0.0, rg = 0.0;
     while (true) {
         LbfgsOut lo = lbfgs_optimize(t, map, p, tid, s_flag);
         inner_cost = lo.f; last = lo.ret; iters_total += lo.iters;
         if (lo.max_bound > max_bound) max_bound = lo.max_bound;
+        sum_bound += lo.sum_bound;
         __syncthreads();
         if (lo.ret == LBFGS_CONVERGENCE || lo.ret == LBFGS_CANCELED || lo.ret == LBFGS_STOP || lo.ret == LBFGSERR_MAXIMUMITERATION) {
         } else if (lo.ret == LBFGSERR_MAXIMUMLINESEARCH) {
@@ -1418,6 +1455,7 @@ __global__ void __launch_bounds__(UALM_THREADS) solve_kernel(BatchPtrs bp, DevPa
         for (int w = 0; w < UALM_THREADS / 32; w++) { rh = fmax(rh, s_red[2 * w]); rg = fmax(rg, s_red[2 * w + 1]); }
         if (tid == 0) t.sc[SC_RHO] = rho_new;
         __syncthreads();
+        prof_mark(t, tid, PF_DUAL);
         if (fmax(rh, rg) < p.epsilon_con) break;
         if ((R)(++iter) > p.max_iter) { ret_code = 2; break; }
     }
@@ -1429,11 +1467,15 @@ __global__ void __launch_bounds__(UALM_THREADS) solve_kernel(BatchPtrs bp, DevPa
     if (tid == 0) {
         ualm_result_t r;
         r.ret_code = ret_code; r.outer_iters = iter; r.n_evals = t.n_evals; r.n_lbfgs_iters = iters_total; r.last_lbfgs_ret = last;
-        r.max_bound = max_bound; r.inner_cost = inner_cost; r.jerk_cost = t.sc[SC_JERKRAW];
+        r.max_bound = max_bound; r.sum_bound = sum_bound; r.reserved = 0; r.inner_cost = inner_cost; r.jerk_cost = t.sc[SC_JERKRAW];
         R tt = 0.0;
         for (int i = 0; i < N; i++) tt += t.sc[SC_TX1];
         r.total_T = tt; r.res_h = rh; r.res_g = rg; r.scale_fx = t.sc[SC_SCALE_FX]; r.rho_final = t.sc[SC_RHO];
         bp.results[prob] = r;
+        if (bp.prof) {
+            t.prof[PF_TOTAL] += clock64();
+            for (int q = 0; q < UALM_NPROF; q++) bp.prof[(size_t)blockIdx.x * UALM_NPROF + q] = t.prof[q];
+        }
     }
 }
 

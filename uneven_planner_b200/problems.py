@@ -64,7 +64,7 @@ class ProblemBatch:
         return self.N.astype(np.int64) * (int_K + 1)
 
     def select(self, idx):
-        idx = np.asarray(idx)
+        idx = np.asarray(idx, dtype=np.int64)
         oxy, oyaw, _, _ = self.offsets()
         return ProblemBatch(self.N[idx].copy(), self.M[idx].copy(), self.bnd[idx].copy(), self.total_time[idx].copy(),
                             np.concatenate([self.inner_xy[oxy[i]:oxy[i + 1]] for i in idx]) if len(idx) else np.zeros(0),
