@@ -54,10 +54,10 @@ struct ualm_ctx {
     int B = 0, Nmax = 0, Mmax = 0, nmax = 0, Smax = 0;
     std::vector<ProbDesc> desc;
     std::vector<int> order;
-    long long tot_x = 0, tot_s = 0, tot_cxy = 0, tot_cyaw = 0, tot_hist = 0, tot_scr = 0, ws_stride = 0;
+    long long tot_x = 0, tot_s = 0, tot_cxy = 0, tot_cyaw = 0, tot_hist = 0, tot_scr = 0, tot_fac = 0, tot_ws = 0;
     DevBuf<ProbDesc> d_desc;
     DevBuf<int> d_order;
-    DevBuf<double> d_x0, d_x, d_lambda, d_mu, d_scale_cx, d_hx, d_gx, d_lm_s, d_lm_y, d_scr, d_ws, d_cxy, d_cyaw, d_f, d_grad, d_sfx;
+    DevBuf<double> d_x0, d_x, d_lambda, d_mu, d_scale_cx, d_hx, d_gx, d_lm_s, d_lm_y, d_lm_aux, d_fac, d_scr, d_ws, d_cxy, d_cyaw, d_f, d_grad, d_sfx;
     DevBuf<ualm_result_t> d_res;
     DevBuf<long long> d_prof;
     bool profile = false;
@@ -94,7 +94,7 @@ extern "C" int ualm_destroy(ualm_ctx_t *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->cells.release(); c->d_desc.release(); c->d_order.release();
-    DevBuf<double> *bufs[] = {&c->d_x0, &c->d_x, &c->d_lambda, &c->d_mu, &c->d_scale_cx, &c->d_hx, &c->d_gx, &c->d_lm_s, &c->d_lm_y,
+    DevBuf<double> *bufs[] = {&c->d_x0, &c->d_x, &c->d_lambda, &c->d_mu, &c->d_scale_cx, &c->d_hx, &c->d_gx, &c->d_lm_s, &c->d_lm_y, &c->d_lm_aux, &c->d_fac,
                               &c->d_scr, &c->d_ws, &c->d_cxy, &c->d_cyaw, &c->d_f, &c->d_grad, &c->d_sfx};
     for (auto *b : bufs) b->release();
     c->d_res.release(); c->d_prof.release();
@@ -164,7 +164,7 @@ static BatchPtrs batch_ptrs(ualm_ctx *c)
     BatchPtrs b;
     b.desc = c->d_desc.p; b.order = c->d_order.p; b.x0 = c->d_x0.p; b.x = c->d_x.p;
     b.lambda = c->d_lambda.p; b.mu = c->d_mu.p; b.scale_cx = c->d_scale_cx.p; b.hx = c->d_hx.p; b.gx = c->d_gx.p;
-    b.lm_s = c->d_lm_s.p; b.lm_y = c->d_lm_y.p; b.scratch = c->d_scr.p; b.ws_scaling = c->d_ws.p; b.ws_stride = c->ws_stride;
+    b.lm_s = c->d_lm_s.p; b.lm_y = c->d_lm_y.p; b.lm_aux = c->d_lm_aux.p; b.fac = c->d_fac.p; b.scratch = c->d_scr.p; b.ws_scaling = c->d_ws.p;
     b.c_xy = c->d_cxy.p; b.c_yaw = c->d_cyaw.p; b.results = c->d_res.p; b.f_out = c->d_f.p; b.grad_out = c->d_grad.p;
     b.scale_fx_io = c->d_sfx.p;
     b.prof = c->profile ? c->d_prof.p : nullptr;
@@ -180,13 +180,13 @@ extern "C" int ualm_upload(ualm_ctx_t *c, int B, const int32_t *N, const int32_t
     const int K = c->dp.int_K, m = c->dp.mem_size;
     c->B = B; c->desc.resize(B); c->order.resize(B);
     c->Nmax = c->Mmax = c->nmax = c->Smax = 1;
-    long long ox = 0, os = 0, ocx = 0, ocy = 0, oh = 0, oscr = 0, oixy = 0, oiyaw = 0;
+    long long ox = 0, os = 0, ocx = 0, ocy = 0, oh = 0, oscr = 0, oixy = 0, oiyaw = 0, ofac = 0, ows = 0;
     std::vector<double> x0;
     for (int b = 0; b < B; b++) {
         ProbDesc &d = c->desc[b];
         if (N[b] < 1 || M[b] < 1 || N[b] > 64 || M[b] > 128) return fail(UALM_ELIMIT, "piece count outside [1,64] x [1,128]");
         d.N = N[b]; d.M = M[b]; d.n = 1 + 2 * (N[b] - 1) + (M[b] - 1); d.S = N[b] * (K + 1);
-        d.off_x = ox; d.off_s = os; d.off_cxy = ocx; d.off_cyaw = ocy; d.off_hist = oh; d.off_scr = oscr;
+        d.off_x = ox; d.off_s = os; d.off_cxy = ocx; d.off_cyaw = ocy; d.off_hist = oh; d.off_scr = oscr; d.off_fac = ofac; d.off_ws = ows;
         for (int k = 0; k < 18; k++) d.bnd[k] = bnd[(size_t)b * 18 + k];
         d.total_time = total_time[b];
         // x = [tau | Pxy | Pyaw]  (alm_traj_opt.cpp:205-216); logC2 (alm_traj_opt.h:238-241) is two IEEE ops + sqrt
@@ -196,17 +196,20 @@ extern "C" int ualm_upload(ualm_ctx_t *c, int B, const int32_t *N, const int32_t
         for (int q = 0; q < d.M - 1; q++) x0.push_back(inner_yaw[oiyaw + q]);
         oixy += 2 * (d.N - 1); oiyaw += d.M - 1;
         ox += d.n; os += d.S; ocx += 12 * d.N; ocy += 6 * d.M; oh += (long long)m * d.n; oscr += (long long)UALM_NFIELD * d.S;
+        ofac += 2LL * UALM_FW * ((6 * d.N + 2 * UALM_FPAD) + (6 * d.M + 2 * UALM_FPAD));
+        ows += (long long)(12 * d.N + 6 * d.M) * 32;
         c->Nmax = std::max(c->Nmax, d.N); c->Mmax = std::max(c->Mmax, d.M); c->nmax = std::max(c->nmax, d.n); c->Smax = std::max(c->Smax, d.S);
     }
-    c->tot_x = ox; c->tot_s = os; c->tot_cxy = ocx; c->tot_cyaw = ocy; c->tot_hist = oh; c->tot_scr = oscr;
+    c->tot_x = ox; c->tot_s = os; c->tot_cxy = ocx; c->tot_cyaw = ocy; c->tot_hist = oh; c->tot_scr = oscr; c->tot_fac = ofac; c->tot_ws = ows;
     // launch order: most samples first (longest-processing-time-first keeps the tail short)
     std::iota(c->order.begin(), c->order.end(), 0);
     std::stable_sort(c->order.begin(), c->order.end(), [&](int a, int b2) { return c->desc[a].S > c->desc[b2].S; });
-    c->ws_stride = (long long)(12 * c->Nmax + 6 * c->Mmax) * UALM_THREADS;
     CK(c->d_desc.ensure(B)); CK(c->d_order.ensure(B)); CK(c->d_x0.ensure(ox)); CK(c->d_x.ensure(ox)); CK(c->d_grad.ensure(ox));
     CK(c->d_lambda.ensure(os)); CK(c->d_hx.ensure(os)); CK(c->d_mu.ensure(6 * os)); CK(c->d_gx.ensure(6 * os)); CK(c->d_scale_cx.ensure(7 * os));
     CK(c->d_lm_s.ensure(oh)); CK(c->d_lm_y.ensure(oh)); CK(c->d_scr.ensure(oscr));
-    CK(c->d_ws.ensure(c->hp.use_scaling ? (size_t)c->ws_stride * B : 1));
+    CK(c->d_ws.ensure(ows)); CK(c->d_fac.ensure(ofac)); CK(c->d_lm_aux.ensure((size_t)std::max(B, 1) * 2 * m));
+    // factor arrays: entries outside the band-in-matrix positions (and the pad rows) are never written and must read 0
+    CK(cudaMemsetAsync(c->d_fac.p, 0, sizeof(double) * std::max<long long>(ofac, 1), c->stream));
     CK(c->d_prof.ensure((size_t)std::max(B, 1) * UALM_NPROF));
     CK(c->d_cxy.ensure(ocx)); CK(c->d_cyaw.ensure(ocy)); CK(c->d_res.ensure(B)); CK(c->d_f.ensure(B)); CK(c->d_sfx.ensure(B));
     if (B > 0) {
@@ -333,7 +336,6 @@ extern "C" int ualm_init_scaling_batch(ualm_ctx_t *c, double *scale_fx, double *
 {
     if (!c || !c->have_batch || !c->have_map) return fail(UALM_ESTATE, "upload and set_map first");
     CK(cudaSetDevice(c->device));
-    CK(c->d_ws.ensure((size_t)c->ws_stride * std::max(c->B, 1)));
     if (c->B > 0) {
         scaling_kernel<<<c->B, UALM_THREADS, c->smem_bytes, c->stream>>>(batch_ptrs(c), c->dp, c->dm, c->L);
         CK(cudaGetLastError());

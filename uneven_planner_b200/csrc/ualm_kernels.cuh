@@ -1,15 +1,19 @@
 // ualm_kernels.cuh -- sm_100a device code of the batched MINCO / PHR-ALM / L-BFGS trajectory optimizer.
 //
-// One CTA (UALM_THREADS threads) owns one optimizeSE2Traj problem from the first evaluation to the last
-// dual update (no host round trips).  The arithmetic is IEEE double with contraction OFF (-fmad=false) and is
-// ordered so that every floating-point result is bit-identical to the CPU oracle (oracle/oracle.cpp):
+// ONE WARP owns one optimizeSE2Traj problem from the first evaluation to the last dual update (no host round trips);
+// a launch is B independent warps (CTA = 32 threads), so a whole batch of ~10^3 problems is resident on the 148 SMs.
+// The arithmetic is IEEE double with contraction OFF (-fmad=false) and is ordered so that every floating-point result is
+// bit-identical to the CPU oracle (oracle/oracle.cpp):
 //   * work that is independent per element (band-matrix entries inside one pivot step, constraint samples,
-//     coefficient-gradient entries, history vectors) is spread over threads;
-//   * every reduction whose order is visible in the reference source is evaluated in that order by one thread
-//     (cost accumulation alm_traj_opt.cpp:825-943, gdC/gdT accumulation :969-985, triangular sweeps
-//     banded_system.hpp:96-145);
-//   * dot products / norms of the L-BFGS driver (order left to Eigen in the reference) use the canonical
-//     32-lane order: lane-strided partial sums + xor-butterfly 16,8,4,2,1 (warp shuffles).
+//     coefficient-gradient entries, history vectors) is spread over the 32 lanes;
+//   * every reduction whose order is visible in the reference source is evaluated in that order (cost accumulation
+//     alm_traj_opt.cpp:825-943, gdC/gdT accumulation :969-985, triangular sweeps banded_system.hpp:96-145);
+//   * dot products / norms of the L-BFGS driver (order left to Eigen in the reference) use the canonical 32-lane order:
+//     lane-strided partial sums + xor-butterfly 16,8,4,2,1 (warp shuffles).
+// Memory plan per trajectory: coefficients, gradients and the decision vectors live in shared memory (~17 KB); the band
+// LU runs on a 16-row sliding window in shared memory and streams its factors to global memory (L2) in row-major (F) and
+// column-major (FT) form; the four triangular sweeps read them back through cp.async rings with the last six solution
+// values in registers; L-BFGS history, duals, constraint values and the per-sample scratch are coalesced global arrays.
 // Reference citations are relative to /root/reference/src/uneven_planner/.
 #pragma once
 
@@ -19,9 +23,12 @@
 #include "ualm.h"
 #include "ualm_detmath.h"
 
-#define UALM_THREADS 128
+#define UALM_THREADS 32         // one warp per trajectory
 #define UALM_NFIELD 26          // per-sample scratch fields (see SF_* below)
 #define UALM_NPROF 16
+#define UALM_FW 14              // doubles per factor row (13 band entries + 1 pad -> 112 B = 7 x 16 B)
+#define UALM_FPAD 8             // zero pad rows before and after each factor array (chunked prefetch may overrun)
+#define UALM_SYNC() __syncwarp()
 
 namespace ualm {
 
@@ -69,6 +76,8 @@ struct ProbDesc {
     long long off_cyaw;   // 6 M
     long long off_hist;   // mem_size * n  (lm_s, lm_y)
     long long off_scr;    // UALM_NFIELD * S per-sample scratch
+    long long off_fac;    // factor arrays: Fxy, FTxy ((6N + 2 pad) rows each), Fyaw, FTyaw, UALM_FW doubles per row
+    long long off_ws;     // initScaling adjoint workspace (12 N + 6 M) * 32
     R bnd[18];
     R total_time;
 };
@@ -80,14 +89,15 @@ struct BatchPtrs {
     R *x;                    // packed final decision vectors
     R *lambda, *mu, *scale_cx, *hx, *gx;
     R *lm_s, *lm_y;
+    R *lm_aux;               // per problem 2 * mem_size: lm_alpha | lm_ys
     R *scratch;
-    R *ws_scaling;           // initScaling adjoint workspace: per CTA  (6N*2 + 6M) * UALM_THREADS
-    long long ws_stride;     // elements per CTA
+    R *fac;                  // LU factors
+    R *ws_scaling;           // initScaling adjoint workspace
     R *c_xy, *c_yaw;
     ualm_result_t *results;
     // eval entry
     R *f_out, *grad_out, *scale_fx_io;
-    long long *prof;         // optional [grid][UALM_NPROF] phase cycle counters (thread 0 of each CTA)
+    long long *prof;         // optional [grid][UALM_NPROF] phase cycle counters (lane 0 of each warp)
 };
 
 // per-sample scratch fields (SoA: scratch[field * S + s])
@@ -101,50 +111,42 @@ enum {
 // shared-memory layout (doubles), sized on the host from the batch maxima
 // ---------------------------------------------------------------------------------------------
 struct SmemLayout {
-    int Axy, Ayaw, cxy, cyaw, gCxy, gCyaw, gCxy_j, gCyaw_j, gTxy, gTyaw, gTxy_j, gTyaw_j, pcost_xy, pcost_yaw;
-    int x, g, xp, gp, d, lm_alpha, lm_ys, pf, s1tab, base, sc, yawidx /* shorts */, total_doubles;
+    int cxy, cyaw, gCxy, gCyaw, gTxy, gTyaw, x, g, xp, gp, d, pf, s1tab, base, sc, win, tmpl, ring, yawidx /* shorts */, total_doubles;
 };
 
 __host__ __device__ inline SmemLayout make_layout(int Nmax, int Mmax, int nmax, int m, int past, int K, int Smax)
 {
     SmemLayout L;
     int o = 0;
-    L.Axy = o; o += 13 * 6 * Nmax;
-    L.Ayaw = o; o += 13 * 6 * Mmax;
     L.cxy = o; o += 12 * Nmax;
     L.cyaw = o; o += 6 * Mmax;
     L.gCxy = o; o += 12 * Nmax;
     L.gCyaw = o; o += 6 * Mmax;
-    L.gCxy_j = o; o += 12 * Nmax;
-    L.gCyaw_j = o; o += 6 * Mmax;
     L.gTxy = o; o += Nmax;
     L.gTyaw = o; o += Mmax;
-    L.gTxy_j = o; o += Nmax;
-    L.gTyaw_j = o; o += Mmax;
-    L.pcost_xy = o; o += Nmax;
-    L.pcost_yaw = o; o += Mmax;
     L.x = o; o += nmax;
     L.g = o; o += nmax;
     L.xp = o; o += nmax;
     L.gp = o; o += nmax;
     L.d = o; o += nmax;
-    L.lm_alpha = o; o += m;
-    L.lm_ys = o; o += m;
     L.pf = o; o += (past > 1 ? past : 1);
     L.s1tab = o; o += K + 1;
     L.base = o; o += Nmax;
-    L.sc = o; o += 64;               // scalars
-    L.yawidx = o; o += (Smax + 3) / 4; // shorts packed
+    L.sc = o; o += 48;                   // scalars
+    o = (o + 1) & ~1;                    // 16-byte alignment for the cp.async destinations
+    L.win = o; o += 2 * 16 * UALM_FW;    // LU sliding windows: 16 row slots per system
+    L.tmpl = o; o += 2 * 12 * UALM_FW;   // template rows of A per system
+    L.ring = o; o += 2 * 8 * 6 * UALM_FW; // factor prefetch rings: 8 blocks of 6 rows per system
+    L.yawidx = o; o += (Smax + 3) / 4;   // shorts packed
     L.total_doubles = o;
+    (void)m;
     return L;
 }
 
 // scalar slots in sm[L.sc + ...]
 enum {
     SC_TX1 = 0, SC_TX2, SC_TX3, SC_TX4, SC_TX5, SC_TY1, SC_TY2, SC_TY3, SC_TY4, SC_TY5,
-    SC_SCALE_FX, SC_RHO, SC_F, SC_JERK, SC_CONSTR, SC_TAUCOST, SC_RED0, SC_RED1, SC_RED2, SC_RED3,
-    SC_STEP, SC_FX, SC_FINIT, SC_DGINIT, SC_DGTEST, SC_DSTEST, SC_MU, SC_NU, SC_YS, SC_YY, SC_TMP0, SC_TMP1,
-    SC_RESH, SC_RESG, SC_JERKRAW
+    SC_SCALE_FX, SC_RHO, SC_F, SC_JERK, SC_CONSTR, SC_TAUCOST, SC_JERKRAW
 };
 
 struct Traj {
@@ -152,15 +154,15 @@ struct Traj {
     int N, M, n, S, K;
     const ProbDesc *pd;
     // smem
-    R *sm;
-    SmemLayout L;
-    R *Axy, *Ayaw, *cxy, *cyaw, *gCxy, *gCyaw, *gCxy_j, *gCyaw_j, *gTxy, *gTyaw, *gTxy_j, *gTyaw_j, *pcx, *pcy;
-    R *x, *g, *xp, *gp, *d, *lm_alpha, *lm_ys, *pf, *s1tab, *base, *sc;
+    R *cxy, *cyaw, *gCxy, *gCyaw, *gTxy, *gTyaw;
+    R *x, *g, *xp, *gp, *d, *pf, *s1tab, *base, *sc, *win, *tmpl, *ring;
     unsigned short *yawidx;
     // global
-    R *lambda, *mu, *scale_cx, *hx, *gx, *lm_s, *lm_y, *scr;
+    R *lambda, *mu, *scale_cx, *hx, *gx, *lm_s, *lm_y, *lm_alpha, *lm_ys, *scr;
+    R *Fxy, *FTxy, *Fyaw, *FTyaw;   // row 0 of each factor array
+    R *ws;
     int n_evals;
-    long long *prof;   // shared-memory phase counters (thread 0 only)
+    long long *prof;   // shared-memory phase counters (lane 0 only)
     long long *plast;
 };
 
@@ -180,10 +182,6 @@ __device__ __forceinline__ R expC2(R tau) // alm_traj_opt.h:232-235
 {
     return tau > 0.0 ? ((0.5 * tau + 1.0) * tau + 1.0) : 1.0 / ((0.5 * tau - 1.0) * tau + 1.0);
 }
-__device__ __forceinline__ R logC2(R T) // alm_traj_opt.h:238-241
-{
-    return T > 1.0 ? (sqrt(2.0 * T - 1.0) - 1.0) : (1.0 - sqrt(2.0 / T - 1.0));
-}
 __device__ __forceinline__ R getTtoTauGrad(R tau) // alm_traj_opt.h:244-253
 {
     if (tau > 0) return tau + 1.0;
@@ -196,247 +194,365 @@ __device__ __forceinline__ void normSO2(R &yaw) // uneven_map.cpp:64-71
     while (yaw > M_PI) yaw -= 2 * M_PI;
 }
 
-// band accessor: ptr[(i - j + 6) * n6 + j]   (banded_system.hpp:55-62)
-#define BAND(A, n6, i, j) (A)[((i) - (j) + 6) * (n6) + (j)]
+// The kernel is latency bound and eight warps per SM sit in different phases, so instruction-cache footprint matters
+// (L0 ~6 KB, L1.5 32 KB): every large device function is __noinline__ (one copy, called), not inlined per call site.
+#define UALM_NOINLINE __noinline__
+__device__ UALM_NOINLINE void dev_sincos(R x, R *s, R *c) { ualm_sincos(x, s, c); }
+__device__ UALM_NOINLINE R dev_atan2(R y, R x) { return ualm_atan2(y, x); }
 
 // ---------------------------------------------------------------------------------------------
-// MINCO: fill A and b (se2traj.hpp:609-674).  All threads; ends with __syncthreads.
+// cp.async (LDGSTS) helpers: 16-byte global -> shared copies that bypass L1 (factors are produced by this warp and
+// consumed once per sweep: L2 is the right home)
 // ---------------------------------------------------------------------------------------------
-__device__ void minco_fill(Traj &t, int tid)
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
-    const int N = t.N, M = t.M, nx = 6 * N, ny = 6 * M;
-    for (int q = tid; q < 13 * nx; q += UALM_THREADS) t.Axy[q] = 0.0;
-    for (int q = tid; q < 13 * ny; q += UALM_THREADS) t.Ayaw[q] = 0.0;
-    for (int q = tid; q < 2 * nx; q += UALM_THREADS) t.cxy[q] = 0.0;
-    for (int q = tid; q < ny; q += UALM_THREADS) t.cyaw[q] = 0.0;
-    __syncthreads();
-    // two systems: sys 0 = xy (Dim 2), sys 1 = yaw (Dim 1)
-    for (int sys = 0; sys < 2; sys++) {
-        R *A = sys ? t.Ayaw : t.Axy;
-        const int P = sys ? M : N, n6 = 6 * P;
-        const R T1 = t.sc[sys ? SC_TY1 : SC_TX1], T2 = t.sc[sys ? SC_TY2 : SC_TX2], T3 = t.sc[sys ? SC_TY3 : SC_TX3],
-                T4 = t.sc[sys ? SC_TY4 : SC_TX4], T5 = t.sc[sys ? SC_TY5 : SC_TX5];
-        for (int i = tid; i < P - 1; i += UALM_THREADS) {
-            BAND(A, n6, 6 * i + 3, 6 * i + 3) = 6.0;
-            BAND(A, n6, 6 * i + 3, 6 * i + 4) = 24.0 * T1;
-            BAND(A, n6, 6 * i + 3, 6 * i + 5) = 60.0 * T2;
-            BAND(A, n6, 6 * i + 3, 6 * i + 9) = -6.0;
-            BAND(A, n6, 6 * i + 4, 6 * i + 4) = 24.0;
-            BAND(A, n6, 6 * i + 4, 6 * i + 5) = 120.0 * T1;
-            BAND(A, n6, 6 * i + 4, 6 * i + 10) = -24.0;
-            BAND(A, n6, 6 * i + 5, 6 * i) = 1.0;
-            BAND(A, n6, 6 * i + 5, 6 * i + 1) = T1;
-            BAND(A, n6, 6 * i + 5, 6 * i + 2) = T2;
-            BAND(A, n6, 6 * i + 5, 6 * i + 3) = T3;
-            BAND(A, n6, 6 * i + 5, 6 * i + 4) = T4;
-            BAND(A, n6, 6 * i + 5, 6 * i + 5) = T5;
-            BAND(A, n6, 6 * i + 6, 6 * i) = 1.0;
-            BAND(A, n6, 6 * i + 6, 6 * i + 1) = T1;
-            BAND(A, n6, 6 * i + 6, 6 * i + 2) = T2;
-            BAND(A, n6, 6 * i + 6, 6 * i + 3) = T3;
-            BAND(A, n6, 6 * i + 6, 6 * i + 4) = T4;
-            BAND(A, n6, 6 * i + 6, 6 * i + 5) = T5;
-            BAND(A, n6, 6 * i + 6, 6 * i + 6) = -1.0;
-            BAND(A, n6, 6 * i + 7, 6 * i + 1) = 1.0;
-            BAND(A, n6, 6 * i + 7, 6 * i + 2) = 2.0 * T1;
-            BAND(A, n6, 6 * i + 7, 6 * i + 3) = 3.0 * T2;
-            BAND(A, n6, 6 * i + 7, 6 * i + 4) = 4.0 * T3;
-            BAND(A, n6, 6 * i + 7, 6 * i + 5) = 5.0 * T4;
-            BAND(A, n6, 6 * i + 7, 6 * i + 7) = -1.0;
-            BAND(A, n6, 6 * i + 8, 6 * i + 2) = 2.0;
-            BAND(A, n6, 6 * i + 8, 6 * i + 3) = 6.0 * T1;
-            BAND(A, n6, 6 * i + 8, 6 * i + 4) = 12.0 * T2;
-            BAND(A, n6, 6 * i + 8, 6 * i + 5) = 20.0 * T3;
-            BAND(A, n6, 6 * i + 8, 6 * i + 8) = -2.0;
-        }
-        if (tid == 0) {
-            BAND(A, n6, 0, 0) = 1.0;
-            BAND(A, n6, 1, 1) = 1.0;
-            BAND(A, n6, 2, 2) = 2.0;
-            BAND(A, n6, n6 - 3, n6 - 6) = 1.0;
-            BAND(A, n6, n6 - 3, n6 - 5) = T1;
-            BAND(A, n6, n6 - 3, n6 - 4) = T2;
-            BAND(A, n6, n6 - 3, n6 - 3) = T3;
-            BAND(A, n6, n6 - 3, n6 - 2) = T4;
-            BAND(A, n6, n6 - 3, n6 - 1) = T5;
-            BAND(A, n6, n6 - 2, n6 - 5) = 1.0;
-            BAND(A, n6, n6 - 2, n6 - 4) = 2.0 * T1;
-            BAND(A, n6, n6 - 2, n6 - 3) = 3.0 * T2;
-            BAND(A, n6, n6 - 2, n6 - 2) = 4.0 * T3;
-            BAND(A, n6, n6 - 2, n6 - 1) = 5.0 * T4;
-            BAND(A, n6, n6 - 1, n6 - 4) = 2.0;
-            BAND(A, n6, n6 - 1, n6 - 3) = 6.0 * T1;
-            BAND(A, n6, n6 - 1, n6 - 2) = 12.0 * T2;
-            BAND(A, n6, n6 - 1, n6 - 1) = 20.0 * T3;
-        }
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int NPEND>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NPEND) : "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// MINCO system matrix entry A(r, r - 6 + q) of a P-piece, uniform-duration system (se2traj.hpp:609-674)
+// ---------------------------------------------------------------------------------------------
+__device__ UALM_NOINLINE R a_entry(int P, int r, int q, R T1, R T2, R T3, R T4, R T5)
+{
+    const int n6 = 6 * P;
+    const int c = r - 6 + q;
+    if (c < 0 || c >= n6 || r >= n6) return 0.0;
+    if (r < 3) {
+        if (c != r) return 0.0;
+        return r == 2 ? 2.0 : 1.0;
     }
-    // right-hand sides
-    const R *bnd = t.pd->bnd;
-    const R *Pxy = t.x + 1, *Pyaw = t.x + 1 + 2 * (N - 1);
-    if (tid < 2) { // dim d = tid: head PVA rows 0..2, tail rows
-        const int d = tid;
-        t.cxy[0 + d * nx] = bnd[d + 0]; t.cxy[1 + d * nx] = bnd[d + 2]; t.cxy[2 + d * nx] = bnd[d + 4];
-        t.cxy[nx - 3 + d * nx] = bnd[6 + d + 0]; t.cxy[nx - 2 + d * nx] = bnd[6 + d + 2]; t.cxy[nx - 1 + d * nx] = bnd[6 + d + 4];
+    if (r >= n6 - 3) {
+        const int e = c - (n6 - 6), tr = r - (n6 - 3);
+        if (e < 0) return 0.0;
+        if (tr == 0) return e == 0 ? 1.0 : e == 1 ? T1 : e == 2 ? T2 : e == 3 ? T3 : e == 4 ? T4 : T5;
+        if (tr == 1) return e == 0 ? 0.0 : e == 1 ? 1.0 : e == 2 ? 2.0 * T1 : e == 3 ? 3.0 * T2 : e == 4 ? 4.0 * T3 : 5.0 * T4;
+        return e < 2 ? 0.0 : e == 2 ? 2.0 : e == 3 ? 6.0 * T1 : e == 4 ? 12.0 * T2 : 20.0 * T3;
     }
-    if (tid == 2) {
-        t.cyaw[0] = bnd[12]; t.cyaw[1] = bnd[13]; t.cyaw[2] = bnd[14];
-        t.cyaw[ny - 3] = bnd[15]; t.cyaw[ny - 2] = bnd[16]; t.cyaw[ny - 1] = bnd[17];
+    const int i = (r - 3) / 6, tt = (r - 3) - 6 * i, e = c - 6 * i;
+    switch (tt) {
+    case 0: return e == 3 ? 6.0 : e == 4 ? 24.0 * T1 : e == 5 ? 60.0 * T2 : e == 9 ? -6.0 : 0.0;
+    case 1: return e == 4 ? 24.0 : e == 5 ? 120.0 * T1 : e == 10 ? -24.0 : 0.0;
+    case 2: return e == 0 ? 1.0 : e == 1 ? T1 : e == 2 ? T2 : e == 3 ? T3 : e == 4 ? T4 : e == 5 ? T5 : 0.0;
+    case 3: return e == 0 ? 1.0 : e == 1 ? T1 : e == 2 ? T2 : e == 3 ? T3 : e == 4 ? T4 : e == 5 ? T5 : e == 6 ? -1.0 : 0.0;
+    case 4: return e == 1 ? 1.0 : e == 2 ? 2.0 * T1 : e == 3 ? 3.0 * T2 : e == 4 ? 4.0 * T3 : e == 5 ? 5.0 * T4 : e == 7 ? -1.0 : 0.0;
+    default: return e == 2 ? 2.0 : e == 3 ? 6.0 * T1 : e == 4 ? 12.0 * T2 : e == 5 ? 20.0 * T3 : e == 8 ? -2.0 : 0.0;
     }
-    for (int i = tid; i < N - 1; i += UALM_THREADS) {
-        t.cxy[6 * i + 5] = Pxy[2 * i];
-        t.cxy[6 * i + 5 + nx] = Pxy[2 * i + 1];
-    }
-    for (int i = tid; i < M - 1; i += UALM_THREADS) t.cyaw[6 * i + 5] = Pyaw[i];
-    __syncthreads();
 }
 
-// banded LU without pivoting, one warp per system (banded_system.hpp:66-91).  Element-wise the update
-// sequence is that of the reference; the 6 multipliers / 36 updates of one pivot step run on different lanes.
-__device__ void banded_lu_warp(R *A, int n6, int lane)
+// ---------------------------------------------------------------------------------------------
+// Structure of the MINCO band matrix and of its LU factors (symbolic elimination, period 6 in the row index; the last six
+// rows/columns -- the tail position/velocity/acceleration rows -- have their own patterns).  Offsets are relative to the
+// pivot: multiplier rows k+o, U columns k+o.  Types 0..5 = k mod 6, types 6..11 = the last six pivots.  The lists are
+// supersets of the numerically non-zero entries (exact cancellations make some fill entries 0), so every use keeps the
+// reference's numeric `!= 0` test (banded_system.hpp:74,81,83) and stays bit-identical to the dense-band loops.
+// ---------------------------------------------------------------------------------------------
+__constant__ signed char LU_NM[12] = {2, 3, 4, 4, 4, 3, 1, 2, 3, 2, 1, 0};
+__constant__ signed char LU_MULT[12][4] = {{5, 6, 0, 0}, {4, 5, 6, 0}, {3, 4, 5, 6}, {2, 3, 4, 5}, {1, 2, 3, 4}, {1, 2, 3, 0},
+                                           {3, 0, 0, 0}, {2, 3, 0, 0}, {1, 2, 3, 0}, {1, 2, 0, 0}, {1, 0, 0, 0}, {0, 0, 0, 0}};
+__constant__ signed char LU_NU[12] = {2, 2, 2, 3, 2, 2, 2, 2, 2, 2, 1, 0};
+__constant__ signed char LU_UCOL[12][3] = {{3, 4, 0}, {2, 3, 0}, {1, 2, 0}, {1, 2, 6}, {1, 6, 0}, {4, 5, 0},
+                                           {3, 4, 0}, {2, 3, 0}, {1, 2, 0}, {1, 2, 0}, {1, 0, 0}, {0, 0, 0}};
+
+// template rows of A: 12 rows x UALM_FW per system: [0..5] junction rows (row index r with (r-3) mod 6 = 0..5), [6..8] head
+// rows 0..2, [9..11] tail rows 6P-3..6P-1.  Filled once per evaluation (the durations are uniform, alm_traj_opt.h:257-261).
+__device__ __forceinline__ int tmpl_index(int r, int n6)
 {
-    for (int k = 0; k <= n6 - 2; k++) {
-        const int iM = min(k + 6, n6 - 1);
-        const R cVl = BAND(A, n6, k, k);
-        if (lane < 6) {
-            const int i = k + 1 + lane;
-            if (i <= iM) {
-                R v = BAND(A, n6, i, k);
-                if (v != 0.0) BAND(A, n6, i, k) = v / cVl;
+    if (r < 3) return 6 + r;
+    if (r >= n6 - 3) return 9 + (r - (n6 - 3));
+    return (r - 3) % 6;
+}
+
+// Banded LU without pivoting (banded_system.hpp:66-91) of the xy system (lanes 0..15) and the yaw system (lanes 16..31) in
+// lockstep on two 16-row sliding windows in shared memory.  Element-wise the update sequence is the reference's; within one
+// pivot step the <=4 multipliers and <=12 updates run on different lanes.  Final factors stream to global memory:
+// F[row][q] = LU(row, row-6+q) and FT[col][q] = LU(col-6+q, col).
+__device__ UALM_NOINLINE void lu_dual(Traj &t, int lane)
+{
+    const int sys = lane >> 4, hl = lane & 15;
+    const int P = sys ? t.M : t.N, n6 = 6 * P;
+    R *W = t.win + sys * (16 * UALM_FW);
+    const R *TM = t.tmpl + sys * (12 * UALM_FW);
+    R *F = sys ? t.Fyaw : t.Fxy, *FT = sys ? t.FTyaw : t.FTxy;
+    // template rows
+    {
+        const R T1 = t.sc[sys ? SC_TY1 : SC_TX1], T2 = t.sc[sys ? SC_TY2 : SC_TX2], T3 = t.sc[sys ? SC_TY3 : SC_TX3],
+                T4 = t.sc[sys ? SC_TY4 : SC_TX4], T5 = t.sc[sys ? SC_TY5 : SC_TX5];
+        R *TMw = t.tmpl + sys * (12 * UALM_FW);
+        for (int e = hl; e < 12 * 13; e += 16) {
+            const int row = e / 13, q = e - 13 * row;
+            // representative row indices in a system with >= 3 pieces; head/tail/junction rows of shorter systems have the
+            // same entries because a_entry only looks at the row type and the column offset
+            R v;
+            if (row < 6) v = a_entry(4, 9 + row, q, T1, T2, T3, T4, T5);          // junction i=1 of a 4-piece system
+            else if (row < 9) v = (q == 6) ? (row == 8 ? 2.0 : 1.0) : 0.0;        // head rows
+            else v = a_entry(4, 21 + (row - 9), q, T1, T2, T3, T4, T5);          // tail rows of a 4-piece system
+            TMw[row * UALM_FW + q] = v;
+        }
+    }
+    UALM_SYNC();
+    // window rows 0..7 (entries whose column falls outside the matrix are zeroed)
+    for (int e = hl; e < 8 * 13; e += 16) {
+        const int r = e / 13, q = e - 13 * r;
+        const int c = r - 6 + q;
+        R v = 0.0;
+        if (r < n6 && c >= 0 && c < n6) v = TM[tmpl_index(r, n6) * UALM_FW + q];
+        W[(r & 15) * UALM_FW + q] = v;
+    }
+    UALM_SYNC();
+    const int nmax6 = 6 * (t.N > t.M ? t.N : t.M);
+    for (int k = 0; k < nmax6; k++) {
+        const bool on = k < n6;
+        if (on && (k % 6) == 0) { // bring rows k+8 .. k+13 into the window
+            for (int e = hl; e < 6 * 13; e += 16) {
+                const int rr = e / 13, q = e - 13 * rr, r = k + 8 + rr;
+                const int c = r - 6 + q;
+                R v = 0.0;
+                if (r < n6 && c >= 0 && c < n6) v = TM[tmpl_index(r, n6) * UALM_FW + q];
+                W[(r & 15) * UALM_FW + q] = v;
             }
         }
-        __syncwarp();
-        const int jM = min(k + 6, n6 - 1);
-        for (int e = lane; e < 36; e += 32) {
-            const int i = k + 1 + e / 6, j = k + 1 + e % 6;
-            if (i <= iM && j <= jM) {
-                const R c = BAND(A, n6, k, j);
-                if (c != 0.0) {
-                    const R l = BAND(A, n6, i, k);
-                    if (l != 0.0) BAND(A, n6, i, j) = BAND(A, n6, i, j) - l * c;
+        const int ty = (k >= n6 - 6) ? 6 + (k - (n6 - 6)) : (k % 6);
+        const R *Wk = W + (k & 15) * UALM_FW;
+        const int nm = on ? LU_NM[ty] : 0, nu = on ? LU_NU[ty] : 0;
+        R m = 0.0;
+        if (hl < nm) {
+            const int o = LU_MULT[ty][hl], i = k + o;
+            R *pa = W + (i & 15) * UALM_FW + 6 - o;
+            const R a = *pa;
+            m = a;
+            if (a != 0.0) { m = a / Wk[6]; *pa = m; }
+            F[(size_t)i * UALM_FW + 6 - o] = m;
+            FT[(size_t)k * UALM_FW + 6 + o] = m;
+        } else if (on && hl >= 4 && hl < 11) {
+            const int q = hl - 4;
+            const R u = Wk[6 + q];
+            F[(size_t)k * UALM_FW + 6 + q] = u;
+            if (k + q < n6) FT[(size_t)(k + q) * UALM_FW + 6 - q] = u;
+        }
+        // updates: lane e < nm*nu handles (multiplier l = e / nu, U column c = e % nu)
+        const int l = (nu > 0) ? hl / nu : 0, cc = (nu > 0) ? hl - l * nu : 0;
+        const R mr = __shfl_sync(0xffffffffu, m, (lane & 16) + (l < 4 ? l : 0));
+        if (hl < nm * nu) {
+            const int o = LU_MULT[ty][l], c = LU_UCOL[ty][cc];
+            const int i = k + o, j = k + c;
+            if (j < n6) {
+                const R u = Wk[6 + c];
+                if (u != 0.0 && mr != 0.0) {
+                    R *pw = W + (i & 15) * UALM_FW + 6 + c - o;
+                    *pw = *pw - mr * u;
                 }
             }
         }
-        __syncwarp();
+        UALM_SYNC();
     }
 }
 
-// forward + backward substitution of ONE right-hand-side column by one thread, row-oriented but with the
-// per-element update order of banded_system.hpp:96-118 (ascending j, then descending j, then the division).
-__device__ void banded_solve_col(const R *A, int n6, R *b)
+// ---------------------------------------------------------------------------------------------
+// Triangular sweeps (banded_system.hpp:96-145), one block of six rows at a time with the static patterns above and the
+// reference's per-element update order (ascending j for the forward sweeps, descending j for the backward ones, then the
+// division).
+//   KIND 0: L y = b      blocks ascending,  entries F[i][6-d]
+//   KIND 1: U x = y      blocks descending, entries F[i][6+d],  then / F[i][6]
+//   KIND 2: U^T y = b    blocks ascending,  entries FT[i][6-d], then / FT[i][6]
+//   KIND 3: L^T x = y    blocks descending, entries FT[i][6+d]
+// Bit d-1 of the mask of row type t (= row mod 6) says whether term d can be non-zero; the last block of a system (tail
+// rows) uses the full mask for the L-based kinds.  Factor blocks arrive through an 8-block cp.async ring per system
+// (prefetch distance 4 blocks); the previous block's six results stay in registers, so no window shifting is needed.
+// ---------------------------------------------------------------------------------------------
+// six 6-bit masks packed per kind (row type t at bits 6t..6t+5)
+__host__ __device__ constexpr unsigned long long pack6(int a, int b, int c, int d, int e, int f)
 {
-    for (int i = 0; i < n6; i++) {
-        R v = b[i];
-        for (int j = max(0, i - 6); j < i; j++) {
-            const R l = BAND(A, n6, i, j);
-            if (l != 0.0) v = v - l * b[j];
-        }
-        b[i] = v;
-    }
-    for (int i = n6 - 1; i >= 0; i--) {
-        R v = b[i];
-        for (int j = min(n6 - 1, i + 6); j > i; j--) {
-            const R u = BAND(A, n6, i, j);
-            if (u != 0.0) v = v - u * b[j];
-        }
-        b[i] = v / BAND(A, n6, i, i);
-    }
+    return (unsigned long long)a | ((unsigned long long)b << 6) | ((unsigned long long)c << 12) | ((unsigned long long)d << 18) |
+           ((unsigned long long)e << 24) | ((unsigned long long)f << 30);
+}
+__host__ __device__ constexpr int sweep_mask(int kind, int t)
+{
+    return (int)(((kind == 0 ? pack6(0x3f, 0x3e, 0x3c, 0x00, 0x00, 0x1f)      // L rows
+                 : kind == 1 ? pack6(0x0c, 0x06, 0x03, 0x23, 0x21, 0x18)      // U rows
+                 : kind == 2 ? pack6(0x00, 0x00, 0x00, 0x2f, 0x3f, 0x03)      // U columns
+                             : pack6(0x30, 0x38, 0x3c, 0x1e, 0x0f, 0x07))     // L columns
+                  >> (6 * t)) & 0x3f);
 }
 
-// A^T x = b, same conventions (banded_system.hpp:123-145).  b has element stride `st` (1 = smem vector;
-// UALM_THREADS = the interleaved per-thread workspace of initScaling).
-__device__ void banded_solve_adj_col(const R *A, int n6, R *b, int st)
+template <int KIND, int NCOL, bool FULL>
+__device__ __forceinline__ void sweep_block(const R *blk, R *b0, R *b1, int bst, int row0, R (&prev0)[6], R (&prev1)[6])
 {
-    for (int i = 0; i < n6; i++) {
-        R v = b[(size_t)i * st];
-        for (int j = max(0, i - 6); j < i; j++) {
-            const R u = BAND(A, n6, j, i);
-            if (u != 0.0) v = v - u * b[(size_t)j * st];
+    constexpr bool ASC = (KIND == 0 || KIND == 2);
+    constexpr bool DIV = (KIND == 1 || KIND == 2);
+    R cur0[6], cur1[6];
+#pragma unroll
+    for (int tt = 0; tt < 6; tt++) {
+        const int t = ASC ? tt : 5 - tt;            // row type processed now
+        const R *f = blk + t * UALM_FW;
+        R v0 = b0[(size_t)(row0 + t) * bst], v1 = 0.0;
+        if (NCOL == 2) v1 = b1[(size_t)(row0 + t) * bst];
+#pragma unroll
+        for (int d = 6; d >= 1; d--) {
+            if (FULL || ((sweep_mask(KIND, t) >> (d - 1)) & 1)) {
+                const R fv = f[ASC ? 6 - d : 6 + d];
+                // neighbour value: ascending kinds use b[i-d], descending kinds x[i+d]
+                const int tn = ASC ? t - d : t + d;
+                const bool incur = ASC ? (tn >= 0) : (tn <= 5);
+                const R w0 = incur ? cur0[ASC ? tn : tn] : prev0[ASC ? tn + 6 : tn - 6];
+                if (fv != 0.0) {
+                    v0 = v0 - fv * w0;
+                    if (NCOL == 2) {
+                        const R w1 = incur ? cur1[tn] : prev1[ASC ? tn + 6 : tn - 6];
+                        v1 = v1 - fv * w1;
+                    }
+                }
+            }
         }
-        b[(size_t)i * st] = v / BAND(A, n6, i, i);
-    }
-    for (int i = n6 - 1; i >= 0; i--) {
-        R v = b[(size_t)i * st];
-        for (int j = min(n6 - 1, i + 6); j > i; j--) {
-            const R l = BAND(A, n6, j, i);
-            if (l != 0.0) v = v - l * b[(size_t)j * st];
+        if (DIV) {
+            const R dg = f[6];
+            v0 = v0 / dg;
+            if (NCOL == 2) v1 = v1 / dg;
         }
-        b[(size_t)i * st] = v;
+        b0[(size_t)(row0 + t) * bst] = v0;
+        cur0[t] = v0;
+        if (NCOL == 2) { b1[(size_t)(row0 + t) * bst] = v1; cur1[t] = v1; }
     }
+#pragma unroll
+    for (int q = 0; q < 6; q++) { prev0[q] = cur0[q]; if (NCOL == 2) prev1[q] = cur1[q]; }
 }
 
-// x -> T powers, A, LU, c   (alm_traj_opt.cpp:293-299 + se2traj.hpp:595-680)
-__device__ void minco_generate(Traj &t, int tid)
+// facA/nA: system of the lanes with sel == 0, facB/nB: system of the lanes with sel == 1 (DUAL only).  Each active lane
+// solves NCOL right-hand sides.  ringA/ringB: 8 blocks x 6 rows x UALM_FW doubles each.
+template <int KIND, int NCOL, bool DUAL>
+__device__ UALM_NOINLINE void sweep(const R *facA, int PA, const R *facB, int PB, R *ringA, R *ringB, R *b0, R *b1, int bst, int sel,
+                                    bool active, int lane)
 {
-    if (tid == 0) {
+    constexpr bool ASC = (KIND == 0 || KIND == 2);
+    constexpr bool LKIND = (KIND == 0 || KIND == 3);   // kinds whose tail block needs the full pattern
+    constexpr int BLK = 6 * UALM_FW;                    // doubles per block (42 x 16 B)
+    const int nb = DUAL ? (PA > PB ? PA : PB) : PA;
+    auto issue = [&](int c) {
+        if (c < PA) {
+            const int blk = ASC ? c : PA - 1 - c;
+            const R *src = facA + (long long)blk * BLK;
+            R *dst = ringA + (c & 7) * BLK;
+            for (int p = lane; p < BLK / 2; p += 32) cp_async16(dst + 2 * p, src + 2 * p);
+        }
+        if (DUAL && c < PB) {
+            const int blk = ASC ? c : PB - 1 - c;
+            const R *src = facB + (long long)blk * BLK;
+            R *dst = ringB + (c & 7) * BLK;
+            for (int p = lane; p < BLK / 2; p += 32) cp_async16(dst + 2 * p, src + 2 * p);
+        }
+        cp_async_commit();
+    };
+    R prev0[6] = {0, 0, 0, 0, 0, 0}, prev1[6] = {0, 0, 0, 0, 0, 0};
+    const int myP = (DUAL && sel) ? PB : PA;
+    R *myring = (DUAL && sel) ? ringB : ringA;
+    issue(0); issue(1); issue(2); issue(3);
+#pragma unroll 1
+    for (int c = 0; c < nb; c++) {
+        issue(c + 4);
+        cp_async_wait<4>();
+        UALM_SYNC();
+        if (active && c < myP) {
+            const int blk = ASC ? c : myP - 1 - c;
+            const R *chunk = myring + (c & 7) * BLK;
+            if (LKIND && blk == myP - 1) sweep_block<KIND, NCOL, true>(chunk, b0, b1, bst, 6 * blk, prev0, prev1);
+            else sweep_block<KIND, NCOL, false>(chunk, b0, b1, bst, 6 * blk, prev0, prev1);
+        }
+        UALM_SYNC();
+    }
+    cp_async_wait<0>();
+}
+
+// x -> T powers, LU of both systems, coefficients c   (alm_traj_opt.cpp:293-299 + se2traj.hpp:595-680)
+__device__ UALM_NOINLINE void minco_generate(Traj &t, int lane)
+{
+    const int N = t.N, M = t.M, nx = 6 * N, ny = 6 * M;
+    if (lane == 0) {
         const R tau = t.x[0];
         const R T = expC2(tau);
-        const R Tx = T / (R)t.N, Ty = T / (R)t.M; // calTfromTau alm_traj_opt.h:257-261
+        const R Tx = T / (R)N, Ty = T / (R)M; // calTfromTau alm_traj_opt.h:257-261
         t.sc[SC_TX1] = Tx; t.sc[SC_TX2] = Tx * Tx; t.sc[SC_TX3] = t.sc[SC_TX2] * Tx; t.sc[SC_TX4] = t.sc[SC_TX2] * t.sc[SC_TX2];
         t.sc[SC_TX5] = t.sc[SC_TX4] * Tx;
         t.sc[SC_TY1] = Ty; t.sc[SC_TY2] = Ty * Ty; t.sc[SC_TY3] = t.sc[SC_TY2] * Ty; t.sc[SC_TY4] = t.sc[SC_TY2] * t.sc[SC_TY2];
         t.sc[SC_TY5] = t.sc[SC_TY4] * Ty;
     }
-    __syncthreads();
-    minco_fill(t, tid);
-    prof_mark(t, tid, PF_FILL);
-    const int warp = tid >> 5, lane = tid & 31;
-    if (warp == 0) banded_lu_warp(t.Axy, 6 * t.N, lane);
-    else if (warp == 1) banded_lu_warp(t.Ayaw, 6 * t.M, lane);
-    __syncthreads();
-    prof_mark(t, tid, PF_LU);
-    if (tid == 0) banded_solve_col(t.Axy, 6 * t.N, t.cxy);
-    else if (tid == 32) banded_solve_col(t.Axy, 6 * t.N, t.cxy + 6 * t.N);
-    else if (tid == 64) banded_solve_col(t.Ayaw, 6 * t.M, t.cyaw);
-    __syncthreads();
-    prof_mark(t, tid, PF_SOLVE);
+    // right-hand sides (se2traj.hpp:615-617, 653, 672-674)
+    for (int q = lane; q < 2 * nx; q += 32) t.cxy[q] = 0.0;
+    for (int q = lane; q < ny; q += 32) t.cyaw[q] = 0.0;
+    UALM_SYNC();
+    const R *bnd = t.pd->bnd;
+    const R *Pxy = t.x + 1, *Pyaw = t.x + 1 + 2 * (N - 1);
+    if (lane < 2) {
+        const int d = lane;
+        t.cxy[0 + d * nx] = bnd[d + 0]; t.cxy[1 + d * nx] = bnd[d + 2]; t.cxy[2 + d * nx] = bnd[d + 4];
+        t.cxy[nx - 3 + d * nx] = bnd[6 + d + 0]; t.cxy[nx - 2 + d * nx] = bnd[6 + d + 2]; t.cxy[nx - 1 + d * nx] = bnd[6 + d + 4];
+    }
+    if (lane == 2) {
+        t.cyaw[0] = bnd[12]; t.cyaw[1] = bnd[13]; t.cyaw[2] = bnd[14];
+        t.cyaw[ny - 3] = bnd[15]; t.cyaw[ny - 2] = bnd[16]; t.cyaw[ny - 1] = bnd[17];
+    }
+    for (int i = lane; i < N - 1; i += 32) {
+        t.cxy[6 * i + 5] = Pxy[2 * i];
+        t.cxy[6 * i + 5 + nx] = Pxy[2 * i + 1];
+    }
+    for (int i = lane; i < M - 1; i += 32) t.cyaw[6 * i + 5] = Pyaw[i];
+    UALM_SYNC();
+    prof_mark(t, lane, PF_FILL);
+    lu_dual(t, lane);
+    prof_mark(t, lane, PF_LU);
+    // lanes 0/1: x / y columns against the xy factors; lane 2: the yaw column, all in lockstep
+    {
+        R *col = lane < 2 ? t.cxy + lane * nx : t.cyaw;
+        sweep<0, 1, true>(t.Fxy, N, t.Fyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, nullptr, 1, lane == 2, lane < 3, lane);
+        sweep<1, 1, true>(t.Fxy, N, t.Fyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, nullptr, 1, lane == 2, lane < 3, lane);
+    }
+    UALM_SYNC();
+    prof_mark(t, lane, PF_SOLVE);
 }
 
-// jerk cost and its (C,T) gradient (se2traj.hpp:697-747).  Per-piece values in parallel, the sum over pieces
-// sequentially by thread 0 (same order as the reference's `energy +=` loop).  Leaves sc[SC_JERKRAW].
-__device__ void jerk_cost_grad(Traj &t, int tid)
+// jerk gradient entries on the fly (se2traj.hpp:719-747): dJ/dc(6i+k, col) and dJ/dT(i)
+__device__ __forceinline__ R jerk_gc(const R *c6, int k, R T1, R T2, R T3, R T4, R T5)
+{
+    const R c3 = c6[3], c4 = c6[4], c5 = c6[5];
+    if (k == 5) return 240.0 * c3 * T3 + 720.0 * c4 * T4 + 1440.0 * c5 * T5;
+    if (k == 4) return 144.0 * c3 * T2 + 384.0 * c4 * T3 + 720.0 * c5 * T4;
+    if (k == 3) return 72.0 * c3 * T1 + 144.0 * c4 * T2 + 240.0 * c5 * T3;
+    return 0.0;
+}
+// per-piece jerk energy and dJ/dT (se2traj.hpp:702-707, 739-744); a = first column block, b = second (or null)
+__device__ __forceinline__ void jerk_piece(const R *a, const R *b, R T1, R T2, R T3, R T4, R T5, R &e, R &gt)
+{
+    R d33, d43, d44, d53, d54, d55;
+    if (b) {
+        d33 = a[3] * a[3] + b[3] * b[3]; d43 = a[4] * a[3] + b[4] * b[3]; d44 = a[4] * a[4] + b[4] * b[4];
+        d53 = a[5] * a[3] + b[5] * b[3]; d54 = a[5] * a[4] + b[5] * b[4]; d55 = a[5] * a[5] + b[5] * b[5];
+    } else {
+        d33 = a[3] * a[3]; d43 = a[4] * a[3]; d44 = a[4] * a[4]; d53 = a[5] * a[3]; d54 = a[5] * a[4]; d55 = a[5] * a[5];
+    }
+    e = 36.0 * d33 * T1 + 144.0 * d43 * T2 + 192.0 * d44 * T3 + 240.0 * d53 * T3 + 720.0 * d54 * T4 + 720.0 * d55 * T5;
+    gt = 36.0 * d33 + 288.0 * d43 * T1 + 576.0 * d44 * T2 + 720.0 * d53 * T2 + 2880.0 * d54 * T3 + 3600.0 * d55 * T4;
+}
+
+// jerk cost (se2traj.hpp:697-710, 852-855): per-piece energies in parallel (parked in gTxy/gTyaw), summed by lane 0 in
+// piece order like the reference's `energy +=` loop.  Leaves sc[SC_JERKRAW].
+__device__ UALM_NOINLINE void jerk_cost(Traj &t, int lane)
 {
     const int N = t.N, M = t.M, nx = 6 * N;
-    for (int q = tid; q < N + M; q += UALM_THREADS) {
-        const bool isy = q >= N;
-        const int i = isy ? q - N : q;
-        const R T1 = t.sc[isy ? SC_TY1 : SC_TX1], T2 = t.sc[isy ? SC_TY2 : SC_TX2], T3 = t.sc[isy ? SC_TY3 : SC_TX3],
-                T4 = t.sc[isy ? SC_TY4 : SC_TX4], T5 = t.sc[isy ? SC_TY5 : SC_TX5];
-        R d33, d43, d44, d53, d54, d55;
-        if (!isy) {
-            const R a3 = t.cxy[6 * i + 3], a4 = t.cxy[6 * i + 4], a5 = t.cxy[6 * i + 5];
-            const R b3 = t.cxy[6 * i + 3 + nx], b4 = t.cxy[6 * i + 4 + nx], b5 = t.cxy[6 * i + 5 + nx];
-            d33 = a3 * a3 + b3 * b3; d43 = a4 * a3 + b4 * b3; d44 = a4 * a4 + b4 * b4;
-            d53 = a5 * a3 + b5 * b3; d54 = a5 * a4 + b5 * b4; d55 = a5 * a5 + b5 * b5;
-            for (int dd = 0; dd < 2; dd++) {
-                const R c3 = t.cxy[6 * i + 3 + dd * nx], c4 = t.cxy[6 * i + 4 + dd * nx], c5 = t.cxy[6 * i + 5 + dd * nx];
-                R *G = t.gCxy_j + dd * nx + 6 * i;
-                G[5] = 240.0 * c3 * T3 + 720.0 * c4 * T4 + 1440.0 * c5 * T5;
-                G[4] = 144.0 * c3 * T2 + 384.0 * c4 * T3 + 720.0 * c5 * T4;
-                G[3] = 72.0 * c3 * T1 + 144.0 * c4 * T2 + 240.0 * c5 * T3;
-                G[0] = 0.0; G[1] = 0.0; G[2] = 0.0;
-            }
-        } else {
-            const R c3 = t.cyaw[6 * i + 3], c4 = t.cyaw[6 * i + 4], c5 = t.cyaw[6 * i + 5];
-            d33 = c3 * c3; d43 = c4 * c3; d44 = c4 * c4; d53 = c5 * c3; d54 = c5 * c4; d55 = c5 * c5;
-            R *G = t.gCyaw_j + 6 * i;
-            G[5] = 240.0 * c3 * T3 + 720.0 * c4 * T4 + 1440.0 * c5 * T5;
-            G[4] = 144.0 * c3 * T2 + 384.0 * c4 * T3 + 720.0 * c5 * T4;
-            G[3] = 72.0 * c3 * T1 + 144.0 * c4 * T2 + 240.0 * c5 * T3;
-            G[0] = 0.0; G[1] = 0.0; G[2] = 0.0;
-        }
-        const R e = 36.0 * d33 * T1 + 144.0 * d43 * T2 + 192.0 * d44 * T3 + 240.0 * d53 * T3 + 720.0 * d54 * T4 + 720.0 * d55 * T5;
-        const R gt = 36.0 * d33 + 288.0 * d43 * T1 + 576.0 * d44 * T2 + 720.0 * d53 * T2 + 2880.0 * d54 * T3 + 3600.0 * d55 * T4;
-        if (!isy) { t.pcx[i] = e; t.gTxy_j[i] = gt; }
-        else { t.pcy[i] = e; t.gTyaw_j[i] = gt; }
+    for (int q = lane; q < N + M; q += 32) {
+        R e, gt;
+        if (q < N) { jerk_piece(t.cxy + 6 * q, t.cxy + 6 * q + nx, t.sc[SC_TX1], t.sc[SC_TX2], t.sc[SC_TX3], t.sc[SC_TX4], t.sc[SC_TX5], e, gt); t.gTxy[q] = e; }
+        else { jerk_piece(t.cyaw + 6 * (q - N), nullptr, t.sc[SC_TY1], t.sc[SC_TY2], t.sc[SC_TY3], t.sc[SC_TY4], t.sc[SC_TY5], e, gt); t.gTyaw[q - N] = e; }
     }
-    __syncthreads();
-    if (tid == 0) {
+    UALM_SYNC();
+    if (lane == 0) {
         R ex = 0.0, ey = 0.0;
-        for (int i = 0; i < N; i++) ex += t.pcx[i];
-        for (int i = 0; i < M; i++) ey += t.pcy[i];
-        t.sc[SC_JERKRAW] = ex + ey; // MINCO_SE2::getTrajJerkCost se2traj.hpp:852-855
+        for (int i = 0; i < N; i++) ex += t.gTxy[i];
+        for (int i = 0; i < M; i++) ey += t.gTyaw[i];
+        t.sc[SC_JERKRAW] = ex + ey;
     }
-    __syncthreads();
+    UALM_SYNC();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -449,7 +565,7 @@ __device__ __forceinline__ bool map_in(const DevMap &m, const R pos[3]) // uneve
     return true;
 }
 
-__device__ void map_get_all_with_grad(const DevMap &m, const R pos[3], R values[7], R grads[7][3])
+__device__ UALM_NOINLINE void map_get_all_with_grad(const DevMap &m, const R pos[3], R values[7], R grads[7][3])
 {
     R rs[3], rg[4][3];
     if (!map_in(m, pos)) {
@@ -471,8 +587,8 @@ __device__ void map_get_all_with_grad(const DevMap &m, const R pos[3], R values[
         diff[1] = (pos[1] - idx_pos[1]) * m.xy_inv;
         {
             R sd, cd;
-            ualm_sincos(pos[2] - idx_pos[2], &sd, &cd);
-            diff[2] = ualm_atan2(sd, cd) * m.yaw_inv;
+            dev_sincos(pos[2] - idx_pos[2], &sd, &cd);
+            diff[2] = dev_atan2(sd, cd) * m.yaw_inv;
         }
         R v[2][2][2][3];
 #pragma unroll
@@ -514,7 +630,7 @@ __device__ void map_get_all_with_grad(const DevMap &m, const R pos[3], R values[
     const R c = sqrt(1.0 - rs[1] * rs[1] - rs[2] * rs[2]);
     const R inv_c = 1.0 / c;
     R syaw, cyaw;
-    ualm_sincos(pos[2], &syaw, &cyaw);
+    dev_sincos(pos[2], &syaw, &cyaw);
     const R xyaw[2] = {cyaw, syaw};
     const R yyaw[2] = {-syaw, cyaw};
     const R tt = xyaw[0] * rs[1] + xyaw[1] * rs[2];
@@ -559,7 +675,7 @@ struct SampleK {
     int yaw_idx;
 };
 
-__device__ void sample_kin(const Traj &t, const DevMap &map, R gravity, int i, R s1, R base_time, SampleK &S)
+__device__ UALM_NOINLINE void sample_kin(const Traj &t, const DevMap &map, R gravity, int i, R s1, R base_time, SampleK &S)
 {
     const int nx = 6 * t.N;
     const R s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
@@ -596,7 +712,7 @@ __device__ void sample_kin(const Traj &t, const DevMap &map, R gravity, int i, R
     S.yaw = yaw; S.dyaw = dyaw; S.d2yaw = d2yaw;
     R se2[3] = {S.pos[0], S.pos[1], yaw};
     normSO2(se2[2]);
-    ualm_sincos(yaw, &S.syaw, &S.cyaw);
+    dev_sincos(yaw, &S.syaw, &S.cyaw);
     S.v_norm = sqrt(S.vel[0] * S.vel[0] + S.vel[1] * S.vel[1]);
     S.lon_acc = S.acc[0] * S.cyaw + S.acc[1] * S.syaw;
     S.lat_acc = S.acc[0] * (-S.syaw) + S.acc[1] * S.cyaw;
@@ -609,25 +725,25 @@ __device__ void sample_kin(const Traj &t, const DevMap &map, R gravity, int i, R
 }
 
 // sample-time tables: s1tab[j] = j-fold accumulated step, base[i] = i-fold accumulated T (alm_traj_opt.cpp:713-714, 987-989)
-__device__ void sample_tables(Traj &t, int tid)
+__device__ UALM_NOINLINE void sample_tables(Traj &t, int lane)
 {
-    if (tid == 0) {
+    if (lane == 0) {
         const R step = t.sc[SC_TX1] / (R)t.K;
         R s1 = 0.0;
         for (int j = 0; j <= t.K; j++) { t.s1tab[j] = s1; s1 += step; }
     }
-    if (tid == 32) {
+    if (lane == 1) {
         R b = 0.0;
         for (int i = 0; i < t.N; i++) { t.base[i] = b; b += t.sc[SC_TX1]; }
     }
-    __syncthreads();
+    UALM_SYNC();
 }
 
 // ---------------------------------------------------------------------------------------------
-// calConstrainCostGrad, phase A: one thread per sample (alm_traj_opt.cpp:710-964).  Writes hx/gx, the 8 cost
+// calConstrainCostGrad, phase A: one lane per sample (alm_traj_opt.cpp:710-964).  Writes hx/gx, the 8 cost
 // terms and the per-sample gradients to the scratch; phase B accumulates them in the reference's order.
 // ---------------------------------------------------------------------------------------------
-__device__ void penalty_samples(Traj &t, const DevMap &map, const DevParams &p, int tid)
+__device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const DevParams &p, int tid)
 {
     const int S = t.S, K = t.K;
     const R rho = t.sc[SC_RHO], scale_fx = t.sc[SC_SCALE_FX];
@@ -768,92 +884,104 @@ __device__ void penalty_samples(Traj &t, const DevMap &map, const DevParams &p, 
         scr[SF_DYAW * S + s] = q.dyaw; scr[SF_D2YAW * S + s] = q.d2yaw;
         scr[SF_S1YAW * S + s] = q.y0[1];
     }
-    __syncthreads();
+    UALM_SYNC();
 }
 
-// phase B: accumulate in the reference's order (alm_traj_opt.cpp:825-946 cost; :969-985 gradients).
-// warp 3 lane 0 runs the sequential cost chain while the other threads do the per-entry gradient sums.
-__device__ void penalty_accumulate(Traj &t, int tid)
+// phase B: accumulate in the reference's order (alm_traj_opt.cpp:825-946 cost; :969-985 gradients).  Homogeneous rounds of
+// 32 tasks: (piece, dim) coefficient-gradient blocks, per-piece time gradients, yaw blocks; then the cost chain.
+__device__ UALM_NOINLINE void penalty_accumulate(Traj &t, int lane)
 {
     const int N = t.N, M = t.M, S = t.S, K = t.K, nx = 6 * N;
     const R *scr = t.scr;
-    if (tid == UALM_THREADS - 32) {
-        R cost = 0.0;
-        for (int s = 0; s < S; s++) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) cost += scr[(SF_COST0 + k) * S + s];
+    // gdCxy: one task per (piece, dim): 6 accumulators over the K+1 samples of the piece, in sample order
+    for (int q = lane; q < 2 * N; q += 32) {
+        const int i = q >> 1, d = q & 1;
+        R acc[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll 4
+        for (int j = 0; j <= K; j++) {
+            const int s = i * (K + 1) + j;
+            const R s1 = t.s1tab[j];
+            const R s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
+            const R gp = scr[(SF_GP + d) * S + s], gv = scr[(SF_GV + d) * S + s], ga = scr[(SF_GA + d) * S + s];
+            acc[0] += (1.0 * gp + 0.0 * gv + 0.0 * ga);
+            acc[1] += (s1 * gp + 1.0 * gv + 0.0 * ga);
+            acc[2] += (s2 * gp + (2.0 * s1) * gv + 2.0 * ga);
+            acc[3] += (s3 * gp + (3.0 * s2) * gv + (6.0 * s1) * ga);
+            acc[4] += (s4 * gp + (4.0 * s3) * gv + (12.0 * s2) * ga);
+            acc[5] += (s5 * gp + (5.0 * s4) * gv + (20.0 * s3) * ga);
         }
-        t.sc[SC_CONSTR] = cost;
-    } else if (tid < UALM_THREADS - 32) {
-        const int nt = UALM_THREADS - 32;
-        // gdCxy: one thread per (piece, dim): 6 accumulators
-        for (int q = tid; q < 2 * N + N + M; q += nt) {
-            if (q < 2 * N) {
-                const int i = q >> 1, d = q & 1;
-                R acc[6] = {0, 0, 0, 0, 0, 0};
-                for (int j = 0; j <= K; j++) {
-                    const int s = i * (K + 1) + j;
-                    const R s1 = t.s1tab[j];
-                    const R s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
-                    const R gp = scr[(SF_GP + d) * S + s], gv = scr[(SF_GV + d) * S + s], ga = scr[(SF_GA + d) * S + s];
-                    acc[0] += (1.0 * gp + 0.0 * gv + 0.0 * ga);
-                    acc[1] += (s1 * gp + 1.0 * gv + 0.0 * ga);
-                    acc[2] += (s2 * gp + (2.0 * s1) * gv + 2.0 * ga);
-                    acc[3] += (s3 * gp + (3.0 * s2) * gv + (6.0 * s1) * ga);
-                    acc[4] += (s4 * gp + (4.0 * s3) * gv + (12.0 * s2) * ga);
-                    acc[5] += (s5 * gp + (5.0 * s4) * gv + (20.0 * s3) * ga);
-                }
 #pragma unroll
-                for (int k = 0; k < 6; k++) t.gCxy[6 * i + k + d * nx] = acc[k];
-            } else if (q < 3 * N) {
-                // gdTxy(i): three += per sample (alm_traj_opt.cpp:827, 973-975, 984-985)
-                const int i = q - 2 * N;
-                R acc = 0.0;
-                for (int j = 0; j <= K; j++) {
-                    const int s = i * (K + 1) + j;
-                    const R alpha = 1.0 / (R)K * (R)j;
-                    acc += scr[SF_USER * S + s] / (R)K;
-                    const R gp0 = scr[(SF_GP + 0) * S + s], gp1 = scr[(SF_GP + 1) * S + s];
-                    const R gv0 = scr[(SF_GV + 0) * S + s], gv1 = scr[(SF_GV + 1) * S + s];
-                    const R ga0 = scr[(SF_GA + 0) * S + s], ga1 = scr[(SF_GA + 1) * S + s];
-                    const R ve0 = scr[(SF_VEL + 0) * S + s], ve1 = scr[(SF_VEL + 1) * S + s];
-                    const R ac0 = scr[(SF_ACC + 0) * S + s], ac1 = scr[(SF_ACC + 1) * S + s];
-                    const R je0 = scr[(SF_JER + 0) * S + s], je1 = scr[(SF_JER + 1) * S + s];
-                    acc += ((gp0 * ve0 + gp1 * ve1) + (gv0 * ac0 + gv1 * ac1) + (ga0 * je0 + ga1 * je1)) * alpha;
-                    const R gy = scr[SF_GYAW * S + s], gdy = scr[SF_GDYAW * S + s];
-                    acc += (gy * scr[SF_DYAW * S + s] + gdy * scr[SF_D2YAW * S + s]) * (alpha + (R)i);
-                }
-                t.gTxy[i] = acc;
-            } else {
-                // gdCyaw block m and gdTyaw(m): samples with yaw_idx == m in ascending sample order
-                const int m = q - 3 * N;
-                R acc[6] = {0, 0, 0, 0, 0, 0};
-                R accT = 0.0;
-                for (int s = 0; s < S; s++) {
-                    if (t.yawidx[s] != m) continue;
-                    const R sy1 = scr[SF_S1YAW * S + s];
-                    const R sy2 = sy1 * sy1, sy3 = sy2 * sy1, sy4 = sy2 * sy2, sy5 = sy4 * sy1;
-                    const R gy = scr[SF_GYAW * S + s], gdy = scr[SF_GDYAW * S + s];
-                    const R gd2 = 0.0;
-                    acc[0] += (1.0 * gy + 0.0 * gdy + 0.0 * gd2);
-                    acc[1] += (sy1 * gy + 1.0 * gdy + 0.0 * gd2);
-                    acc[2] += (sy2 * gy + (2.0 * sy1) * gdy + 2.0 * gd2);
-                    acc[3] += (sy3 * gy + (3.0 * sy2) * gdy + (6.0 * sy1) * gd2);
-                    acc[4] += (sy4 * gy + (4.0 * sy3) * gdy + (12.0 * sy2) * gd2);
-                    acc[5] += (sy5 * gy + (5.0 * sy4) * gdy + (20.0 * sy3) * gd2);
-                    accT += -(gy * scr[SF_DYAW * S + s] + gdy * scr[SF_D2YAW * S + s]) * (R)m;
-                }
+        for (int k = 0; k < 6; k++) t.gCxy[6 * i + k + d * nx] = acc[k];
+    }
+    // gdTxy(i): three += per sample (alm_traj_opt.cpp:827, 973-975, 984-985)
+    for (int i = lane; i < N; i += 32) {
+        R acc = 0.0;
+#pragma unroll 2
+        for (int j = 0; j <= K; j++) {
+            const int s = i * (K + 1) + j;
+            const R alpha = 1.0 / (R)K * (R)j;
+            acc += scr[SF_USER * S + s] / (R)K;
+            const R gp0 = scr[(SF_GP + 0) * S + s], gp1 = scr[(SF_GP + 1) * S + s];
+            const R gv0 = scr[(SF_GV + 0) * S + s], gv1 = scr[(SF_GV + 1) * S + s];
+            const R ga0 = scr[(SF_GA + 0) * S + s], ga1 = scr[(SF_GA + 1) * S + s];
+            const R ve0 = scr[(SF_VEL + 0) * S + s], ve1 = scr[(SF_VEL + 1) * S + s];
+            const R ac0 = scr[(SF_ACC + 0) * S + s], ac1 = scr[(SF_ACC + 1) * S + s];
+            const R je0 = scr[(SF_JER + 0) * S + s], je1 = scr[(SF_JER + 1) * S + s];
+            acc += ((gp0 * ve0 + gp1 * ve1) + (gv0 * ac0 + gv1 * ac1) + (ga0 * je0 + ga1 * je1)) * alpha;
+            const R gy = scr[SF_GYAW * S + s], gdy = scr[SF_GDYAW * S + s];
+            acc += (gy * scr[SF_DYAW * S + s] + gdy * scr[SF_D2YAW * S + s]) * (alpha + (R)i);
+        }
+        t.gTxy[i] = acc;
+    }
+    // gdCyaw block m and gdTyaw(m): the samples with yaw_idx == m in ascending sample order.  yaw_idx is monotone in the
+    // sample index up to rounding at piece boundaries, so only a window around the block's time span is scanned.
+    for (int m = lane; m < M; m += 32) {
+        R acc[6] = {0, 0, 0, 0, 0, 0};
+        R accT = 0.0;
+        const R ratio = (R)(K + 1) * (R)N / (R)M;   // samples per yaw piece
+        int lo = (int)((R)m * ratio) - (K + 3), hi = (int)((R)(m + 1) * ratio) + (K + 3);
+        if (lo < 0) lo = 0;
+        if (hi > S || m == M - 1) hi = S;
+        for (int s = lo; s < hi; s++) {
+            if (t.yawidx[s] != m) continue;
+            const R sy1 = scr[SF_S1YAW * S + s];
+            const R sy2 = sy1 * sy1, sy3 = sy2 * sy1, sy4 = sy2 * sy2, sy5 = sy4 * sy1;
+            const R gy = scr[SF_GYAW * S + s], gdy = scr[SF_GDYAW * S + s];
+            const R gd2 = 0.0;
+            acc[0] += (1.0 * gy + 0.0 * gdy + 0.0 * gd2);
+            acc[1] += (sy1 * gy + 1.0 * gdy + 0.0 * gd2);
+            acc[2] += (sy2 * gy + (2.0 * sy1) * gdy + 2.0 * gd2);
+            acc[3] += (sy3 * gy + (3.0 * sy2) * gdy + (6.0 * sy1) * gd2);
+            acc[4] += (sy4 * gy + (4.0 * sy3) * gdy + (12.0 * sy2) * gd2);
+            acc[5] += (sy5 * gy + (5.0 * sy4) * gdy + (20.0 * sy3) * gd2);
+            accT += -(gy * scr[SF_DYAW * S + s] + gdy * scr[SF_D2YAW * S + s]) * (R)m;
+        }
 #pragma unroll
-                for (int k = 0; k < 6; k++) t.gCyaw[6 * m + k] = acc[k];
-                t.gTyaw[m] = accT;
+        for (int k = 0; k < 6; k++) t.gCyaw[6 * m + k] = acc[k];
+        t.gTyaw[m] = accT;
+    }
+    // cost chain: 8 terms per sample in sample order on lane 0; the terms are fetched 32 samples at a time by all lanes
+    // and handed over by shuffles so the loads stay off the dependent chain
+    {
+        R cost = 0.0;
+        for (int s0 = 0; s0 < S; s0 += 32) {
+            const int s = s0 + lane;
+            R term[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) term[k] = (s < S) ? scr[(SF_COST0 + k) * S + s] : 0.0;
+            const int cnt = min(32, S - s0);
+            for (int l = 0; l < cnt; l++) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) cost += __shfl_sync(0xffffffffu, term[k], l);
             }
         }
+        if (lane == 0) t.sc[SC_CONSTR] = cost;
     }
-    __syncthreads();
+    UALM_SYNC();
 }
 
 // gdT(i) += B1 . adj  (se2traj.hpp:763-814); adj = solved adjoint vector (element stride st), Dim columns
-__device__ R adj_time_term(const R *c, int cst /*col stride of c*/, const R *adj, int ast /*col stride*/, int st, int Dim,
+__device__ UALM_NOINLINE R adj_time_term(const R *c, int cst /*col stride of c*/, const R *adj, int ast /*col stride*/, int st, int Dim,
                            int i, int P, R T1, R T2, R T3, R T4)
 {
     R s = 0.0;
@@ -886,79 +1014,91 @@ __device__ R adj_time_term(const R *c, int cst /*col stride of c*/, const R *adj
 // ---------------------------------------------------------------------------------------------
 // innerCallback (alm_traj_opt.cpp:280-347): x (smem t.x) -> f (sc[SC_F]) and g (smem t.g)
 // ---------------------------------------------------------------------------------------------
-__device__ void evaluate(Traj &t, const DevMap &map, const DevParams &p, int tid)
+__device__ UALM_NOINLINE void evaluate(Traj &t, const DevMap &map, const DevParams &p, int lane)
 {
     const int N = t.N, M = t.M, nx = 6 * N, ny = 6 * M;
     t.n_evals++;
-    prof_mark(t, tid, PF_OTHER);
-    minco_generate(t, tid);
-    jerk_cost_grad(t, tid);
-    prof_mark(t, tid, PF_JERK);
-    sample_tables(t, tid);
-    prof_mark(t, tid, PF_TABLES);
-    penalty_samples(t, map, p, tid);
-    prof_mark(t, tid, PF_SAMPLES);
-    penalty_accumulate(t, tid);
-    prof_mark(t, tid, PF_ACCUM);
-    // combine jerk and constraint gradients (alm_traj_opt.cpp:322-332)
+    prof_mark(t, lane, PF_OTHER);
+    minco_generate(t, lane);
+    jerk_cost(t, lane);
+    prof_mark(t, lane, PF_JERK);
+    sample_tables(t, lane);
+    prof_mark(t, lane, PF_TABLES);
+    penalty_samples(t, map, p, lane);
+    prof_mark(t, lane, PF_SAMPLES);
+    penalty_accumulate(t, lane);
+    prof_mark(t, lane, PF_ACCUM);
+    // combine jerk and constraint gradients (alm_traj_opt.cpp:322-332); the jerk gradient is formed on the fly
     const R scale_fx = t.sc[SC_SCALE_FX];
-    for (int q = tid; q < 2 * nx; q += UALM_THREADS) {
-        R gj = t.gCxy_j[q];
-        if (p.use_scaling) gj *= UALM_SCALE_TRICK_JERK;
-        t.gCxy[q] = gj * scale_fx + t.gCxy[q];
+    {
+        const R T1 = t.sc[SC_TX1], T2 = t.sc[SC_TX2], T3 = t.sc[SC_TX3], T4 = t.sc[SC_TX4], T5 = t.sc[SC_TX5];
+        for (int q = lane; q < 2 * nx; q += 32) {
+            const int d = q >= nx, r = q - d * nx, i = r / 6, k = r - 6 * i;
+            R gj = jerk_gc(t.cxy + d * nx + 6 * i, k, T1, T2, T3, T4, T5);
+            if (p.use_scaling) gj *= UALM_SCALE_TRICK_JERK;
+            t.gCxy[q] = gj * scale_fx + t.gCxy[q];
+        }
+        for (int i = lane; i < N; i += 32) {
+            R e, gj;
+            jerk_piece(t.cxy + 6 * i, t.cxy + 6 * i + nx, T1, T2, T3, T4, T5, e, gj);
+            if (p.use_scaling) gj *= UALM_SCALE_TRICK_JERK;
+            t.gTxy[i] = gj * scale_fx + t.gTxy[i];
+        }
     }
-    for (int q = tid; q < ny; q += UALM_THREADS) {
-        R gj = t.gCyaw_j[q];
-        if (p.use_scaling) gj *= UALM_SCALE_TRICK_JERK;
-        t.gCyaw[q] = gj * scale_fx + t.gCyaw[q];
+    {
+        const R T1 = t.sc[SC_TY1], T2 = t.sc[SC_TY2], T3 = t.sc[SC_TY3], T4 = t.sc[SC_TY4], T5 = t.sc[SC_TY5];
+        for (int q = lane; q < ny; q += 32) {
+            const int i = q / 6, k = q - 6 * i;
+            R gj = jerk_gc(t.cyaw + 6 * i, k, T1, T2, T3, T4, T5);
+            if (p.use_scaling) gj *= UALM_SCALE_TRICK_JERK;
+            t.gCyaw[q] = gj * scale_fx + t.gCyaw[q];
+        }
+        for (int i = lane; i < M; i += 32) {
+            R e, gj;
+            jerk_piece(t.cyaw + 6 * i, nullptr, T1, T2, T3, T4, T5, e, gj);
+            if (p.use_scaling) gj *= UALM_SCALE_TRICK_JERK;
+            t.gTyaw[i] = gj * scale_fx + t.gTyaw[i];
+        }
     }
-    for (int q = tid; q < N; q += UALM_THREADS) {
-        R gj = t.gTxy_j[q];
-        if (p.use_scaling) gj *= UALM_SCALE_TRICK_JERK;
-        t.gTxy[q] = gj * scale_fx + t.gTxy[q];
-    }
-    for (int q = tid; q < M; q += UALM_THREADS) {
-        R gj = t.gTyaw_j[q];
-        if (p.use_scaling) gj *= UALM_SCALE_TRICK_JERK;
-        t.gTyaw[q] = gj * scale_fx + t.gTyaw[q];
-    }
-    __syncthreads();
-    prof_mark(t, tid, PF_COMBINE);
+    UALM_SYNC();
+    prof_mark(t, lane, PF_COMBINE);
     // calGradCTtoQT (se2traj.hpp:751-816): adjoint solves in place in gCxy / gCyaw
-    if (tid == 0) banded_solve_adj_col(t.Axy, nx, t.gCxy, 1);
-    else if (tid == 32) banded_solve_adj_col(t.Axy, nx, t.gCxy + nx, 1);
-    else if (tid == 64) banded_solve_adj_col(t.Ayaw, ny, t.gCyaw, 1);
-    __syncthreads();
-    prof_mark(t, tid, PF_ADJ);
-    for (int q = tid; q < N + M; q += UALM_THREADS) {
+    {
+        R *col = lane < 2 ? t.gCxy + lane * nx : t.gCyaw;
+        sweep<2, 1, true>(t.FTxy, N, t.FTyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, nullptr, 1, lane == 2, lane < 3, lane);
+        sweep<3, 1, true>(t.FTxy, N, t.FTyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, nullptr, 1, lane == 2, lane < 3, lane);
+    }
+    UALM_SYNC();
+    prof_mark(t, lane, PF_ADJ);
+    for (int q = lane; q < N + M; q += 32) {
         if (q < N) t.gTxy[q] += adj_time_term(t.cxy, nx, t.gCxy, nx, 1, 2, q, N, t.sc[SC_TX1], t.sc[SC_TX2], t.sc[SC_TX3], t.sc[SC_TX4]);
         else t.gTyaw[q - N] += adj_time_term(t.cyaw, ny, t.gCyaw, ny, 1, 1, q - N, M, t.sc[SC_TY1], t.sc[SC_TY2], t.sc[SC_TY3], t.sc[SC_TY4]);
     }
-    for (int i = tid; i < N - 1; i += UALM_THREADS) {
+    for (int i = lane; i < N - 1; i += 32) {
         t.g[1 + 2 * i] = t.gCxy[6 * i + 5];
         t.g[1 + 2 * i + 1] = t.gCxy[6 * i + 5 + nx];
     }
-    for (int i = tid; i < M - 1; i += UALM_THREADS) t.g[1 + 2 * (N - 1) + i] = t.gCyaw[6 * i + 5];
-    __syncthreads();
-    if (tid == 0) {
+    for (int i = lane; i < M - 1; i += 32) t.g[1 + 2 * (N - 1) + i] = t.gCyaw[6 * i + 5];
+    UALM_SYNC();
+    if (lane == 0) {
         const R tau = t.x[0];
-        R jerk_cost = t.sc[SC_JERKRAW] * scale_fx;
-        if (p.use_scaling) jerk_cost *= UALM_SCALE_TRICK_JERK;
+        R jerk_c = t.sc[SC_JERKRAW] * scale_fx;
+        if (p.use_scaling) jerk_c *= UALM_SCALE_TRICK_JERK;
         const R tau_cost = p.rho_T * expC2(tau) * scale_fx;
         R sx = 0.0, sy = 0.0;
         for (int i = 0; i < N; i++) sx += t.gTxy[i];
         for (int i = 0; i < M; i++) sy += t.gTyaw[i];
         const R grad_Tsum = p.rho_T * scale_fx + sx / (R)N + sy / (R)M;
         t.g[0] = grad_Tsum * getTtoTauGrad(tau);
-        t.sc[SC_JERK] = jerk_cost; t.sc[SC_TAUCOST] = tau_cost;
-        t.sc[SC_F] = jerk_cost + t.sc[SC_CONSTR] + tau_cost;
+        t.sc[SC_JERK] = jerk_c; t.sc[SC_TAUCOST] = tau_cost;
+        t.sc[SC_F] = jerk_c + t.sc[SC_CONSTR] + tau_cost;
     }
-    __syncthreads();
-    prof_mark(t, tid, PF_TAIL);
+    UALM_SYNC();
+    prof_mark(t, lane, PF_TAIL);
 }
 
 // ---------------------------------------------------------------------------------------------
-// canonical 32-lane dot product (warp 0 only); result on every lane of the calling warp
+// canonical 32-lane dot product; result on every lane
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ R lane_dot(const R *a, const R *b, int n, int lane)
 {
@@ -979,58 +1119,46 @@ __device__ __forceinline__ R lane_absmax(const R *a, int n, int lane)
 
 struct LbfgsOut { int ret; R f; int iters; int max_bound; int sum_bound; };
 
-// lbfgs_optimize + line_search_lewisoverton (lbfgs.hpp:276-389, 439-722).  Control flow is uniform over the
-// CTA: every decision is computed identically by all lanes of warp 0 and broadcast through shared memory.
-__device__ LbfgsOut lbfgs_optimize(Traj &t, const DevMap &map, const DevParams &p, int tid, int *s_flag)
+// lbfgs_optimize + line_search_lewisoverton (lbfgs.hpp:276-389, 439-722).  All 32 lanes follow the same control flow:
+// every scalar the decisions depend on is the result of a warp-uniform reduction or a shared-memory scalar.
+__device__ UALM_NOINLINE LbfgsOut lbfgs_optimize(Traj &t, const DevMap &map, const DevParams &p, int lane)
 {
-    const int n = t.n, m = p.mem_size, lane = tid & 31, warp = tid >> 5;
+    const int n = t.n, m = p.mem_size;
     const R f_dec_coeff = 1.0e-4, s_curv_coeff = 0.9, cautious_factor = 1.0e-6, machine_prec = 1.0e-16;
     const R max_step = 1.0e+20, min_step = p.min_step;
     const int max_linesearch = 64;
     LbfgsOut out; out.ret = 0; out.iters = 0; out.max_bound = 0; out.sum_bound = 0;
 
-    for (int q = tid; q < m; q += UALM_THREADS) { t.lm_alpha[q] = 0.0; t.lm_ys[q] = 0.0; }
-    evaluate(t, map, p, tid);
+    evaluate(t, map, p, lane);
     R fx = t.sc[SC_F];
-    if (tid == 0) t.pf[0] = fx;
-    for (int q = tid; q < n; q += UALM_THREADS) t.d[q] = -t.g[q];
-    __syncthreads();
-    if (warp == 0) {
+    if (lane == 0) t.pf[0] = fx;
+    for (int q = lane; q < n; q += 32) t.d[q] = -t.g[q];
+    UALM_SYNC();
+    {
         const R gn = lane_absmax(t.g, n, lane), xn = lane_absmax(t.x, n, lane);
-        const R dn = lane_dot(t.d, t.d, n, lane);
-        if (lane == 0) {
-            s_flag[0] = (gn / fmax(1.0, xn) < p.g_epsilon) ? 1 : 0;
-            t.sc[SC_STEP] = 1.0 / sqrt(dn);
-        }
+        if (gn / fmax(1.0, xn) < p.g_epsilon) { out.ret = LBFGS_CONVERGENCE; out.f = fx; return out; }
     }
-    __syncthreads();
-    if (s_flag[0]) { out.ret = LBFGS_CONVERGENCE; out.f = fx; return out; }
-    R step = t.sc[SC_STEP];
+    R step = 1.0 / sqrt(lane_dot(t.d, t.d, n, lane));
     int k = 1, end = 0, bound = 0, ret = 0;
     while (true) {
-        for (int q = tid; q < n; q += UALM_THREADS) { t.xp[q] = t.x[q]; t.gp[q] = t.g[q]; }
-        __syncthreads();
+        for (int q = lane; q < n; q += 32) { t.xp[q] = t.x[q]; t.gp[q] = t.g[q]; }
+        UALM_SYNC();
         // ---- line search (lbfgs.hpp:276-389) ----
         int ls;
         {
             int count = 0;
             bool brackt = false, touched = false;
             R stp = step, mu = 0.0, nu = max_step;
-            if (warp == 0) {
-                const R dg = lane_dot(t.gp, t.d, n, lane);
-                if (lane == 0) t.sc[SC_DGINIT] = dg;
-            }
-            __syncthreads();
-            const R dginit = t.sc[SC_DGINIT];
+            const R dginit = lane_dot(t.gp, t.d, n, lane);
             const R finit = fx;
             if (!(stp > 0.0)) ls = LBFGSERR_INVALIDPARAMETERS;
             else if (0.0 < dginit) ls = LBFGSERR_INCREASEGRADIENT;
             else {
                 const R dgtest = f_dec_coeff * dginit, dstest = s_curv_coeff * dginit;
                 while (true) {
-                    for (int q = tid; q < n; q += UALM_THREADS) t.x[q] = t.xp[q] + stp * t.d[q];
-                    __syncthreads();
-                    evaluate(t, map, p, tid);
+                    for (int q = lane; q < n; q += 32) t.x[q] = t.xp[q] + stp * t.d[q];
+                    UALM_SYNC();
+                    evaluate(t, map, p, lane);
                     fx = t.sc[SC_F];
                     ++count;
                     if (isinf(fx) || isnan(fx)) { ls = LBFGSERR_INVALID_FUNCVAL; break; }
@@ -1039,13 +1167,7 @@ __device__ LbfgsOut lbfgs_optimize(Traj &t, const DevMap &map, const DevParams &
                         nu = stp;
                         brackt = true;
                     } else {
-                        if (warp == 0) {
-                            const R dg = lane_dot(t.g, t.d, n, lane);
-                            if (lane == 0) t.sc[SC_TMP0] = dg;
-                        }
-                        __syncthreads();
-                        const R dg = t.sc[SC_TMP0];
-                        __syncthreads();
+                        const R dg = lane_dot(t.g, t.d, n, lane);
                         if (dg < dstest) mu = stp;
                         else { ls = count; break; }
                     }
@@ -1063,88 +1185,122 @@ __device__ LbfgsOut lbfgs_optimize(Traj &t, const DevMap &map, const DevParams &
             }
             step = stp;
         }
+        prof_mark(t, lane, PF_LS);
         if (ls < 0) {
-            for (int q = tid; q < n; q += UALM_THREADS) { t.x[q] = t.xp[q]; t.g[q] = t.gp[q]; }
-            __syncthreads();
+            for (int q = lane; q < n; q += 32) { t.x[q] = t.xp[q]; t.g[q] = t.gp[q]; }
+            UALM_SYNC();
             ret = ls;
             break;
         }
         out.iters++;
         if (k > 1000) { ret = LBFGS_CANCELED; break; } // earlyExit alm_traj_opt.cpp:1016 (k > 1e3)
-        if (warp == 0) {
+        {
             const R gn = lane_absmax(t.g, n, lane), xn = lane_absmax(t.x, n, lane);
-            if (lane == 0) s_flag[0] = (gn / fmax(1.0, xn) < p.g_epsilon) ? 1 : 0;
+            if (gn / fmax(1.0, xn) < p.g_epsilon) { ret = LBFGS_CONVERGENCE; break; }
         }
-        __syncthreads();
-        const int conv = s_flag[0];
-        __syncthreads();
-        if (conv) { ret = LBFGS_CONVERGENCE; break; }
         if (0 < p.past) {
             if (p.past <= k) {
                 const R rate = fabs(t.pf[k % p.past] - fx) / fmax(1.0, fabs(fx));
                 if (rate < p.delta) { ret = LBFGS_STOP; break; }
             }
-            __syncthreads();
-            if (tid == 0) t.pf[k % p.past] = fx;
-            __syncthreads();
+            UALM_SYNC();
+            if (lane == 0) t.pf[k % p.past] = fx;
+            UALM_SYNC();
         }
         if (p.inner_max_iter != 0 && p.inner_max_iter <= k) { ret = LBFGSERR_MAXIMUMITERATION; break; }
         ++k;
         R *sE = t.lm_s + (size_t)end * n, *yE = t.lm_y + (size_t)end * n;
-        for (int q = tid; q < n; q += UALM_THREADS) {
+        for (int q = lane; q < n; q += 32) {
             sE[q] = t.x[q] - t.xp[q];
             yE[q] = t.g[q] - t.gp[q];
             t.d[q] = -t.g[q];
         }
-        __syncthreads();
-        if (warp == 0) {
-            const R ys = lane_dot(yE, sE, n, lane);
-            const R yy = lane_dot(yE, yE, n, lane);
-            const R ss = lane_dot(sE, sE, n, lane);
-            const R gpn = lane_dot(t.gp, t.gp, n, lane);
-            const R cau = ss * sqrt(gpn) * cautious_factor;
-            if (lane == 0) {
-                t.lm_ys[end] = ys;
-                t.sc[SC_YS] = ys; t.sc[SC_YY] = yy;
-                s_flag[0] = (ys > cau) ? 1 : 0;
-            }
-        }
-        __syncthreads();
-        const int upd = s_flag[0];
-        prof_mark(t, tid, PF_LS);
-        if (upd) {
+        UALM_SYNC();
+        const R ys = lane_dot(yE, sE, n, lane);
+        const R yy = lane_dot(yE, yE, n, lane);
+        const R ss = lane_dot(sE, sE, n, lane);
+        const R gpn = lane_dot(t.gp, t.gp, n, lane);
+        const R cau = ss * sqrt(gpn) * cautious_factor;
+        if (lane == 0) t.lm_ys[end] = ys;
+        UALM_SYNC();
+        if (ys > cau) {
             ++bound;
             bound = m < bound ? m : bound;
             if (bound > out.max_bound) out.max_bound = bound;
             out.sum_bound += bound;
             end = (end + 1) % m;
-            if (warp == 0) { // two-loop recursion (lbfgs.hpp:691-710) on warp 0; d lives in shared memory
-                const R ys = t.sc[SC_YS], yy = t.sc[SC_YY];
-                int j = end;
-                for (int i = 0; i < bound; ++i) {
-                    j = (j + m - 1) % m;
-                    const R *sj = t.lm_s + (size_t)j * n, *yj = t.lm_y + (size_t)j * n;
-                    const R a = lane_dot(sj, t.d, n, lane) / t.lm_ys[j];
-                    if (lane == 0) t.lm_alpha[j] = a;
-                    const R na = -a;
-                    for (int q = lane; q < n; q += 32) t.d[q] = t.d[q] + na * yj[q];
-                    __syncwarp();
+            // two-loop recursion (lbfgs.hpp:691-710).  Each lane owns elements lane, lane+32, ... (<= 8 of them) of d in
+            // registers; the history vectors of the NEXT step are loaded while the current step's dot product runs.
+            R dreg[8], sc_[8], yc_[8], sn_[8], yn_[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) { const int q = lane + 32 * e; dreg[e] = q < n ? t.d[q] : 0.0; sn_[e] = 0.0; yn_[e] = 0.0; }
+            int j = (end + m - 1) % m;
+            {
+                const R *sj = t.lm_s + (size_t)j * n, *yj = t.lm_y + (size_t)j * n;
+#pragma unroll
+                for (int e = 0; e < 8; e++) { const int q = lane + 32 * e; sc_[e] = q < n ? sj[q] : 0.0; yc_[e] = q < n ? yj[q] : 0.0; }
+            }
+            R ysj = t.lm_ys[j];
+            for (int i = 0; i < bound; ++i) {
+                const int jn = (j + m - 1) % m;
+                R ysn = 0.0;
+                if (i + 1 < bound) {
+                    const R *sj = t.lm_s + (size_t)jn * n, *yj = t.lm_y + (size_t)jn * n;
+#pragma unroll
+                    for (int e = 0; e < 8; e++) { const int q = lane + 32 * e; if (q < n) { sn_[e] = sj[q]; yn_[e] = yj[q]; } }
+                    ysn = t.lm_ys[jn];
                 }
-                const R scl = ys / yy;
-                for (int q = lane; q < n; q += 32) t.d[q] = t.d[q] * scl;
-                __syncwarp();
-                for (int i = 0; i < bound; ++i) {
-                    const R *sj = t.lm_s + (size_t)j * n, *yj = t.lm_y + (size_t)j * n;
-                    const R beta = lane_dot(yj, t.d, n, lane) / t.lm_ys[j];
-                    const R cf = t.lm_alpha[j] - beta;
-                    for (int q = lane; q < n; q += 32) t.d[q] = t.d[q] + cf * sj[q];
-                    __syncwarp();
-                    j = (j + 1) % m;
+                R pacc = 0.0;
+#pragma unroll
+                for (int e = 0; e < 8; e++) if (lane + 32 * e < n) pacc += sc_[e] * dreg[e];
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) pacc = pacc + __shfl_xor_sync(0xffffffffu, pacc, off);
+                const R a = pacc / ysj;
+                if (lane == 0) t.lm_alpha[j] = a;
+                const R na = -a;
+#pragma unroll
+                for (int e = 0; e < 8; e++) dreg[e] = dreg[e] + na * yc_[e];
+                if (i + 1 < bound) {
+#pragma unroll
+                    for (int e = 0; e < 8; e++) { sc_[e] = sn_[e]; yc_[e] = yn_[e]; }
+                    j = jn; ysj = ysn;
                 }
             }
+            const R scl = ys / yy;
+#pragma unroll
+            for (int e = 0; e < 8; e++) dreg[e] = dreg[e] * scl;
+            UALM_SYNC();
+            // second loop walks oldest -> newest starting at the j where the first loop stopped (vectors still in sc_/yc_)
+            R alj = t.lm_alpha[j];
+            for (int i = 0; i < bound; ++i) {
+                const int jn = (j + 1) % m;
+                R ysn = 0.0, aln = 0.0;
+                if (i + 1 < bound) {
+                    const R *sj = t.lm_s + (size_t)jn * n, *yj = t.lm_y + (size_t)jn * n;
+#pragma unroll
+                    for (int e = 0; e < 8; e++) { const int q = lane + 32 * e; if (q < n) { sn_[e] = sj[q]; yn_[e] = yj[q]; } }
+                    ysn = t.lm_ys[jn]; aln = t.lm_alpha[jn];
+                }
+                R pacc = 0.0;
+#pragma unroll
+                for (int e = 0; e < 8; e++) if (lane + 32 * e < n) pacc += yc_[e] * dreg[e];
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) pacc = pacc + __shfl_xor_sync(0xffffffffu, pacc, off);
+                const R beta = pacc / ysj;
+                const R cf = alj - beta;
+#pragma unroll
+                for (int e = 0; e < 8; e++) dreg[e] = dreg[e] + cf * sc_[e];
+                if (i + 1 < bound) {
+#pragma unroll
+                    for (int e = 0; e < 8; e++) { sc_[e] = sn_[e]; yc_[e] = yn_[e]; }
+                    j = jn; ysj = ysn; alj = aln;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; e++) { const int q = lane + 32 * e; if (q < n) t.d[q] = dreg[e]; }
         }
-        __syncthreads();
-        prof_mark(t, tid, PF_TWOLOOP);
+        UALM_SYNC();
+        prof_mark(t, lane, PF_TWOLOOP);
         step = 1.0;
     }
     out.ret = ret;
@@ -1153,28 +1309,26 @@ __device__ LbfgsOut lbfgs_optimize(Traj &t, const DevMap &map, const DevParams &
 }
 
 // ---------------------------------------------------------------------------------------------
-// initScaling (alm_traj_opt.cpp:349-661): one task per constraint, each task runs the reference's adjoint
-// solves on its own (interleaved) workspace column.  Requires c / LU at x0 (calls minco_generate).
+// initScaling (alm_traj_opt.cpp:349-661): one task per constraint (sample x 7), 32 tasks at a time, each lane running
+// the reference's adjoint solves on its own interleaved workspace column while the whole warp streams the factors.
 // ---------------------------------------------------------------------------------------------
-__device__ void init_scaling(Traj &t, const DevMap &map, const DevParams &p, int tid, R *ws /* per CTA */)
+__device__ UALM_NOINLINE void init_scaling(Traj &t, const DevMap &map, const DevParams &p, int lane)
 {
     const int N = t.N, M = t.M, S = t.S, K = t.K, nx = 6 * N, ny = 6 * M;
-    minco_generate(t, tid);
-    jerk_cost_grad(t, tid); // gdC*_j, gdT*_j = jerk gradient (alm_traj_opt.cpp:370)
-    sample_tables(t, tid);
+    minco_generate(t, lane);
+    sample_tables(t, lane);
     const R tau = t.x[0];
     const R dTdtau = getTtoTauGrad(tau);
     const R step = t.sc[SC_TX1] / (R)K;
-    const R Tx1 = t.sc[SC_TX1], Tx2 = t.sc[SC_TX2], Tx3 = t.sc[SC_TX3], Tx4 = t.sc[SC_TX4];
-    const R Ty1 = t.sc[SC_TY1], Ty2 = t.sc[SC_TY2], Ty3 = t.sc[SC_TY3], Ty4 = t.sc[SC_TY4];
-    const int st = UALM_THREADS;
-    R *wx = ws + tid;                       // x column: rows 0..nx-1 at stride st
-    R *wy = ws + (size_t)nx * st + tid;     // y column
-    R *ww = ws + (size_t)2 * nx * st + tid; // yaw
+    const R Tx1 = t.sc[SC_TX1], Tx2 = t.sc[SC_TX2], Tx3 = t.sc[SC_TX3], Tx4 = t.sc[SC_TX4], Tx5 = t.sc[SC_TX5];
+    const R Ty1 = t.sc[SC_TY1], Ty2 = t.sc[SC_TY2], Ty3 = t.sc[SC_TY3], Ty4 = t.sc[SC_TY4], Ty5 = t.sc[SC_TY5];
+    const int st = 32;
+    R *wx = t.ws + lane;                       // x column: rows 0..nx-1 at stride 32
+    R *wy = t.ws + (size_t)nx * st + lane;     // y column
+    R *ww = t.ws + (size_t)2 * nx * st + lane; // yaw
     R *scr = t.scr;
-    // ---- per-sample pass: f-gradient contributions to the scratch, and the 7 constraint tasks ----
-    for (int s0 = 0; s0 < S; s0 += UALM_THREADS) {
-        const int s = s0 + tid;
+    for (int s0 = 0; s0 < S; s0 += 32) {
+        const int s = s0 + lane;
         const bool act = s < S;
         SampleK q;
         int i = 0, j = 0;
@@ -1184,7 +1338,7 @@ __device__ void init_scaling(Traj &t, const DevMap &map, const DevParams &p, int
             alpha = 1.0 / (R)K * (R)j;
             sample_kin(t, map, p.gravity, i, t.s1tab[j], t.base[i], q);
             t.yawidx[s] = (unsigned short)q.yaw_idx;
-            // user-defined cost -> f gradient pieces (alm_traj_opt.cpp:507-519): stored like a penalty sample
+            // user-defined cost -> f gradient pieces (alm_traj_opt.cpp:507-519), parked in the sample scratch
             const R omega = (j == 0 || j == K) ? 0.5 * p.rho_ter * step : p.rho_ter * step;
             const R sigma = q.tv[6];
             const R user_cost = omega * sigma * sigma;
@@ -1198,7 +1352,7 @@ __device__ void init_scaling(Traj &t, const DevMap &map, const DevParams &p, int
             scr[SF_S1YAW * S + s] = q.y0[1];
         }
         for (int ct = 0; ct < 7; ct++) {
-            R m1 = 0.0, m2 = 0.0, gdTau = 0.0;
+            R dTx = 0.0, dTy = 0.0;
             if (act) {
                 R grad_p[2] = {0, 0}, grad_v[2] = {0, 0}, grad_a[2] = {0, 0}, grad_se2[3];
                 R grad_yaw = 0.0, grad_dyaw = 0.0;
@@ -1247,7 +1401,7 @@ __device__ void init_scaling(Traj &t, const DevMap &map, const DevParams &p, int
                     grad_p[0] = grad_se2[0]; grad_p[1] = grad_se2[1]; grad_yaw = grad_se2[2];
                     usep = 1;
                 }
-                // build this constraint's gdC (only block i / block yaw_idx are non-zero)
+                // this constraint's gdC: only block i / block yaw_idx are non-zero
                 for (int r = 0; r < nx; r++) { wx[(size_t)r * st] = 0.0; wy[(size_t)r * st] = 0.0; }
                 for (int r = 0; r < ny; r++) ww[(size_t)r * st] = 0.0;
                 for (int k = 0; k < 6; k++) {
@@ -1264,7 +1418,6 @@ __device__ void init_scaling(Traj &t, const DevMap &map, const DevParams &p, int
                     ww[(size_t)(6 * q.yaw_idx + k) * st] = 0.0 + vw;
                 }
                 // direct time-gradient terms of this constraint
-                R dTx = 0.0, dTy = 0.0;
                 if (usep && usev) dTx += ((grad_p[0] * q.vel[0] + grad_p[1] * q.vel[1]) + (grad_v[0] * q.acc[0] + grad_v[1] * q.acc[1])) * alpha;
                 else if (usep && usea) dTx += ((grad_p[0] * q.vel[0] + grad_p[1] * q.vel[1]) + (grad_a[0] * q.jer[0] + grad_a[1] * q.jer[1])) * alpha;
                 else if (usep) dTx += (grad_p[0] * q.vel[0] + grad_p[1] * q.vel[1]) * alpha;
@@ -1276,10 +1429,15 @@ __device__ void init_scaling(Traj &t, const DevMap &map, const DevParams &p, int
                     dTy += -(grad_yaw * q.dyaw) * (R)q.yaw_idx;
                     dTx += (grad_yaw * q.dyaw) * (alpha + (R)i);
                 }
-                // adjoint solves (calGradCTtoQT, se2traj.hpp:751-816)
-                banded_solve_adj_col(t.Axy, nx, wx, st);
-                banded_solve_adj_col(t.Axy, nx, wy, st);
-                banded_solve_adj_col(t.Ayaw, ny, ww, st);
+            }
+            UALM_SYNC();
+            // adjoint solves (calGradCTtoQT, se2traj.hpp:751-816), all lanes in lockstep
+            sweep<2, 2, false>(t.FTxy, N, nullptr, 0, t.ring, nullptr, wx, wy, st, 0, act, lane);
+            sweep<3, 2, false>(t.FTxy, N, nullptr, 0, t.ring, nullptr, wx, wy, st, 0, act, lane);
+            sweep<2, 1, false>(t.FTyaw, M, nullptr, 0, t.ring, nullptr, ww, nullptr, st, 0, act, lane);
+            sweep<3, 1, false>(t.FTyaw, M, nullptr, 0, t.ring, nullptr, ww, nullptr, st, 0, act, lane);
+            if (act) {
+                R m1 = 0.0, m2 = 0.0;
                 for (int r = 0; r < N - 1; r++) {
                     m1 = fmax(m1, fabs(wx[(size_t)(6 * r + 5) * st]));
                     m1 = fmax(m1, fabs(wy[(size_t)(6 * r + 5) * st]));
@@ -1288,7 +1446,7 @@ __device__ void init_scaling(Traj &t, const DevMap &map, const DevParams &p, int
                 R sx = 0.0, sy = 0.0;
                 for (int r = 0; r < N; r++) {
                     R gT = (r == i) ? dTx : 0.0;
-                    gT += adj_time_term(t.cxy, nx, ws + tid, nx * st, st, 2, r, N, Tx1, Tx2, Tx3, Tx4);
+                    gT += adj_time_term(t.cxy, nx, t.ws + lane, nx * st, st, 2, r, N, Tx1, Tx2, Tx3, Tx4);
                     sx += gT;
                 }
                 for (int r = 0; r < M; r++) {
@@ -1296,68 +1454,70 @@ __device__ void init_scaling(Traj &t, const DevMap &map, const DevParams &p, int
                     gT += adj_time_term(t.cyaw, ny, ww, 0, st, 1, r, M, Ty1, Ty2, Ty3, Ty4);
                     sy += gT;
                 }
-                gdTau = (sx / (R)N + sy / (R)M) * dTdtau;
+                const R gdTau = (sx / (R)N + sy / (R)M) * dTdtau;
                 t.scale_cx[7 * (size_t)s + ct] = 1.0 / fmax(1.0, fmax(fmax(m1, m2), fabs(gdTau)));
             }
         }
     }
-    __syncthreads();
-    // ---- f gradient: jerk (already in gC*_j / gT*_j) + user cost (alm_traj_opt.cpp:507-519), then adjoint ----
-    {
-        const int nt = UALM_THREADS;
-        for (int qq = tid; qq < 2 * N + N + M; qq += nt) {
-            if (qq < 2 * N) {
-                const int i = qq >> 1, d = qq & 1;
-                R acc[6];
-                for (int k = 0; k < 6; k++) acc[k] = t.gCxy_j[6 * i + k + d * nx];
-                for (int j = 0; j <= K; j++) {
-                    const int s = i * (K + 1) + j;
-                    const R s1 = t.s1tab[j];
-                    const R s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
-                    const R gp = scr[(SF_GP + d) * S + s];
-                    acc[0] += 1.0 * gp; acc[1] += s1 * gp; acc[2] += s2 * gp; acc[3] += s3 * gp; acc[4] += s4 * gp; acc[5] += s5 * gp;
-                }
-                for (int k = 0; k < 6; k++) t.gCxy[6 * i + k + d * nx] = acc[k];
-            } else if (qq < 3 * N) {
-                const int i = qq - 2 * N;
-                R acc = t.gTxy_j[i];
-                for (int j = 0; j <= K; j++) {
-                    const int s = i * (K + 1) + j;
-                    const R alpha = 1.0 / (R)K * (R)j;
-                    acc += scr[SF_USER * S + s] / (R)K;
-                    acc += (scr[(SF_GP + 0) * S + s] * scr[(SF_VEL + 0) * S + s] + scr[(SF_GP + 1) * S + s] * scr[(SF_VEL + 1) * S + s]) * alpha;
-                    acc += (scr[SF_GYAW * S + s] * scr[SF_DYAW * S + s]) * (alpha + (R)i);
-                }
-                t.gTxy[i] = acc;
-            } else {
-                const int m = qq - 3 * N;
-                R acc[6];
-                for (int k = 0; k < 6; k++) acc[k] = t.gCyaw_j[6 * m + k];
-                R accT = t.gTyaw_j[m];
-                for (int s = 0; s < S; s++) {
-                    if (t.yawidx[s] != m) continue;
-                    const R sy1 = scr[SF_S1YAW * S + s];
-                    const R sy2 = sy1 * sy1, sy3 = sy2 * sy1, sy4 = sy2 * sy2, sy5 = sy4 * sy1;
-                    const R gy = scr[SF_GYAW * S + s];
-                    acc[0] += (1.0 * gy); acc[1] += (sy1 * gy); acc[2] += (sy2 * gy); acc[3] += (sy3 * gy); acc[4] += (sy4 * gy); acc[5] += (sy5 * gy);
-                    accT += -(gy * scr[SF_DYAW * S + s]) * (R)m;
-                }
-                for (int k = 0; k < 6; k++) t.gCyaw[6 * m + k] = acc[k];
-                t.gTyaw[m] = accT;
-            }
+    UALM_SYNC();
+    // ---- f gradient: jerk gradient (formed on the fly) + user cost (alm_traj_opt.cpp:507-519), then adjoint ----
+    for (int qq = lane; qq < 2 * N; qq += 32) {
+        const int i = qq >> 1, d = qq & 1;
+        R acc[6];
+        for (int k = 0; k < 6; k++) acc[k] = jerk_gc(t.cxy + d * nx + 6 * i, k, Tx1, Tx2, Tx3, Tx4, Tx5);
+        for (int j = 0; j <= K; j++) {
+            const int s = i * (K + 1) + j;
+            const R s1 = t.s1tab[j];
+            const R s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
+            const R gp = scr[(SF_GP + d) * S + s];
+            acc[0] += 1.0 * gp; acc[1] += s1 * gp; acc[2] += s2 * gp; acc[3] += s3 * gp; acc[4] += s4 * gp; acc[5] += s5 * gp;
         }
+        for (int k = 0; k < 6; k++) t.gCxy[6 * i + k + d * nx] = acc[k];
     }
-    __syncthreads();
-    if (tid == 0) banded_solve_adj_col(t.Axy, nx, t.gCxy, 1);
-    else if (tid == 32) banded_solve_adj_col(t.Axy, nx, t.gCxy + nx, 1);
-    else if (tid == 64) banded_solve_adj_col(t.Ayaw, ny, t.gCyaw, 1);
-    __syncthreads();
-    for (int q = tid; q < N + M; q += UALM_THREADS) {
+    for (int i = lane; i < N; i += 32) {
+        R e, acc;
+        jerk_piece(t.cxy + 6 * i, t.cxy + 6 * i + nx, Tx1, Tx2, Tx3, Tx4, Tx5, e, acc);
+        for (int j = 0; j <= K; j++) {
+            const int s = i * (K + 1) + j;
+            const R alpha = 1.0 / (R)K * (R)j;
+            acc += scr[SF_USER * S + s] / (R)K;
+            acc += (scr[(SF_GP + 0) * S + s] * scr[(SF_VEL + 0) * S + s] + scr[(SF_GP + 1) * S + s] * scr[(SF_VEL + 1) * S + s]) * alpha;
+            acc += (scr[SF_GYAW * S + s] * scr[SF_DYAW * S + s]) * (alpha + (R)i);
+        }
+        t.gTxy[i] = acc;
+    }
+    for (int m = lane; m < M; m += 32) {
+        R acc[6], e, accT;
+        for (int k = 0; k < 6; k++) acc[k] = jerk_gc(t.cyaw + 6 * m, k, Ty1, Ty2, Ty3, Ty4, Ty5);
+        jerk_piece(t.cyaw + 6 * m, nullptr, Ty1, Ty2, Ty3, Ty4, Ty5, e, accT);
+        const R ratio = (R)(K + 1) * (R)N / (R)M;
+        int lo = (int)((R)m * ratio) - (K + 3), hi = (int)((R)(m + 1) * ratio) + (K + 3);
+        if (lo < 0) lo = 0;
+        if (hi > S || m == M - 1) hi = S;
+        for (int s = lo; s < hi; s++) {
+            if (t.yawidx[s] != m) continue;
+            const R sy1 = scr[SF_S1YAW * S + s];
+            const R sy2 = sy1 * sy1, sy3 = sy2 * sy1, sy4 = sy2 * sy2, sy5 = sy4 * sy1;
+            const R gy = scr[SF_GYAW * S + s];
+            acc[0] += (1.0 * gy); acc[1] += (sy1 * gy); acc[2] += (sy2 * gy); acc[3] += (sy3 * gy); acc[4] += (sy4 * gy); acc[5] += (sy5 * gy);
+            accT += -(gy * scr[SF_DYAW * S + s]) * (R)m;
+        }
+        for (int k = 0; k < 6; k++) t.gCyaw[6 * m + k] = acc[k];
+        t.gTyaw[m] = accT;
+    }
+    UALM_SYNC();
+    {
+        R *col = lane < 2 ? t.gCxy + lane * nx : t.gCyaw;
+        sweep<2, 1, true>(t.FTxy, N, t.FTyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, nullptr, 1, lane == 2, lane < 3, lane);
+        sweep<3, 1, true>(t.FTxy, N, t.FTyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, nullptr, 1, lane == 2, lane < 3, lane);
+    }
+    UALM_SYNC();
+    for (int q = lane; q < N + M; q += 32) {
         if (q < N) t.gTxy[q] += adj_time_term(t.cxy, nx, t.gCxy, nx, 1, 2, q, N, Tx1, Tx2, Tx3, Tx4);
         else t.gTyaw[q - N] += adj_time_term(t.cyaw, ny, t.gCyaw, ny, 1, 1, q - N, M, Ty1, Ty2, Ty3, Ty4);
     }
-    __syncthreads();
-    if (tid == 0) {
+    UALM_SYNC();
+    if (lane == 0) {
         R sx = 0.0, sy = 0.0, m1 = 0.0, m2 = 0.0;
         for (int i = 0; i < N; i++) sx += t.gTxy[i];
         for (int i = 0; i < M; i++) sy += t.gTyaw[i];
@@ -1367,104 +1527,111 @@ __device__ void init_scaling(Traj &t, const DevMap &map, const DevParams &p, int
         for (int i = 0; i < M - 1; i++) m2 = fmax(m2, fabs(t.gCyaw[6 * i + 5]));
         t.sc[SC_SCALE_FX] = 1.0 / fmax(1.0, fmax(fmax(m1, m2), fabs(gdTau_fx)));
     }
-    __syncthreads();
+    UALM_SYNC();
 }
 
 // ---------------------------------------------------------------------------------------------
 // set up the Traj view of one problem
 // ---------------------------------------------------------------------------------------------
-__device__ void traj_setup(Traj &t, const BatchPtrs &bp, const DevParams &p, const SmemLayout &L, R *sm, int prob)
+__device__ UALM_NOINLINE void traj_setup(Traj &t, const BatchPtrs &bp, const DevParams &p, const SmemLayout &L, R *sm, int prob)
 {
     const ProbDesc *pd = bp.desc + prob;
     t.pd = pd; t.N = pd->N; t.M = pd->M; t.n = pd->n; t.S = pd->S; t.K = p.int_K;
-    t.sm = sm; t.L = L;
-    t.Axy = sm + L.Axy; t.Ayaw = sm + L.Ayaw; t.cxy = sm + L.cxy; t.cyaw = sm + L.cyaw; t.gCxy = sm + L.gCxy; t.gCyaw = sm + L.gCyaw;
-    t.gCxy_j = sm + L.gCxy_j; t.gCyaw_j = sm + L.gCyaw_j; t.gTxy = sm + L.gTxy; t.gTyaw = sm + L.gTyaw; t.gTxy_j = sm + L.gTxy_j;
-    t.gTyaw_j = sm + L.gTyaw_j; t.pcx = sm + L.pcost_xy; t.pcy = sm + L.pcost_yaw;
-    t.x = sm + L.x; t.g = sm + L.g; t.xp = sm + L.xp; t.gp = sm + L.gp; t.d = sm + L.d; t.lm_alpha = sm + L.lm_alpha; t.lm_ys = sm + L.lm_ys;
-    t.pf = sm + L.pf; t.s1tab = sm + L.s1tab; t.base = sm + L.base; t.sc = sm + L.sc;
+    t.cxy = sm + L.cxy; t.cyaw = sm + L.cyaw; t.gCxy = sm + L.gCxy; t.gCyaw = sm + L.gCyaw; t.gTxy = sm + L.gTxy; t.gTyaw = sm + L.gTyaw;
+    t.x = sm + L.x; t.g = sm + L.g; t.xp = sm + L.xp; t.gp = sm + L.gp; t.d = sm + L.d;
+    t.pf = sm + L.pf; t.s1tab = sm + L.s1tab; t.base = sm + L.base; t.sc = sm + L.sc; t.win = sm + L.win; t.tmpl = sm + L.tmpl; t.ring = sm + L.ring;
     t.yawidx = reinterpret_cast<unsigned short *>(sm + L.yawidx);
     t.lambda = bp.lambda + pd->off_s; t.hx = bp.hx + pd->off_s;
     t.mu = bp.mu + 6 * pd->off_s; t.gx = bp.gx + 6 * pd->off_s;
     t.scale_cx = bp.scale_cx + 7 * pd->off_s;
-    t.lm_s = bp.lm_s ? bp.lm_s + pd->off_hist : nullptr;
-    t.lm_y = bp.lm_y ? bp.lm_y + pd->off_hist : nullptr;
+    t.lm_s = bp.lm_s + pd->off_hist; t.lm_y = bp.lm_y + pd->off_hist;
+    t.lm_alpha = bp.lm_aux + (size_t)prob * 2 * p.mem_size; t.lm_ys = t.lm_alpha + p.mem_size;
     t.scr = bp.scratch + pd->off_scr;
+    {
+        const long long rx = 6 * pd->N + 2 * UALM_FPAD, ry = 6 * pd->M + 2 * UALM_FPAD;
+        R *f = bp.fac + pd->off_fac;
+        t.Fxy = f + UALM_FPAD * UALM_FW;
+        t.FTxy = f + rx * UALM_FW + UALM_FPAD * UALM_FW;
+        t.Fyaw = f + 2 * rx * UALM_FW + UALM_FPAD * UALM_FW;
+        t.FTyaw = f + (2 * rx + ry) * UALM_FW + UALM_FPAD * UALM_FW;
+    }
+    t.ws = bp.ws_scaling ? bp.ws_scaling + pd->off_ws : nullptr;
     t.n_evals = 0;
     __shared__ long long s_prof[UALM_NPROF + 1];
     if (threadIdx.x < UALM_NPROF + 1) s_prof[threadIdx.x] = 0;
     t.prof = s_prof; t.plast = s_prof + UALM_NPROF;
-    __syncthreads();
+    UALM_SYNC();
     if (threadIdx.x == 0) { *t.plast = clock64(); s_prof[PF_TOTAL] = -clock64(); }
 }
 
 // =============================================================================================
-// kernels
+// kernels (one warp = one CTA = one trajectory)
 // =============================================================================================
 
 // full solve: optimizeSE2Traj (alm_traj_opt.cpp:168-278)
 __global__ void __launch_bounds__(UALM_THREADS) solve_kernel(BatchPtrs bp, DevParams p, DevMap map, SmemLayout L)
 {
-    extern __shared__ double sm[];
-    __shared__ int s_flag[4];
-    const int tid = threadIdx.x;
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x;
     const int prob = bp.order[blockIdx.x];
     Traj t;
     traj_setup(t, bp, p, L, sm, prob);
     const int N = t.N, M = t.M, n = t.n, S = t.S;
     // duals and scales (alm_traj_opt.cpp:193-203)
-    for (int q = tid; q < S; q += UALM_THREADS) { t.lambda[q] = 0.0; t.hx[q] = 0.0; }
-    for (int q = tid; q < 6 * S; q += UALM_THREADS) { t.mu[q] = 0.0; t.gx[q] = 0.0; }
-    for (int q = tid; q < 7 * S; q += UALM_THREADS) t.scale_cx[q] = 1.0;
-    for (int q = tid; q < n; q += UALM_THREADS) t.x[q] = bp.x0[t.pd->off_x + q];
-    if (tid == 0) { t.sc[SC_SCALE_FX] = 1.0; t.sc[SC_RHO] = p.rho; }
-    __syncthreads();
-    if (p.use_scaling) init_scaling(t, map, p, tid, bp.ws_scaling + (size_t)blockIdx.x * bp.ws_stride);
-    prof_mark(t, tid, PF_SCALING);
+    for (int q = lane; q < S; q += 32) { t.lambda[q] = 0.0; t.hx[q] = 0.0; }
+    for (int q = lane; q < 6 * S; q += 32) { t.mu[q] = 0.0; t.gx[q] = 0.0; }
+    for (int q = lane; q < 7 * S; q += 32) t.scale_cx[q] = 1.0;
+    for (int q = lane; q < n; q += 32) t.x[q] = bp.x0[t.pd->off_x + q];
+    if (lane == 0) { t.sc[SC_SCALE_FX] = 1.0; t.sc[SC_RHO] = p.rho; }
+    UALM_SYNC();
+    if (p.use_scaling) init_scaling(t, map, p, lane);
+    prof_mark(t, lane, PF_SCALING);
 
     int ret_code = 0, iter = 0, last = 0, iters_total = 0, max_bound = 0, sum_bound = 0;
     R inner_cost = 0.0, rh = 0.0, rg = 0.0;
     while (true) {
-        LbfgsOut lo = lbfgs_optimize(t, map, p, tid, s_flag);
+        LbfgsOut lo = lbfgs_optimize(t, map, p, lane);
         inner_cost = lo.f; last = lo.ret; iters_total += lo.iters;
         if (lo.max_bound > max_bound) max_bound = lo.max_bound;
         sum_bound += lo.sum_bound;
-        __syncthreads();
+        UALM_SYNC();
         if (lo.ret == LBFGS_CONVERGENCE || lo.ret == LBFGS_CANCELED || lo.ret == LBFGS_STOP || lo.ret == LBFGSERR_MAXIMUMITERATION) {
         } else if (lo.ret == LBFGSERR_MAXIMUMLINESEARCH) {
         } else { ret_code = 1; break; }
-        // updateDualVars (alm_traj_opt.h:132-138) with hx/gx of the LAST evaluation (Q1)
+        // updateDualVars (alm_traj_opt.h:132-138) with hx/gx of the LAST evaluation (Q1), judgeConvergence (:140-151)
         const R rho = t.sc[SC_RHO];
-        for (int q = tid; q < S; q += UALM_THREADS) t.lambda[q] += rho * t.hx[q];
-        for (int q = tid; q < 6 * S; q += UALM_THREADS) t.mu[q] = fmax(t.mu[q] + rho * t.gx[q], 0.0);
-        __syncthreads();
         const R rho_new = fmin((1 + p.gamma) * rho, p.beta);
-        // judgeConvergence (alm_traj_opt.h:140-151): max-norms are order independent
         R mh = 0.0, mg = 0.0;
-        for (int q = tid; q < S; q += UALM_THREADS) mh = fmax(mh, fabs(t.hx[q]));
-        for (int q = tid; q < 6 * S; q += UALM_THREADS) mg = fmax(mg, fabs(fmax(t.gx[q], -t.mu[q] / rho_new)));
+        for (int q = lane; q < S; q += 32) {
+            const R h = t.hx[q];
+            t.lambda[q] += rho * h;
+            mh = fmax(mh, fabs(h));
+        }
+        for (int q = lane; q < 6 * S; q += 32) {
+            const R gq = t.gx[q];
+            const R mq = fmax(t.mu[q] + rho * gq, 0.0);
+            t.mu[q] = mq;
+            mg = fmax(mg, fabs(fmax(gq, -mq / rho_new)));
+        }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
             mh = fmax(mh, __shfl_xor_sync(0xffffffffu, mh, off));
             mg = fmax(mg, __shfl_xor_sync(0xffffffffu, mg, off));
         }
-        __shared__ R s_red[2 * (UALM_THREADS / 32)];
-        if ((tid & 31) == 0) { s_red[2 * (tid >> 5)] = mh; s_red[2 * (tid >> 5) + 1] = mg; }
-        __syncthreads();
-        rh = 0.0; rg = 0.0;
-        for (int w = 0; w < UALM_THREADS / 32; w++) { rh = fmax(rh, s_red[2 * w]); rg = fmax(rg, s_red[2 * w + 1]); }
-        if (tid == 0) t.sc[SC_RHO] = rho_new;
-        __syncthreads();
-        prof_mark(t, tid, PF_DUAL);
+        rh = mh; rg = mg;
+        UALM_SYNC();
+        if (lane == 0) t.sc[SC_RHO] = rho_new;
+        UALM_SYNC();
+        prof_mark(t, lane, PF_DUAL);
         if (fmax(rh, rg) < p.epsilon_con) break;
         if ((R)(++iter) > p.max_iter) { ret_code = 2; break; }
     }
     // outputs: coefficients / decision vector of the LAST evaluation's MINCO state (Q1), result record
     const int nx = 6 * N, ny = 6 * M;
-    for (int q = tid; q < 2 * nx; q += UALM_THREADS) bp.c_xy[t.pd->off_cxy + q] = t.cxy[q];
-    for (int q = tid; q < ny; q += UALM_THREADS) bp.c_yaw[t.pd->off_cyaw + q] = t.cyaw[q];
-    for (int q = tid; q < n; q += UALM_THREADS) bp.x[t.pd->off_x + q] = t.x[q];
-    if (tid == 0) {
+    for (int q = lane; q < 2 * nx; q += 32) bp.c_xy[t.pd->off_cxy + q] = t.cxy[q];
+    for (int q = lane; q < ny; q += 32) bp.c_yaw[t.pd->off_cyaw + q] = t.cyaw[q];
+    for (int q = lane; q < n; q += 32) bp.x[t.pd->off_x + q] = t.x[q];
+    if (lane == 0) {
         ualm_result_t r;
         r.ret_code = ret_code; r.outer_iters = iter; r.n_evals = t.n_evals; r.n_lbfgs_iters = iters_total; r.last_lbfgs_ret = last;
         r.max_bound = max_bound; r.sum_bound = sum_bound; r.reserved = 0; r.inner_cost = inner_cost; r.jerk_cost = t.sc[SC_JERKRAW];
@@ -1482,56 +1649,56 @@ __global__ void __launch_bounds__(UALM_THREADS) solve_kernel(BatchPtrs bp, DevPa
 // one innerCallback evaluation per problem at caller-provided x / duals (kernel-level parity)
 __global__ void __launch_bounds__(UALM_THREADS) eval_kernel(BatchPtrs bp, DevParams p, DevMap map, SmemLayout L, R rho)
 {
-    extern __shared__ double sm[];
-    const int tid = threadIdx.x;
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x;
     const int prob = bp.order[blockIdx.x];
     Traj t;
     traj_setup(t, bp, p, L, sm, prob);
-    for (int q = tid; q < t.n; q += UALM_THREADS) t.x[q] = bp.x0[t.pd->off_x + q];
-    if (tid == 0) { t.sc[SC_SCALE_FX] = bp.scale_fx_io[prob]; t.sc[SC_RHO] = rho; }
-    __syncthreads();
-    evaluate(t, map, p, tid);
+    for (int q = lane; q < t.n; q += 32) t.x[q] = bp.x0[t.pd->off_x + q];
+    if (lane == 0) { t.sc[SC_SCALE_FX] = bp.scale_fx_io[prob]; t.sc[SC_RHO] = rho; }
+    UALM_SYNC();
+    evaluate(t, map, p, lane);
     const int nx = 6 * t.N, ny = 6 * t.M;
-    for (int q = tid; q < t.n; q += UALM_THREADS) bp.grad_out[t.pd->off_x + q] = t.g[q];
-    for (int q = tid; q < 2 * nx; q += UALM_THREADS) bp.c_xy[t.pd->off_cxy + q] = t.cxy[q];
-    for (int q = tid; q < ny; q += UALM_THREADS) bp.c_yaw[t.pd->off_cyaw + q] = t.cyaw[q];
-    if (tid == 0) bp.f_out[prob] = t.sc[SC_F];
+    for (int q = lane; q < t.n; q += 32) bp.grad_out[t.pd->off_x + q] = t.g[q];
+    for (int q = lane; q < 2 * nx; q += 32) bp.c_xy[t.pd->off_cxy + q] = t.cxy[q];
+    for (int q = lane; q < ny; q += 32) bp.c_yaw[t.pd->off_cyaw + q] = t.cyaw[q];
+    if (lane == 0) bp.f_out[prob] = t.sc[SC_F];
 }
 
 // initScaling per problem at x0
 __global__ void __launch_bounds__(UALM_THREADS) scaling_kernel(BatchPtrs bp, DevParams p, DevMap map, SmemLayout L)
 {
-    extern __shared__ double sm[];
-    const int tid = threadIdx.x;
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x;
     const int prob = bp.order[blockIdx.x];
     Traj t;
     traj_setup(t, bp, p, L, sm, prob);
-    for (int q = tid; q < t.n; q += UALM_THREADS) t.x[q] = bp.x0[t.pd->off_x + q];
-    if (tid == 0) { t.sc[SC_SCALE_FX] = 1.0; t.sc[SC_RHO] = p.rho; }
-    __syncthreads();
-    init_scaling(t, map, p, tid, bp.ws_scaling + (size_t)blockIdx.x * bp.ws_stride);
-    if (tid == 0) bp.scale_fx_io[prob] = t.sc[SC_SCALE_FX];
+    for (int q = lane; q < t.n; q += 32) t.x[q] = bp.x0[t.pd->off_x + q];
+    if (lane == 0) { t.sc[SC_SCALE_FX] = 1.0; t.sc[SC_RHO] = p.rho; }
+    UALM_SYNC();
+    init_scaling(t, map, p, lane);
+    if (lane == 0) bp.scale_fx_io[prob] = t.sc[SC_SCALE_FX];
 }
 
-// the penalty-sampling phase alone (calConstrainCostGrad samples, alm_traj_opt.cpp:710-964) for roofline timing:
-// MINCO state is generated once, then `reps` sampling passes are run.
+// the penalty-sampling phase alone (calConstrainCostGrad, alm_traj_opt.cpp:663-991) for roofline timing:
+// MINCO state is generated once, then `reps` sampling + accumulation passes are run.
 __global__ void __launch_bounds__(UALM_THREADS) penalty_only_kernel(BatchPtrs bp, DevParams p, DevMap map, SmemLayout L, int reps)
 {
-    extern __shared__ double sm[];
-    const int tid = threadIdx.x;
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x;
     const int prob = bp.order[blockIdx.x];
     Traj t;
     traj_setup(t, bp, p, L, sm, prob);
-    for (int q = tid; q < t.n; q += UALM_THREADS) t.x[q] = bp.x0[t.pd->off_x + q];
-    if (tid == 0) { t.sc[SC_SCALE_FX] = 1.0; t.sc[SC_RHO] = p.rho; }
-    __syncthreads();
-    minco_generate(t, tid);
-    sample_tables(t, tid);
+    for (int q = lane; q < t.n; q += 32) t.x[q] = bp.x0[t.pd->off_x + q];
+    if (lane == 0) { t.sc[SC_SCALE_FX] = 1.0; t.sc[SC_RHO] = p.rho; }
+    UALM_SYNC();
+    minco_generate(t, lane);
+    sample_tables(t, lane);
     for (int r = 0; r < reps; r++) {
-        penalty_samples(t, map, p, tid);
-        penalty_accumulate(t, tid);
+        penalty_samples(t, map, p, lane);
+        penalty_accumulate(t, lane);
     }
-    if (tid == 0) bp.f_out[prob] = t.sc[SC_CONSTR];
+    if (lane == 0) bp.f_out[prob] = t.sc[SC_CONSTR];
 }
 
 // fixed-stride result records for the multi-GPU all-gather
