@@ -1,0 +1,142 @@
+// ualm_traj_opt.hpp -- C++ host-side mirror of the reference's back-end interface, over the C ABI of ualm.h.
+//
+// The reference class is uneven_planner::ALMTrajOpt (back_end/include/back_end/alm_traj_opt.h:21-120):
+//     init(nh), setEnvironment(map), optimizeSE2Traj(initXY, endXY, innerXY, initYaw, endYaw, innerYaw, totalTime) -> int,
+//     getTraj() -> SE2Trajectory
+// This header keeps those names, argument meaning (column-major Eigen layouts) and return codes (0 ok / 1 L-BFGS error /
+// 2 ALM max-iter, alm_traj_opt.cpp:176,252,267) so PlanManager::rcvWpsCallBack (plan_manager.cpp:134-138) compiles against
+// it unchanged when Eigen is present (define UALM_WITH_EIGEN), and adds the batch entry point the GPU is built for.
+// No ROS, no Eigen required: the plain-pointer overloads are always available.  Header-only; link libualm.so.
+#pragma once
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "ualm.h"
+
+#ifdef UALM_WITH_EIGEN
+#include <Eigen/Eigen>
+#endif
+
+namespace uneven_planner_b200 {
+
+// Result container with the reference's Piece / PolyTrajectory / SE2Trajectory conventions (se2traj.hpp:31-150, 255-414):
+// per piece a duration and a Dim x 6 coefficient matrix, HIGHEST power first (MinJerkOpt::getTraj reverses the solver's
+// low->high order, se2traj.hpp:682-695).
+template <int Dim>
+struct Piece {
+    double duration = 0.0;
+    double coeff[Dim][6];                       // coeff[d][0] * t^5 + ... + coeff[d][5]
+    void getValue(double t, double *out) const  // Piece::getValue, se2traj.hpp:106-118
+    {
+        for (int d = 0; d < Dim; d++) {
+            double v = 0.0, tn = 1.0;
+            for (int i = 5; i >= 0; i--) { v += tn * coeff[d][i]; tn *= t; }
+            out[d] = v;
+        }
+    }
+    double getDuration() const { return duration; }
+};
+
+struct SE2Trajectory {
+    std::vector<Piece<2>> pos_traj;
+    std::vector<Piece<1>> yaw_traj;
+    double getTotalDuration() const
+    {
+        double a = 0, b = 0;
+        for (auto &p : pos_traj) a += p.duration;
+        for (auto &p : yaw_traj) b += p.duration;
+        return a < b ? a : b;                   // SE2Trajectory::getTotalDuration, se2traj.hpp:416-419
+    }
+};
+
+// c_xy: 6N x 2 column-major, c_yaw: 6M (solver order, low -> high power), T_total = sum of piece durations
+inline SE2Trajectory make_traj(int N, int M, const double *c_xy, const double *c_yaw, double T_total)
+{
+    SE2Trajectory tr;
+    tr.pos_traj.resize(N);
+    tr.yaw_traj.resize(M);
+    for (int i = 0; i < N; i++) {
+        tr.pos_traj[i].duration = T_total / N;  // uniform durations, alm_traj_opt.h:257-261
+        for (int d = 0; d < 2; d++)
+            for (int k = 0; k < 6; k++) tr.pos_traj[i].coeff[d][5 - k] = c_xy[6 * i + k + d * 6 * N];
+    }
+    for (int i = 0; i < M; i++) {
+        tr.yaw_traj[i].duration = T_total / M;
+        for (int k = 0; k < 6; k++) tr.yaw_traj[i].coeff[0][5 - k] = c_yaw[6 * i + k];
+    }
+    return tr;
+}
+
+class ALMTrajOpt {
+public:
+    // the reference's public parameter members (alm_traj_opt.h:29-53) live in `params`
+    ualm_params_t params;
+
+    explicit ALMTrajOpt(int device = 0, int precision = 64)
+    {
+        ualm_default_params(&params);
+        if (ualm_create(&ctx_, device, precision) != UALM_OK) throw std::runtime_error(std::string("ualm_create: ") + ualm_last_error());
+    }
+    ~ALMTrajOpt() { ualm_destroy(ctx_); }
+    ALMTrajOpt(const ALMTrajOpt &) = delete;
+    ALMTrajOpt &operator=(const ALMTrajOpt &) = delete;
+
+    // ALMTrajOpt::init(nh): the caller fills `params` from its rosparam server, then calls init()
+    void init() { check(ualm_set_params(ctx_, &params), "ualm_set_params"); }
+
+    // ALMTrajOpt::setEnvironment(UnevenMap::Ptr): the map grid (UnevenMap::map_buffer is private in the reference,
+    // uneven_map.h:91, so the maintainer-side binding passes geometry + a float4 view of the cells)
+    void setEnvironment(const ualm_map_geom_t &geom, const float *cells_xyzw) { check(ualm_set_map(ctx_, &geom, cells_xyzw), "ualm_set_map"); }
+
+    // ---- single problem, the reference's call (alm_traj_opt.h:92-98), plain pointers ----
+    // initStateXY/endStateXY: 2x3 column-major; innerPtsXY: 2 x (N-1) column-major; initYaw/endYaw: 3; innerPtsYaw: M-1
+    int optimizeSE2Traj(const double *initStateXY, const double *endStateXY, const double *innerPtsXY, int n_inner_xy,
+                        const double *initYaw, const double *endYaw, const double *innerPtsYaw, int n_inner_yaw, double totalTime)
+    {
+        const int32_t N = n_inner_xy + 1, M = n_inner_yaw + 1;
+        double bnd[18];
+        for (int k = 0; k < 6; k++) { bnd[k] = initStateXY[k]; bnd[6 + k] = endStateXY[k]; }
+        for (int k = 0; k < 3; k++) { bnd[12 + k] = initYaw[k]; bnd[15 + k] = endYaw[k]; }
+        last_N_ = N; last_M_ = M;
+        c_xy_.assign(12 * (size_t)N, 0.0);
+        c_yaw_.assign(6 * (size_t)M, 0.0);
+        check(ualm_solve_batch(ctx_, 1, &N, &M, bnd, &totalTime, innerPtsXY, innerPtsYaw, &last_, c_xy_.data(), c_yaw_.data()), "ualm_solve_batch");
+        return last_.ret_code;
+    }
+    SE2Trajectory getTraj() const { return make_traj(last_N_, last_M_, c_xy_.data(), c_yaw_.data(), last_.total_T); }
+    const ualm_result_t &lastResult() const { return last_; }
+
+#ifdef UALM_WITH_EIGEN
+    // the reference's exact signature (alm_traj_opt.h:92-98)
+    int optimizeSE2Traj(const Eigen::MatrixXd &initStateXY, const Eigen::MatrixXd &endStateXY, const Eigen::MatrixXd &innerPtsXY,
+                        const Eigen::VectorXd &initYaw, const Eigen::VectorXd &endYaw, const Eigen::VectorXd &innerPtsYaw,
+                        const double &totalTime)
+    {
+        return optimizeSE2Traj(initStateXY.data(), endStateXY.data(), innerPtsXY.data(), (int)innerPtsXY.cols(), initYaw.data(),
+                               endYaw.data(), innerPtsYaw.data(), (int)innerPtsYaw.size(), totalTime);
+    }
+#endif
+
+    // ---- batch: B independent optimizeSE2Traj problems, packed as in ualm.h ----
+    void optimizeBatch(int B, const int32_t *N, const int32_t *M, const double *bnd, const double *total_time, const double *inner_xy,
+                       const double *inner_yaw, ualm_result_t *results, double *c_xy, double *c_yaw)
+    {
+        check(ualm_solve_batch(ctx_, B, N, M, bnd, total_time, inner_xy, inner_yaw, results, c_xy, c_yaw), "ualm_solve_batch");
+    }
+
+    ualm_ctx_t *handle() { return ctx_; }
+
+private:
+    static void check(int rc, const char *what)
+    {
+        if (rc != UALM_OK) throw std::runtime_error(std::string(what) + ": " + ualm_last_error());
+    }
+    ualm_ctx_t *ctx_ = nullptr;
+    ualm_result_t last_{};
+    int last_N_ = 0, last_M_ = 0;
+    std::vector<double> c_xy_, c_yaw_;
+};
+
+} // namespace uneven_planner_b200

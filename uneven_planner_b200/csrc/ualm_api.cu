@@ -209,7 +209,7 @@ extern "C" int ualm_upload(ualm_ctx_t *c, int B, const int32_t *N, const int32_t
     CK(c->d_lm_s.ensure(oh)); CK(c->d_lm_y.ensure(oh)); CK(c->d_scr.ensure(oscr));
     CK(c->d_ws.ensure(ows)); CK(c->d_fac.ensure(ofac)); CK(c->d_lm_aux.ensure((size_t)std::max(B, 1) * 2 * m));
     // factor arrays: entries outside the band-in-matrix positions (and the pad rows) are never written and must read 0
-    CK(cudaMemsetAsync(c->d_fac.p, 0, sizeof(double) * std::max<long long>(ofac, 1), c->stream));
+    if (ofac > 0) CK(cudaMemsetAsync(c->d_fac.p, 0, sizeof(double) * ofac, c->stream));
     CK(c->d_prof.ensure((size_t)std::max(B, 1) * UALM_NPROF));
     CK(c->d_cxy.ensure(ocx)); CK(c->d_cyaw.ensure(ocy)); CK(c->d_res.ensure(B)); CK(c->d_f.ensure(B)); CK(c->d_sfx.ensure(B));
     if (B > 0) {

@@ -111,7 +111,7 @@ enum {
 // shared-memory layout (doubles), sized on the host from the batch maxima
 // ---------------------------------------------------------------------------------------------
 struct SmemLayout {
-    int cxy, cyaw, gCxy, gCyaw, gTxy, gTyaw, x, g, xp, gp, d, pf, s1tab, base, sc, win, tmpl, ring, yawidx /* shorts */, total_doubles;
+    int cxy, cyaw, gCxy, gCyaw, gTxy, gTyaw, x, g, xp, gp, d, pf, s1tab, base, sc, win, tmpl, ring, roles /* shorts */, yawidx /* shorts */, total_doubles;
 };
 
 __host__ __device__ inline SmemLayout make_layout(int Nmax, int Mmax, int nmax, int m, int past, int K, int Smax)
@@ -137,6 +137,7 @@ __host__ __device__ inline SmemLayout make_layout(int Nmax, int Mmax, int nmax, 
     L.win = o; o += 2 * 16 * UALM_FW;    // LU sliding windows: 16 row slots per system
     L.tmpl = o; o += 2 * 12 * UALM_FW;   // template rows of A per system
     L.ring = o; o += 2 * 8 * 6 * UALM_FW; // factor prefetch rings: 8 blocks of 6 rows per system
+    L.roles = o; o += (12 * 16 + 3) / 4;  // shorts packed
     L.yawidx = o; o += (Smax + 3) / 4;   // shorts packed
     L.total_doubles = o;
     (void)m;
@@ -146,7 +147,7 @@ __host__ __device__ inline SmemLayout make_layout(int Nmax, int Mmax, int nmax, 
 // scalar slots in sm[L.sc + ...]
 enum {
     SC_TX1 = 0, SC_TX2, SC_TX3, SC_TX4, SC_TX5, SC_TY1, SC_TY2, SC_TY3, SC_TY4, SC_TY5,
-    SC_SCALE_FX, SC_RHO, SC_F, SC_JERK, SC_CONSTR, SC_TAUCOST, SC_JERKRAW
+    SC_SCALE_FX, SC_RHO, SC_F, SC_JERK, SC_CONSTR, SC_TAUCOST, SC_JERKRAW, SC_RTY
 };
 
 struct Traj {
@@ -156,7 +157,7 @@ struct Traj {
     // smem
     R *cxy, *cyaw, *gCxy, *gCyaw, *gTxy, *gTyaw;
     R *x, *g, *xp, *gp, *d, *pf, *s1tab, *base, *sc, *win, *tmpl, *ring;
-    unsigned short *yawidx;
+    unsigned short *yawidx, *roles;
     // global
     R *lambda, *mu, *scale_cx, *hx, *gx, *lm_s, *lm_y, *lm_alpha, *lm_ys, *scr;
     R *Fxy, *FTxy, *Fyaw, *FTyaw;   // row 0 of each factor array
@@ -199,6 +200,21 @@ __device__ __forceinline__ void normSO2(R &yaw) // uneven_map.cpp:64-71
 #define UALM_NOINLINE __noinline__
 __device__ UALM_NOINLINE void dev_sincos(R x, R *s, R *c) { ualm_sincos(x, s, c); }
 __device__ UALM_NOINLINE R dev_atan2(R y, R x) { return ualm_atan2(y, x); }
+
+// a / b given rb = RN(1/b): q0 = a*rb followed by two residual corrections with FMA returns the correctly rounded quotient
+// (Markstein).  Checked bit for bit against IEEE division on 1.8e10 operand pairs on B200 (tools/microbench/fastdiv.cu).
+// Out-of-range quotients and the flagged all-ones divisor (rb = NaN) fall back to the IEEE division.
+__device__ __forceinline__ R div_by_recip(R a, R b, R rb)
+{
+    R q = a * rb;
+    R e = fma(-q, b, a);
+    q = fma(e, rb, q);
+    e = fma(-q, b, a);
+    q = fma(e, rb, q);
+    const R aq = fabs(q);
+    if (!(aq < 1.0e290) || (aq < 1.0e-290 && a != 0.0)) q = a / b;
+    return q;
+}
 
 // ---------------------------------------------------------------------------------------------
 // cp.async (LDGSTS) helpers: 16-byte global -> shared copies that bypass L1 (factors are produced by this warp and
@@ -250,12 +266,40 @@ __device__ UALM_NOINLINE R a_entry(int P, int r, int q, R T1, R T2, R T3, R T4, 
 // supersets of the numerically non-zero entries (exact cancellations make some fill entries 0), so every use keeps the
 // reference's numeric `!= 0` test (banded_system.hpp:74,81,83) and stays bit-identical to the dense-band loops.
 // ---------------------------------------------------------------------------------------------
-__constant__ signed char LU_NM[12] = {2, 3, 4, 4, 4, 3, 1, 2, 3, 2, 1, 0};
-__constant__ signed char LU_MULT[12][4] = {{5, 6, 0, 0}, {4, 5, 6, 0}, {3, 4, 5, 6}, {2, 3, 4, 5}, {1, 2, 3, 4}, {1, 2, 3, 0},
-                                           {3, 0, 0, 0}, {2, 3, 0, 0}, {1, 2, 3, 0}, {1, 2, 0, 0}, {1, 0, 0, 0}, {0, 0, 0, 0}};
-__constant__ signed char LU_NU[12] = {2, 2, 2, 3, 2, 2, 2, 2, 2, 2, 1, 0};
-__constant__ signed char LU_UCOL[12][3] = {{3, 4, 0}, {2, 3, 0}, {1, 2, 0}, {1, 2, 6}, {1, 6, 0}, {4, 5, 0},
-                                           {3, 4, 0}, {2, 3, 0}, {1, 2, 0}, {1, 2, 0}, {1, 0, 0}, {0, 0, 0}};
+__host__ __device__ constexpr int lu_nm(int ty)
+{
+    return ty == 0 ? 2 : ty == 1 ? 3 : ty == 2 ? 4 : ty == 3 ? 4 : ty == 4 ? 4 : ty == 5 ? 3 : ty == 6 ? 1 : ty == 7 ? 2 : ty == 8 ? 3 : ty == 9 ? 2 : ty == 10 ? 1 : 0;
+}
+__host__ __device__ constexpr int lu_nu(int ty)
+{
+    return ty == 3 ? 3 : (ty == 10 ? 1 : (ty == 11 ? 0 : 2));
+}
+// multiplier row offset l of pivot type ty
+__host__ __device__ constexpr int lu_mult(int ty, int l)
+{
+    return ty == 0 ? (l == 0 ? 5 : 6)
+         : ty == 1 ? (l == 0 ? 4 : l == 1 ? 5 : 6)
+         : ty == 2 ? (3 + l)
+         : ty == 3 ? (2 + l)
+         : ty == 4 ? (1 + l)
+         : ty == 5 ? (1 + l)
+         : ty == 6 ? 3
+         : ty == 7 ? (2 + l)
+         : ty == 8 ? (1 + l)
+         : ty == 9 ? (1 + l)
+         : 1;
+}
+// U column offset c of pivot type ty
+__host__ __device__ constexpr int lu_ucol(int ty, int c)
+{
+    return (ty == 0 || ty == 6) ? (3 + c)
+         : (ty == 1 || ty == 7) ? (2 + c)
+         : (ty == 2 || ty == 8 || ty == 9) ? (1 + c)
+         : ty == 3 ? (c == 2 ? 6 : 1 + c)
+         : ty == 4 ? (c == 0 ? 1 : 6)
+         : ty == 5 ? (4 + c)
+         : 1;
+}
 
 // template rows of A: 12 rows x UALM_FW per system: [0..5] junction rows (row index r with (r-3) mod 6 = 0..5), [6..8] head
 // rows 0..2, [9..11] tail rows 6P-3..6P-1.  Filled once per evaluation (the durations are uniform, alm_traj_opt.h:257-261).
@@ -266,10 +310,44 @@ __device__ __forceinline__ int tmpl_index(int r, int n6)
     return (r - 3) % 6;
 }
 
+// rows r0 .. r0+5 of A into the sliding window (entries whose column falls outside the matrix are zero)
+__device__ __forceinline__ void lu_fill6(R *W, const R *TM, int r0, int n6, int hl)
+{
+#pragma unroll 1
+    for (int e = hl; e < 6 * 13; e += 16) {
+        const int rr = e / 13, q = e - 13 * rr, r = r0 + rr;
+        const int c = r - 6 + q;
+        R v = 0.0;
+        if (r < n6 && c >= 0 && c < n6) v = TM[tmpl_index(r, n6) * UALM_FW + q];
+        W[(r & 15) * UALM_FW + q] = v;
+    }
+}
+
+// lane roles of one pivot step, per pivot type and half-warp lane, packed: bits 0-2 multiplier-row offset (7 = the lane that
+// forms the reciprocal of the pivot, 0 = none), bits 3-5 / 6-8 row / column offset of this lane's update entry (column 0 =
+// none), bits 9-10 the lane holding that update's multiplier.  Built once per kernel in shared memory (768 B).
+__device__ __forceinline__ void lu_build_roles(unsigned short *roles, int lane)
+{
+    for (int e = lane; e < 12 * 16; e += 32) {
+        const int ty = e >> 4, hl = e & 15;
+        const int nm = lu_nm(ty), nu = lu_nu(ty);
+        int mo = 0, uo = 0, uc = 0, ul = 0;
+        if (hl < nm) mo = lu_mult(ty, hl);
+        else if (hl == nm) mo = 7;
+        if (hl < nm * nu) {
+            ul = hl / nu;
+            uo = lu_mult(ty, ul);
+            uc = lu_ucol(ty, hl - ul * nu);
+        }
+        roles[e] = (unsigned short)(mo | (uo << 3) | (uc << 6) | (ul << 9));
+    }
+}
+
 // Banded LU without pivoting (banded_system.hpp:66-91) of the xy system (lanes 0..15) and the yaw system (lanes 16..31) in
 // lockstep on two 16-row sliding windows in shared memory.  Element-wise the update sequence is the reference's; within one
-// pivot step the <=4 multipliers and <=12 updates run on different lanes.  Final factors stream to global memory:
-// F[row][q] = LU(row, row-6+q) and FT[col][q] = LU(col-6+q, col).
+// pivot step the <=4 multipliers, the reciprocal of the pivot and the <=12 updates run on different lanes.  Final factors
+// stream to global memory: F[row][q] = LU(row, row-6+q), FT[col][q] = LU(col-6+q, col), F[row][13] = FT[row][13] =
+// RN(1 / LU(row,row)) for the division-free sweeps.  The loop body is kept small on purpose (instruction cache).
 __device__ UALM_NOINLINE void lu_dual(Traj &t, int lane)
 {
     const int sys = lane >> 4, hl = lane & 15;
@@ -277,77 +355,69 @@ __device__ UALM_NOINLINE void lu_dual(Traj &t, int lane)
     R *W = t.win + sys * (16 * UALM_FW);
     const R *TM = t.tmpl + sys * (12 * UALM_FW);
     R *F = sys ? t.Fyaw : t.Fxy, *FT = sys ? t.FTyaw : t.FTxy;
-    // template rows
     {
         const R T1 = t.sc[sys ? SC_TY1 : SC_TX1], T2 = t.sc[sys ? SC_TY2 : SC_TX2], T3 = t.sc[sys ? SC_TY3 : SC_TX3],
                 T4 = t.sc[sys ? SC_TY4 : SC_TX4], T5 = t.sc[sys ? SC_TY5 : SC_TX5];
         R *TMw = t.tmpl + sys * (12 * UALM_FW);
+#pragma unroll 1
         for (int e = hl; e < 12 * 13; e += 16) {
             const int row = e / 13, q = e - 13 * row;
-            // representative row indices in a system with >= 3 pieces; head/tail/junction rows of shorter systems have the
-            // same entries because a_entry only looks at the row type and the column offset
             R v;
-            if (row < 6) v = a_entry(4, 9 + row, q, T1, T2, T3, T4, T5);          // junction i=1 of a 4-piece system
+            if (row < 6) v = a_entry(4, 9 + row, q, T1, T2, T3, T4, T5);          // junction 1 of a 4-piece system
             else if (row < 9) v = (q == 6) ? (row == 8 ? 2.0 : 1.0) : 0.0;        // head rows
             else v = a_entry(4, 21 + (row - 9), q, T1, T2, T3, T4, T5);          // tail rows of a 4-piece system
             TMw[row * UALM_FW + q] = v;
         }
     }
     UALM_SYNC();
-    // window rows 0..7 (entries whose column falls outside the matrix are zeroed)
-    for (int e = hl; e < 8 * 13; e += 16) {
-        const int r = e / 13, q = e - 13 * r;
-        const int c = r - 6 + q;
-        R v = 0.0;
-        if (r < n6 && c >= 0 && c < n6) v = TM[tmpl_index(r, n6) * UALM_FW + q];
-        W[(r & 15) * UALM_FW + q] = v;
-    }
+    lu_fill6(W, TM, 0, n6, hl);
+    lu_fill6(W, TM, 6, n6, hl);
     UALM_SYNC();
     const int nmax6 = 6 * (t.N > t.M ? t.N : t.M);
+    int kmod = 0;
+#pragma unroll 1
     for (int k = 0; k < nmax6; k++) {
         const bool on = k < n6;
-        if (on && (k % 6) == 0) { // bring rows k+8 .. k+13 into the window
-            for (int e = hl; e < 6 * 13; e += 16) {
-                const int rr = e / 13, q = e - 13 * rr, r = k + 8 + rr;
-                const int c = r - 6 + q;
-                R v = 0.0;
-                if (r < n6 && c >= 0 && c < n6) v = TM[tmpl_index(r, n6) * UALM_FW + q];
-                W[(r & 15) * UALM_FW + q] = v;
-            }
-        }
-        const int ty = (k >= n6 - 6) ? 6 + (k - (n6 - 6)) : (k % 6);
+        if (kmod == 0 && on) lu_fill6(W, TM, k + 8, n6, hl);
+        const int ty = (k >= n6 - 6) ? 6 + (k - (n6 - 6)) : kmod;
+        const unsigned role = on ? t.roles[(ty << 4) + hl] : 0u;
+        const int mo = role & 7, uo = (role >> 3) & 7, uc = (role >> 6) & 7, ul = (role >> 9) & 3;
         const R *Wk = W + (k & 15) * UALM_FW;
-        const int nm = on ? LU_NM[ty] : 0, nu = on ? LU_NU[ty] : 0;
         R m = 0.0;
-        if (hl < nm) {
-            const int o = LU_MULT[ty][hl], i = k + o;
-            R *pa = W + (i & 15) * UALM_FW + 6 - o;
-            const R a = *pa;
+        if (mo) {
+            const bool isr = (mo == 7);
+            const int o = isr ? 0 : mo;
+            R *pa = W + ((k + o) & 15) * UALM_FW + 6 - o;
+            const R piv = Wk[6];
+            const R a = isr ? 1.0 : *pa;
             m = a;
-            if (a != 0.0) { m = a / Wk[6]; *pa = m; }
-            F[(size_t)i * UALM_FW + 6 - o] = m;
-            FT[(size_t)k * UALM_FW + 6 + o] = m;
-        } else if (on && hl >= 4 && hl < 11) {
-            const int q = hl - 4;
+            if (a != 0.0) m = a / piv;
+            if (!isr) {
+                *pa = m;
+                F[(size_t)(k + o) * UALM_FW + 6 - o] = m;
+                FT[(size_t)k * UALM_FW + 6 + o] = m;
+            } else {
+                // a divisor with an all-ones significand is the one case the reciprocal-based division cannot round: flag it
+                if ((__double_as_longlong(piv) & 0xFFFFFFFFFFFFFll) == 0xFFFFFFFFFFFFFll) m = __longlong_as_double(0x7ff8000000000000ll);
+                F[(size_t)k * UALM_FW + 13] = m;
+                FT[(size_t)k * UALM_FW + 13] = m;
+            }
+        } else if (on && hl >= 5 && hl < 12) {
+            const int q = hl - 5;
             const R u = Wk[6 + q];
             F[(size_t)k * UALM_FW + 6 + q] = u;
             if (k + q < n6) FT[(size_t)(k + q) * UALM_FW + 6 - q] = u;
         }
-        // updates: lane e < nm*nu handles (multiplier l = e / nu, U column c = e % nu)
-        const int l = (nu > 0) ? hl / nu : 0, cc = (nu > 0) ? hl - l * nu : 0;
-        const R mr = __shfl_sync(0xffffffffu, m, (lane & 16) + (l < 4 ? l : 0));
-        if (hl < nm * nu) {
-            const int o = LU_MULT[ty][l], c = LU_UCOL[ty][cc];
-            const int i = k + o, j = k + c;
-            if (j < n6) {
-                const R u = Wk[6 + c];
-                if (u != 0.0 && mr != 0.0) {
-                    R *pw = W + (i & 15) * UALM_FW + 6 + c - o;
-                    *pw = *pw - mr * u;
-                }
+        const R mr = __shfl_sync(0xffffffffu, m, (lane & 16) + ul);
+        if (uc && k + uc < n6) {
+            const R u = Wk[6 + uc];
+            if (u != 0.0 && mr != 0.0) {
+                R *pw = W + ((k + uo) & 15) * UALM_FW + 6 + uc - uo;
+                *pw = *pw - mr * u;
             }
         }
         UALM_SYNC();
+        if (++kmod == 6) kmod = 0;
     }
 }
 
@@ -397,20 +467,20 @@ __device__ __forceinline__ void sweep_block(const R *blk, R *b0, R *b1, int bst,
                 // neighbour value: ascending kinds use b[i-d], descending kinds x[i+d]
                 const int tn = ASC ? t - d : t + d;
                 const bool incur = ASC ? (tn >= 0) : (tn <= 5);
-                const R w0 = incur ? cur0[ASC ? tn : tn] : prev0[ASC ? tn + 6 : tn - 6];
-                if (fv != 0.0) {
-                    v0 = v0 - fv * w0;
-                    if (NCOL == 2) {
-                        const R w1 = incur ? cur1[tn] : prev1[ASC ? tn + 6 : tn - 6];
-                        v1 = v1 - fv * w1;
-                    }
+                // the reference skips exact-zero factors (banded_system.hpp:103,112,131,139); subtracting 0 * w instead leaves
+                // every value unchanged (at most the sign of an exact zero differs), so no test is needed here
+                const R w0 = incur ? cur0[tn] : prev0[ASC ? tn + 6 : tn - 6];
+                v0 = v0 - fv * w0;
+                if (NCOL == 2) {
+                    const R w1 = incur ? cur1[tn] : prev1[ASC ? tn + 6 : tn - 6];
+                    v1 = v1 - fv * w1;
                 }
             }
         }
         if (DIV) {
-            const R dg = f[6];
-            v0 = v0 / dg;
-            if (NCOL == 2) v1 = v1 / dg;
+            const R dg = f[6], rdg = f[13];
+            v0 = div_by_recip(v0, dg, rdg);
+            if (NCOL == 2) v1 = div_by_recip(v1, dg, rdg);
         }
         b0[(size_t)(row0 + t) * bst] = v0;
         cur0[t] = v0;
@@ -424,7 +494,7 @@ __device__ __forceinline__ void sweep_block(const R *blk, R *b0, R *b1, int bst,
 // solves NCOL right-hand sides.  ringA/ringB: 8 blocks x 6 rows x UALM_FW doubles each.
 template <int KIND, int NCOL, bool DUAL>
 __device__ UALM_NOINLINE void sweep(const R *facA, int PA, const R *facB, int PB, R *ringA, R *ringB, R *b0, R *b1, int bst, int sel,
-                                    bool active, int lane)
+                                    bool active, int lane, int cstart = 0)
 {
     constexpr bool ASC = (KIND == 0 || KIND == 2);
     constexpr bool LKIND = (KIND == 0 || KIND == 3);   // kinds whose tail block needs the full pattern
@@ -448,9 +518,10 @@ __device__ UALM_NOINLINE void sweep(const R *facA, int PA, const R *facB, int PB
     R prev0[6] = {0, 0, 0, 0, 0, 0}, prev1[6] = {0, 0, 0, 0, 0, 0};
     const int myP = (DUAL && sel) ? PB : PA;
     R *myring = (DUAL && sel) ? ringB : ringA;
-    issue(0); issue(1); issue(2); issue(3);
+    // cstart (ascending kinds only): blocks before it hold an all-zero right-hand side, whose solution is zero as well
+    issue(cstart); issue(cstart + 1); issue(cstart + 2); issue(cstart + 3);
 #pragma unroll 1
-    for (int c = 0; c < nb; c++) {
+    for (int c = cstart; c < nb; c++) {
         issue(c + 4);
         cp_async_wait<4>();
         UALM_SYNC();
@@ -513,7 +584,7 @@ __device__ UALM_NOINLINE void minco_generate(Traj &t, int lane)
 }
 
 // jerk gradient entries on the fly (se2traj.hpp:719-747): dJ/dc(6i+k, col) and dJ/dT(i)
-__device__ __forceinline__ R jerk_gc(const R *c6, int k, R T1, R T2, R T3, R T4, R T5)
+__device__ UALM_NOINLINE R jerk_gc(const R *c6, int k, R T1, R T2, R T3, R T4, R T5)
 {
     const R c3 = c6[3], c4 = c6[4], c5 = c6[5];
     if (k == 5) return 240.0 * c3 * T3 + 720.0 * c4 * T4 + 1440.0 * c5 * T5;
@@ -522,7 +593,7 @@ __device__ __forceinline__ R jerk_gc(const R *c6, int k, R T1, R T2, R T3, R T4,
     return 0.0;
 }
 // per-piece jerk energy and dJ/dT (se2traj.hpp:702-707, 739-744); a = first column block, b = second (or null)
-__device__ __forceinline__ void jerk_piece(const R *a, const R *b, R T1, R T2, R T3, R T4, R T5, R &e, R &gt)
+__device__ UALM_NOINLINE void jerk_piece(const R *a, const R *b, R T1, R T2, R T3, R T4, R T5, R &e, R &gt)
 {
     R d33, d43, d44, d53, d54, d55;
     if (b) {
@@ -695,7 +766,7 @@ __device__ UALM_NOINLINE void sample_kin(const Traj &t, const DevMap &map, R gra
     }
     const R Ty = t.sc[SC_TY1];
     const R now_time = s1 + base_time;
-    int yaw_idx = (int)(now_time / Ty);
+    int yaw_idx = (int)div_by_recip(now_time, Ty, t.sc[SC_RTY]);
     if (yaw_idx >= t.M) yaw_idx = t.M - 1;
     S.yaw_idx = yaw_idx;
     const R sy1 = now_time - (R)yaw_idx * Ty;
@@ -736,6 +807,12 @@ __device__ UALM_NOINLINE void sample_tables(Traj &t, int lane)
         R b = 0.0;
         for (int i = 0; i < t.N; i++) { t.base[i] = b; b += t.sc[SC_TX1]; }
     }
+    if (lane == 2) {
+        const R Ty = t.sc[SC_TY1];
+        R r = 1.0 / Ty;
+        if ((__double_as_longlong(Ty) & 0xFFFFFFFFFFFFFll) == 0xFFFFFFFFFFFFFll) r = __longlong_as_double(0x7ff8000000000000ll);
+        t.sc[SC_RTY] = r;
+    }
     UALM_SYNC();
 }
 
@@ -747,6 +824,7 @@ __device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const 
 {
     const int S = t.S, K = t.K;
     const R rho = t.sc[SC_RHO], scale_fx = t.sc[SC_SCALE_FX];
+    const R rrho = ((__double_as_longlong(rho) & 0xFFFFFFFFFFFFFll) == 0xFFFFFFFFFFFFFll) ? __longlong_as_double(0x7ff8000000000000ll) : 1.0 / rho;   // RN(1/rho): x / rho below is formed as div_by_recip(x, rho, rrho), bit-identical to the IEEE quotient
     const R step = t.sc[SC_TX1] / (R)K;
     R *scr = t.scr;
     for (int s = tid; s < S; s += UALM_THREADS) {
@@ -789,7 +867,7 @@ __device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const 
                 scr[(SF_COST0 + 2) * S + s] = gv * (m_ + 0.5 * rho * gv);
                 aug_grad = (rho * gv + m_) * sc7[1];
                 grad_vx2 += aug_grad;
-            } else scr[(SF_COST0 + 2) * S + s] = -0.5 * m_ * m_ / rho;
+            } else scr[(SF_COST0 + 2) * S + s] = div_by_recip(-0.5 * m_ * m_, rho, rrho);
         }
         { // longitude acceleration
             const R m_ = mu6[1];
@@ -799,7 +877,7 @@ __device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const 
                 scr[(SF_COST0 + 3) * S + s] = gv * (m_ + 0.5 * rho * gv);
                 aug_grad = (rho * gv + m_) * sc7[2];
                 grad_ax += aug_grad * 2.0 * ax;
-            } else scr[(SF_COST0 + 3) * S + s] = -0.5 * m_ * m_ / rho;
+            } else scr[(SF_COST0 + 3) * S + s] = div_by_recip(-0.5 * m_ * m_, rho, rrho);
         }
         { // latitude acceleration
             const R m_ = mu6[2];
@@ -809,7 +887,7 @@ __device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const 
                 scr[(SF_COST0 + 4) * S + s] = gv * (m_ + 0.5 * rho * gv);
                 aug_grad = (rho * gv + m_) * sc7[3];
                 grad_ay += aug_grad * 2.0 * ay;
-            } else scr[(SF_COST0 + 4) * S + s] = -0.5 * m_ * m_ / rho;
+            } else scr[(SF_COST0 + 4) * S + s] = div_by_recip(-0.5 * m_ * m_, rho, rrho);
         }
         { // curvature
             const R m_ = mu6[3];
@@ -824,7 +902,7 @@ __device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const 
                 else aug_grad = (rho * gv + m_) * UALM_CUR_SCALE;
                 grad_wz += aug_grad * denominator * 2.0 * wz;
                 grad_vx2 -= aug_grad * curv_snorm * denominator;
-            } else scr[(SF_COST0 + 5) * S + s] = -0.5 * m_ * m_ / rho;
+            } else scr[(SF_COST0 + 5) * S + s] = div_by_recip(-0.5 * m_ * m_, rho, rrho);
         }
         { // attitude
             const R m_ = mu6[4];
@@ -835,7 +913,7 @@ __device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const 
                 const R ag = rho * gv + m_;
 #pragma unroll
                 for (int k = 0; k < 3; k++) grad_se2[k] -= ag * q.tg[4][k] * sc7[5];
-            } else scr[(SF_COST0 + 6) * S + s] = -0.5 * m_ * m_ / rho;
+            } else scr[(SF_COST0 + 6) * S + s] = div_by_recip(-0.5 * m_ * m_, rho, rrho);
         }
         { // surface variation
             const R m_ = mu6[5];
@@ -853,7 +931,7 @@ __device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const 
 #pragma unroll
                     for (int k = 0; k < 3; k++) grad_se2[k] += ag * q.tg[6][k] * UALM_SIG_SCALE;
                 }
-            } else scr[(SF_COST0 + 7) * S + s] = -0.5 * m_ * m_ / rho;
+            } else scr[(SF_COST0 + 7) * S + s] = div_by_recip(-0.5 * m_ * m_, rho, rrho);
         }
         // process with vx, wz, ax (alm_traj_opt.cpp:948-964)
 #pragma unroll
@@ -897,7 +975,7 @@ __device__ UALM_NOINLINE void penalty_accumulate(Traj &t, int lane)
     for (int q = lane; q < 2 * N; q += 32) {
         const int i = q >> 1, d = q & 1;
         R acc[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll 4
+#pragma unroll 1
         for (int j = 0; j <= K; j++) {
             const int s = i * (K + 1) + j;
             const R s1 = t.s1tab[j];
@@ -916,7 +994,7 @@ __device__ UALM_NOINLINE void penalty_accumulate(Traj &t, int lane)
     // gdTxy(i): three += per sample (alm_traj_opt.cpp:827, 973-975, 984-985)
     for (int i = lane; i < N; i += 32) {
         R acc = 0.0;
-#pragma unroll 2
+#pragma unroll 1
         for (int j = 0; j <= K; j++) {
             const int s = i * (K + 1) + j;
             const R alpha = 1.0 / (R)K * (R)j;
@@ -1100,7 +1178,7 @@ __device__ UALM_NOINLINE void evaluate(Traj &t, const DevMap &map, const DevPara
 // ---------------------------------------------------------------------------------------------
 // canonical 32-lane dot product; result on every lane
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ R lane_dot(const R *a, const R *b, int n, int lane)
+__device__ UALM_NOINLINE R lane_dot(const R *a, const R *b, int n, int lane)
 {
     R pacc = 0.0;
     for (int i = lane; i < n; i += 32) pacc += a[i] * b[i];
@@ -1108,7 +1186,7 @@ __device__ __forceinline__ R lane_dot(const R *a, const R *b, int n, int lane)
     for (int off = 16; off >= 1; off >>= 1) pacc = pacc + __shfl_xor_sync(0xffffffffu, pacc, off);
     return pacc;
 }
-__device__ __forceinline__ R lane_absmax(const R *a, int n, int lane)
+__device__ UALM_NOINLINE R lane_absmax(const R *a, int n, int lane)
 {
     R m = 0.0;
     for (int i = lane; i < n; i += 32) m = fmax(m, fabs(a[i]));
@@ -1431,10 +1509,17 @@ __device__ UALM_NOINLINE void init_scaling(Traj &t, const DevMap &map, const Dev
                 }
             }
             UALM_SYNC();
-            // adjoint solves (calGradCTtoQT, se2traj.hpp:751-816), all lanes in lockstep
-            sweep<2, 2, false>(t.FTxy, N, nullptr, 0, t.ring, nullptr, wx, wy, st, 0, act, lane);
+            // adjoint solves (calGradCTtoQT, se2traj.hpp:751-816), all lanes in lockstep; the forward sweeps start at the first
+            // block any lane has a non-zero right-hand side in
+            int bx0 = act ? i : N - 1, by0 = act ? q.yaw_idx : M - 1;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, off));
+                by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, off));
+            }
+            sweep<2, 2, false>(t.FTxy, N, nullptr, 0, t.ring, nullptr, wx, wy, st, 0, act, lane, bx0);
             sweep<3, 2, false>(t.FTxy, N, nullptr, 0, t.ring, nullptr, wx, wy, st, 0, act, lane);
-            sweep<2, 1, false>(t.FTyaw, M, nullptr, 0, t.ring, nullptr, ww, nullptr, st, 0, act, lane);
+            sweep<2, 1, false>(t.FTyaw, M, nullptr, 0, t.ring, nullptr, ww, nullptr, st, 0, act, lane, by0);
             sweep<3, 1, false>(t.FTyaw, M, nullptr, 0, t.ring, nullptr, ww, nullptr, st, 0, act, lane);
             if (act) {
                 R m1 = 0.0, m2 = 0.0;
@@ -1541,6 +1626,8 @@ __device__ UALM_NOINLINE void traj_setup(Traj &t, const BatchPtrs &bp, const Dev
     t.x = sm + L.x; t.g = sm + L.g; t.xp = sm + L.xp; t.gp = sm + L.gp; t.d = sm + L.d;
     t.pf = sm + L.pf; t.s1tab = sm + L.s1tab; t.base = sm + L.base; t.sc = sm + L.sc; t.win = sm + L.win; t.tmpl = sm + L.tmpl; t.ring = sm + L.ring;
     t.yawidx = reinterpret_cast<unsigned short *>(sm + L.yawidx);
+    t.roles = reinterpret_cast<unsigned short *>(sm + L.roles);
+    lu_build_roles(t.roles, threadIdx.x);
     t.lambda = bp.lambda + pd->off_s; t.hx = bp.hx + pd->off_s;
     t.mu = bp.mu + 6 * pd->off_s; t.gx = bp.gx + 6 * pd->off_s;
     t.scale_cx = bp.scale_cx + 7 * pd->off_s;
