@@ -150,7 +150,7 @@ extern "C" int ualm_set_map(ualm_ctx_t *c, const ualm_map_geom_t *g, const float
 static int prepare_launch(ualm_ctx *c)
 {
     c->L = make_layout(c->Nmax, c->Mmax, c->nmax, c->dp.mem_size, c->dp.past, c->dp.int_K, c->Smax);
-    c->smem_bytes = (size_t)c->L.total_doubles * sizeof(double);
+    c->smem_bytes = (size_t)c->L.total_doubles * sizeof(double) * UALM_WPB;
     if (c->smem_bytes > 227 * 1024) return fail(UALM_ELIMIT, "problem too large for shared memory (N/M/int_K too big)");
     CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     CK(cudaFuncSetAttribute(eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
@@ -162,6 +162,7 @@ static int prepare_launch(ualm_ctx *c)
 static BatchPtrs batch_ptrs(ualm_ctx *c)
 {
     BatchPtrs b;
+    b.B = c->B;
     b.desc = c->d_desc.p; b.order = c->d_order.p; b.x0 = c->d_x0.p; b.x = c->d_x.p;
     b.lambda = c->d_lambda.p; b.mu = c->d_mu.p; b.scale_cx = c->d_scale_cx.p; b.hx = c->d_hx.p; b.gx = c->d_gx.p;
     b.lm_s = c->d_lm_s.p; b.lm_y = c->d_lm_y.p; b.lm_aux = c->d_lm_aux.p; b.fac = c->d_fac.p; b.scratch = c->d_scr.p; b.ws_scaling = c->d_ws.p;
@@ -230,7 +231,7 @@ extern "C" int ualm_solve_resident(ualm_ctx_t *c)
     c->last_launches = 0;
     CK(cudaEventRecord(c->ev0, c->stream));
     if (c->B > 0) {
-        solve_kernel<<<c->B, UALM_THREADS, c->smem_bytes, c->stream>>>(batch_ptrs(c), c->dp, c->dm, c->L);
+        solve_kernel<<<(c->B + UALM_WPB - 1) / UALM_WPB, UALM_THREADS * UALM_WPB, c->smem_bytes, c->stream>>>(batch_ptrs(c), c->dp, c->dm, c->L);
         CK(cudaGetLastError());
         c->last_launches = 1;
     }
@@ -319,7 +320,7 @@ extern "C" int ualm_eval_batch(ualm_ctx_t *c, const double *x, const double *lam
     if ((rc = put(c, c->d_scale_cx.p, scale_cx, 7 * c->tot_s, 1.0))) return rc;
     if ((rc = put(c, c->d_sfx.p, scale_fx, c->B, 1.0))) return rc;
     if (c->B > 0) {
-        eval_kernel<<<c->B, UALM_THREADS, c->smem_bytes, c->stream>>>(batch_ptrs(c), c->dp, c->dm, c->L, rho);
+        eval_kernel<<<(c->B + UALM_WPB - 1) / UALM_WPB, UALM_THREADS * UALM_WPB, c->smem_bytes, c->stream>>>(batch_ptrs(c), c->dp, c->dm, c->L, rho);
         CK(cudaGetLastError());
         if (f) CK(cudaMemcpyAsync(f, c->d_f.p, sizeof(double) * c->B, cudaMemcpyDeviceToHost, c->stream));
         if (grad) CK(cudaMemcpyAsync(grad, c->d_grad.p, sizeof(double) * c->tot_x, cudaMemcpyDeviceToHost, c->stream));
@@ -337,7 +338,7 @@ extern "C" int ualm_init_scaling_batch(ualm_ctx_t *c, double *scale_fx, double *
     if (!c || !c->have_batch || !c->have_map) return fail(UALM_ESTATE, "upload and set_map first");
     CK(cudaSetDevice(c->device));
     if (c->B > 0) {
-        scaling_kernel<<<c->B, UALM_THREADS, c->smem_bytes, c->stream>>>(batch_ptrs(c), c->dp, c->dm, c->L);
+        scaling_kernel<<<(c->B + UALM_WPB - 1) / UALM_WPB, UALM_THREADS * UALM_WPB, c->smem_bytes, c->stream>>>(batch_ptrs(c), c->dp, c->dm, c->L);
         CK(cudaGetLastError());
         if (scale_fx) CK(cudaMemcpyAsync(scale_fx, c->d_sfx.p, sizeof(double) * c->B, cudaMemcpyDeviceToHost, c->stream));
         if (scale_cx) CK(cudaMemcpyAsync(scale_cx, c->d_scale_cx.p, sizeof(double) * 7 * c->tot_s, cudaMemcpyDeviceToHost, c->stream));
@@ -355,9 +356,9 @@ extern "C" int ualm_time_penalty_kernel(ualm_ctx_t *c, int reps, float *ms_per_l
     if ((rc = put(c, c->d_lambda.p, nullptr, c->tot_s, 0.0))) return rc;
     if ((rc = put(c, c->d_mu.p, nullptr, 6 * c->tot_s, 0.0))) return rc;
     if ((rc = put(c, c->d_scale_cx.p, nullptr, 7 * c->tot_s, 1.0))) return rc;
-    penalty_only_kernel<<<c->B, UALM_THREADS, c->smem_bytes, c->stream>>>(batch_ptrs(c), c->dp, c->dm, c->L, 1); // warm-up
+    penalty_only_kernel<<<(c->B + UALM_WPB - 1) / UALM_WPB, UALM_THREADS * UALM_WPB, c->smem_bytes, c->stream>>>(batch_ptrs(c), c->dp, c->dm, c->L, 1); // warm-up
     CK(cudaEventRecord(c->ev0, c->stream));
-    penalty_only_kernel<<<c->B, UALM_THREADS, c->smem_bytes, c->stream>>>(batch_ptrs(c), c->dp, c->dm, c->L, reps);
+    penalty_only_kernel<<<(c->B + UALM_WPB - 1) / UALM_WPB, UALM_THREADS * UALM_WPB, c->smem_bytes, c->stream>>>(batch_ptrs(c), c->dp, c->dm, c->L, reps);
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaGetLastError());
     CK(cudaEventSynchronize(c->ev1));
@@ -383,8 +384,12 @@ extern "C" int ualm_profile(ualm_ctx_t *c, int enable, long long *out16)
         std::vector<long long> h((size_t)c->B * UALM_NPROF);
         CK(cudaMemcpyAsync(h.data(), c->d_prof.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        for (int q = 0; q < UALM_NPROF; q++) out16[q] = 0;
-        for (int b = 0; b < c->B; b++) for (int q = 0; q < UALM_NPROF; q++) out16[q] += h[(size_t)b * UALM_NPROF + q];
+        if (enable == 2) { // raw: out16 has room for B x 16 values, rows in launch order
+            for (size_t q = 0; q < h.size(); q++) out16[q] = h[q];
+        } else {
+            for (int q = 0; q < UALM_NPROF; q++) out16[q] = 0;
+            for (int b = 0; b < c->B; b++) for (int q = 0; q < UALM_NPROF; q++) out16[q] += h[(size_t)b * UALM_NPROF + q];
+        }
     }
     c->profile = enable != 0;
     return UALM_OK;

@@ -24,6 +24,7 @@
 #include "ualm_detmath.h"
 
 #define UALM_THREADS 32         // one warp per trajectory
+#define UALM_WPB 4              // independent trajectories (warps) per CTA: spreads them over the 4 SM sub-partitions
 #define UALM_NFIELD 26          // per-sample scratch fields (see SF_* below)
 #define UALM_NPROF 16
 #define UALM_FW 14              // doubles per factor row (13 band entries + 1 pad -> 112 B = 7 x 16 B)
@@ -83,6 +84,7 @@ struct ProbDesc {
 };
 
 struct BatchPtrs {
+    int B;
     const ProbDesc *desc;
     const int *order;        // launch order (largest first); blockIdx.x -> problem index
     const R *x0;             // packed initial decision vectors
@@ -139,7 +141,7 @@ __host__ __device__ inline SmemLayout make_layout(int Nmax, int Mmax, int nmax, 
     L.ring = o; o += 2 * 8 * 6 * UALM_FW; // factor prefetch rings: 8 blocks of 6 rows per system
     L.roles = o; o += (12 * 16 + 3) / 4;  // shorts packed
     L.yawidx = o; o += (Smax + 3) / 4;   // shorts packed
-    L.total_doubles = o;
+    L.total_doubles = (o + 1) & ~1;
     (void)m;
     return L;
 }
@@ -150,14 +152,34 @@ enum {
     SC_SCALE_FX, SC_RHO, SC_F, SC_JERK, SC_CONSTR, SC_TAUCOST, SC_JERKRAW, SC_RTY
 };
 
+// Handles to shared memory: a 32-bit element offset into the kernel's dynamic shared array.  Accesses through them compile to
+// LDS/STS with 32-bit address arithmetic (plain `double*` members would become generic loads: the pointer provenance is lost
+// across the __noinline__ calls).
+extern __shared__ __align__(16) double ualm_smem[];
+struct SPtr {
+    int off;
+    __device__ __forceinline__ double &operator[](int i) const { return ualm_smem[off + i]; }
+    __device__ __forceinline__ double &operator*() const { return ualm_smem[off]; }
+    __device__ __forceinline__ SPtr operator+(int d) const { return SPtr{off + d}; }
+    __device__ __forceinline__ double *ptr() const { return ualm_smem + off; }
+};
+struct SPtrU16 {
+    int off;   // in unsigned shorts
+    __device__ __forceinline__ unsigned short &operator[](int i) const { return reinterpret_cast<unsigned short *>(ualm_smem)[off + i]; }
+};
+// element access that works for both handle kinds
+__device__ __forceinline__ double &at(SPtr p, int i) { return p[i]; }
+__device__ __forceinline__ double &at(double *p, int i) { return p[i]; }
+__device__ __forceinline__ const double &at(const double *p, int i) { return p[i]; }
+
 struct Traj {
     // problem
     int N, M, n, S, K;
     const ProbDesc *pd;
     // smem
-    R *cxy, *cyaw, *gCxy, *gCyaw, *gTxy, *gTyaw;
-    R *x, *g, *xp, *gp, *d, *pf, *s1tab, *base, *sc, *win, *tmpl, *ring;
-    unsigned short *yawidx, *roles;
+    SPtr cxy, cyaw, gCxy, gCyaw, gTxy, gTyaw;
+    SPtr x, g, xp, gp, d, pf, s1tab, base, sc, win, tmpl, ring;
+    SPtrU16 yawidx, roles;
     // global
     R *lambda, *mu, *scale_cx, *hx, *gx, *lm_s, *lm_y, *lm_alpha, *lm_ys, *scr;
     R *Fxy, *FTxy, *Fyaw, *FTyaw;   // row 0 of each factor array
@@ -311,7 +333,7 @@ __device__ __forceinline__ int tmpl_index(int r, int n6)
 }
 
 // rows r0 .. r0+5 of A into the sliding window (entries whose column falls outside the matrix are zero)
-__device__ __forceinline__ void lu_fill6(R *W, const R *TM, int r0, int n6, int hl)
+__device__ __forceinline__ void lu_fill6(SPtr W, SPtr TM, int r0, int n6, int hl)
 {
 #pragma unroll 1
     for (int e = hl; e < 6 * 13; e += 16) {
@@ -326,7 +348,7 @@ __device__ __forceinline__ void lu_fill6(R *W, const R *TM, int r0, int n6, int 
 // lane roles of one pivot step, per pivot type and half-warp lane, packed: bits 0-2 multiplier-row offset (7 = the lane that
 // forms the reciprocal of the pivot, 0 = none), bits 3-5 / 6-8 row / column offset of this lane's update entry (column 0 =
 // none), bits 9-10 the lane holding that update's multiplier.  Built once per kernel in shared memory (768 B).
-__device__ __forceinline__ void lu_build_roles(unsigned short *roles, int lane)
+__device__ __forceinline__ void lu_build_roles(SPtrU16 roles, int lane)
 {
     for (int e = lane; e < 12 * 16; e += 32) {
         const int ty = e >> 4, hl = e & 15;
@@ -352,13 +374,13 @@ __device__ UALM_NOINLINE void lu_dual(Traj &t, int lane)
 {
     const int sys = lane >> 4, hl = lane & 15;
     const int P = sys ? t.M : t.N, n6 = 6 * P;
-    R *W = t.win + sys * (16 * UALM_FW);
-    const R *TM = t.tmpl + sys * (12 * UALM_FW);
+    const SPtr W = t.win + sys * (16 * UALM_FW);
+    const SPtr TM = t.tmpl + sys * (12 * UALM_FW);
     R *F = sys ? t.Fyaw : t.Fxy, *FT = sys ? t.FTyaw : t.FTxy;
     {
         const R T1 = t.sc[sys ? SC_TY1 : SC_TX1], T2 = t.sc[sys ? SC_TY2 : SC_TX2], T3 = t.sc[sys ? SC_TY3 : SC_TX3],
                 T4 = t.sc[sys ? SC_TY4 : SC_TX4], T5 = t.sc[sys ? SC_TY5 : SC_TX5];
-        R *TMw = t.tmpl + sys * (12 * UALM_FW);
+        const SPtr TMw = t.tmpl + sys * (12 * UALM_FW);
 #pragma unroll 1
         for (int e = hl; e < 12 * 13; e += 16) {
             const int row = e / 13, q = e - 13 * row;
@@ -382,12 +404,12 @@ __device__ UALM_NOINLINE void lu_dual(Traj &t, int lane)
         const int ty = (k >= n6 - 6) ? 6 + (k - (n6 - 6)) : kmod;
         const unsigned role = on ? t.roles[(ty << 4) + hl] : 0u;
         const int mo = role & 7, uo = (role >> 3) & 7, uc = (role >> 6) & 7, ul = (role >> 9) & 3;
-        const R *Wk = W + (k & 15) * UALM_FW;
+        const SPtr Wk = W + (k & 15) * UALM_FW;
         R m = 0.0;
         if (mo) {
             const bool isr = (mo == 7);
             const int o = isr ? 0 : mo;
-            R *pa = W + ((k + o) & 15) * UALM_FW + 6 - o;
+            const SPtr pa = W + (((k + o) & 15) * UALM_FW + 6 - o);
             const R piv = Wk[6];
             const R a = isr ? 1.0 : *pa;
             m = a;
@@ -412,7 +434,7 @@ __device__ UALM_NOINLINE void lu_dual(Traj &t, int lane)
         if (uc && k + uc < n6) {
             const R u = Wk[6 + uc];
             if (u != 0.0 && mr != 0.0) {
-                R *pw = W + ((k + uo) & 15) * UALM_FW + 6 + uc - uo;
+                const SPtr pw = W + (((k + uo) & 15) * UALM_FW + 6 + uc - uo);
                 *pw = *pw - mr * u;
             }
         }
@@ -448,8 +470,8 @@ __host__ __device__ constexpr int sweep_mask(int kind, int t)
                   >> (6 * t)) & 0x3f);
 }
 
-template <int KIND, int NCOL, bool FULL>
-__device__ __forceinline__ void sweep_block(const R *blk, R *b0, R *b1, int bst, int row0, R (&prev0)[6], R (&prev1)[6])
+template <int KIND, int NCOL, bool FULL, class BP>
+__device__ __forceinline__ void sweep_block(SPtr blk, BP b0, BP b1, int bst, int row0, R (&prev0)[6], R (&prev1)[6])
 {
     constexpr bool ASC = (KIND == 0 || KIND == 2);
     constexpr bool DIV = (KIND == 1 || KIND == 2);
@@ -457,9 +479,9 @@ __device__ __forceinline__ void sweep_block(const R *blk, R *b0, R *b1, int bst,
 #pragma unroll
     for (int tt = 0; tt < 6; tt++) {
         const int t = ASC ? tt : 5 - tt;            // row type processed now
-        const R *f = blk + t * UALM_FW;
-        R v0 = b0[(size_t)(row0 + t) * bst], v1 = 0.0;
-        if (NCOL == 2) v1 = b1[(size_t)(row0 + t) * bst];
+        const SPtr f = blk + t * UALM_FW;
+        R v0 = at(b0, (row0 + t) * bst), v1 = 0.0;
+        if (NCOL == 2) v1 = at(b1, (row0 + t) * bst);
 #pragma unroll
         for (int d = 6; d >= 1; d--) {
             if (FULL || ((sweep_mask(KIND, t) >> (d - 1)) & 1)) {
@@ -482,9 +504,9 @@ __device__ __forceinline__ void sweep_block(const R *blk, R *b0, R *b1, int bst,
             v0 = div_by_recip(v0, dg, rdg);
             if (NCOL == 2) v1 = div_by_recip(v1, dg, rdg);
         }
-        b0[(size_t)(row0 + t) * bst] = v0;
+        at(b0, (row0 + t) * bst) = v0;
         cur0[t] = v0;
-        if (NCOL == 2) { b1[(size_t)(row0 + t) * bst] = v1; cur1[t] = v1; }
+        if (NCOL == 2) { at(b1, (row0 + t) * bst) = v1; cur1[t] = v1; }
     }
 #pragma unroll
     for (int q = 0; q < 6; q++) { prev0[q] = cur0[q]; if (NCOL == 2) prev1[q] = cur1[q]; }
@@ -492,8 +514,8 @@ __device__ __forceinline__ void sweep_block(const R *blk, R *b0, R *b1, int bst,
 
 // facA/nA: system of the lanes with sel == 0, facB/nB: system of the lanes with sel == 1 (DUAL only).  Each active lane
 // solves NCOL right-hand sides.  ringA/ringB: 8 blocks x 6 rows x UALM_FW doubles each.
-template <int KIND, int NCOL, bool DUAL>
-__device__ UALM_NOINLINE void sweep(const R *facA, int PA, const R *facB, int PB, R *ringA, R *ringB, R *b0, R *b1, int bst, int sel,
+template <int KIND, int NCOL, bool DUAL, class BP>
+__device__ UALM_NOINLINE void sweep(const R *facA, int PA, const R *facB, int PB, SPtr ringA, SPtr ringB, BP b0, BP b1, int bst, int sel,
                                     bool active, int lane, int cstart = 0)
 {
     constexpr bool ASC = (KIND == 0 || KIND == 2);
@@ -504,20 +526,20 @@ __device__ UALM_NOINLINE void sweep(const R *facA, int PA, const R *facB, int PB
         if (c < PA) {
             const int blk = ASC ? c : PA - 1 - c;
             const R *src = facA + (long long)blk * BLK;
-            R *dst = ringA + (c & 7) * BLK;
-            for (int p = lane; p < BLK / 2; p += 32) cp_async16(dst + 2 * p, src + 2 * p);
+            const SPtr dst = ringA + (c & 7) * BLK;
+            for (int p = lane; p < BLK / 2; p += 32) cp_async16(dst.ptr() + 2 * p, src + 2 * p);
         }
         if (DUAL && c < PB) {
             const int blk = ASC ? c : PB - 1 - c;
             const R *src = facB + (long long)blk * BLK;
-            R *dst = ringB + (c & 7) * BLK;
-            for (int p = lane; p < BLK / 2; p += 32) cp_async16(dst + 2 * p, src + 2 * p);
+            const SPtr dst = ringB + (c & 7) * BLK;
+            for (int p = lane; p < BLK / 2; p += 32) cp_async16(dst.ptr() + 2 * p, src + 2 * p);
         }
         cp_async_commit();
     };
     R prev0[6] = {0, 0, 0, 0, 0, 0}, prev1[6] = {0, 0, 0, 0, 0, 0};
     const int myP = (DUAL && sel) ? PB : PA;
-    R *myring = (DUAL && sel) ? ringB : ringA;
+    const SPtr myring = (DUAL && sel) ? ringB : ringA;
     // cstart (ascending kinds only): blocks before it hold an all-zero right-hand side, whose solution is zero as well
     issue(cstart); issue(cstart + 1); issue(cstart + 2); issue(cstart + 3);
 #pragma unroll 1
@@ -527,9 +549,9 @@ __device__ UALM_NOINLINE void sweep(const R *facA, int PA, const R *facB, int PB
         UALM_SYNC();
         if (active && c < myP) {
             const int blk = ASC ? c : myP - 1 - c;
-            const R *chunk = myring + (c & 7) * BLK;
-            if (LKIND && blk == myP - 1) sweep_block<KIND, NCOL, true>(chunk, b0, b1, bst, 6 * blk, prev0, prev1);
-            else sweep_block<KIND, NCOL, false>(chunk, b0, b1, bst, 6 * blk, prev0, prev1);
+            const SPtr chunk = myring + (c & 7) * BLK;
+            if (LKIND && blk == myP - 1) sweep_block<KIND, NCOL, true, BP>(chunk, b0, b1, bst, 6 * blk, prev0, prev1);
+            else sweep_block<KIND, NCOL, false, BP>(chunk, b0, b1, bst, 6 * blk, prev0, prev1);
         }
         UALM_SYNC();
     }
@@ -554,7 +576,7 @@ __device__ UALM_NOINLINE void minco_generate(Traj &t, int lane)
     for (int q = lane; q < ny; q += 32) t.cyaw[q] = 0.0;
     UALM_SYNC();
     const R *bnd = t.pd->bnd;
-    const R *Pxy = t.x + 1, *Pyaw = t.x + 1 + 2 * (N - 1);
+    const SPtr Pxy = t.x + 1, Pyaw = t.x + (1 + 2 * (N - 1));
     if (lane < 2) {
         const int d = lane;
         t.cxy[0 + d * nx] = bnd[d + 0]; t.cxy[1 + d * nx] = bnd[d + 2]; t.cxy[2 + d * nx] = bnd[d + 4];
@@ -575,16 +597,16 @@ __device__ UALM_NOINLINE void minco_generate(Traj &t, int lane)
     prof_mark(t, lane, PF_LU);
     // lanes 0/1: x / y columns against the xy factors; lane 2: the yaw column, all in lockstep
     {
-        R *col = lane < 2 ? t.cxy + lane * nx : t.cyaw;
-        sweep<0, 1, true>(t.Fxy, N, t.Fyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, nullptr, 1, lane == 2, lane < 3, lane);
-        sweep<1, 1, true>(t.Fxy, N, t.Fyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, nullptr, 1, lane == 2, lane < 3, lane);
+        const SPtr col = lane < 2 ? t.cxy + lane * nx : t.cyaw;
+        sweep<0, 1, true, SPtr>(t.Fxy, N, t.Fyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
+        sweep<1, 1, true, SPtr>(t.Fxy, N, t.Fyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
     }
     UALM_SYNC();
     prof_mark(t, lane, PF_SOLVE);
 }
 
 // jerk gradient entries on the fly (se2traj.hpp:719-747): dJ/dc(6i+k, col) and dJ/dT(i)
-__device__ UALM_NOINLINE R jerk_gc(const R *c6, int k, R T1, R T2, R T3, R T4, R T5)
+__device__ UALM_NOINLINE R jerk_gc(SPtr c6, int k, R T1, R T2, R T3, R T4, R T5)
 {
     const R c3 = c6[3], c4 = c6[4], c5 = c6[5];
     if (k == 5) return 240.0 * c3 * T3 + 720.0 * c4 * T4 + 1440.0 * c5 * T5;
@@ -593,10 +615,10 @@ __device__ UALM_NOINLINE R jerk_gc(const R *c6, int k, R T1, R T2, R T3, R T4, R
     return 0.0;
 }
 // per-piece jerk energy and dJ/dT (se2traj.hpp:702-707, 739-744); a = first column block, b = second (or null)
-__device__ UALM_NOINLINE void jerk_piece(const R *a, const R *b, R T1, R T2, R T3, R T4, R T5, R &e, R &gt)
+__device__ UALM_NOINLINE void jerk_piece(SPtr a, SPtr b, bool has_b, R T1, R T2, R T3, R T4, R T5, R &e, R &gt)
 {
     R d33, d43, d44, d53, d54, d55;
-    if (b) {
+    if (has_b) {
         d33 = a[3] * a[3] + b[3] * b[3]; d43 = a[4] * a[3] + b[4] * b[3]; d44 = a[4] * a[4] + b[4] * b[4];
         d53 = a[5] * a[3] + b[5] * b[3]; d54 = a[5] * a[4] + b[5] * b[4]; d55 = a[5] * a[5] + b[5] * b[5];
     } else {
@@ -613,8 +635,8 @@ __device__ UALM_NOINLINE void jerk_cost(Traj &t, int lane)
     const int N = t.N, M = t.M, nx = 6 * N;
     for (int q = lane; q < N + M; q += 32) {
         R e, gt;
-        if (q < N) { jerk_piece(t.cxy + 6 * q, t.cxy + 6 * q + nx, t.sc[SC_TX1], t.sc[SC_TX2], t.sc[SC_TX3], t.sc[SC_TX4], t.sc[SC_TX5], e, gt); t.gTxy[q] = e; }
-        else { jerk_piece(t.cyaw + 6 * (q - N), nullptr, t.sc[SC_TY1], t.sc[SC_TY2], t.sc[SC_TY3], t.sc[SC_TY4], t.sc[SC_TY5], e, gt); t.gTyaw[q - N] = e; }
+        if (q < N) { jerk_piece(t.cxy + 6 * q, t.cxy + (6 * q + nx), true, t.sc[SC_TX1], t.sc[SC_TX2], t.sc[SC_TX3], t.sc[SC_TX4], t.sc[SC_TX5], e, gt); t.gTxy[q] = e; }
+        else { jerk_piece(t.cyaw + 6 * (q - N), t.cyaw, false, t.sc[SC_TY1], t.sc[SC_TY2], t.sc[SC_TY3], t.sc[SC_TY4], t.sc[SC_TY5], e, gt); t.gTyaw[q - N] = e; }
     }
     UALM_SYNC();
     if (lane == 0) {
@@ -1059,31 +1081,30 @@ __device__ UALM_NOINLINE void penalty_accumulate(Traj &t, int lane)
 }
 
 // gdT(i) += B1 . adj  (se2traj.hpp:763-814); adj = solved adjoint vector (element stride st), Dim columns
-__device__ UALM_NOINLINE R adj_time_term(const R *c, int cst /*col stride of c*/, const R *adj, int ast /*col stride*/, int st, int Dim,
+template <class AP>
+__device__ UALM_NOINLINE R adj_time_term(SPtr c, int cst /*col stride of c*/, AP adj, int ast /*col stride*/, int st, int Dim,
                            int i, int P, R T1, R T2, R T3, R T4)
 {
     R s = 0.0;
     if (i < P - 1) {
         for (int d = 0; d < Dim; d++) {
-            const R *cc = c + d * cst + 6 * i;
+            const SPtr cc = c + (d * cst + 6 * i);
             const R nv = -(cc[1] + 2.0 * T1 * cc[2] + 3.0 * T2 * cc[3] + 4.0 * T3 * cc[4] + 5.0 * T4 * cc[5]);
             const R na = -(2.0 * cc[2] + 6.0 * T1 * cc[3] + 12.0 * T2 * cc[4] + 20.0 * T3 * cc[5]);
             const R nj = -(6.0 * cc[3] + 24.0 * T1 * cc[4] + 60.0 * T2 * cc[5]);
             const R ns = -(24.0 * cc[4] + 120.0 * T1 * cc[5]);
             const R nc = -120.0 * cc[5];
             const R B1[6] = {ns, nc, nv, nv, na, nj};
-            const R *a = adj + (size_t)d * ast;
-            for (int r = 0; r < 6; r++) s += B1[r] * a[(size_t)(6 * i + 3 + r) * st];
+            for (int r = 0; r < 6; r++) s += B1[r] * at(adj, d * ast + (6 * i + 3 + r) * st);
         }
     } else {
         for (int d = 0; d < Dim; d++) {
-            const R *cc = c + d * cst + 6 * (P - 1);
+            const SPtr cc = c + (d * cst + 6 * (P - 1));
             const R nv = -(cc[1] + 2.0 * T1 * cc[2] + 3.0 * T2 * cc[3] + 4.0 * T3 * cc[4] + 5.0 * T4 * cc[5]);
             const R na = -(2.0 * cc[2] + 6.0 * T1 * cc[3] + 12.0 * T2 * cc[4] + 20.0 * T3 * cc[5]);
             const R nj = -(6.0 * cc[3] + 24.0 * T1 * cc[4] + 60.0 * T2 * cc[5]);
             const R B2[3] = {nv, na, nj};
-            const R *a = adj + (size_t)d * ast;
-            for (int r = 0; r < 3; r++) s += B2[r] * a[(size_t)(6 * P - 3 + r) * st];
+            for (int r = 0; r < 3; r++) s += B2[r] * at(adj, d * ast + (6 * P - 3 + r) * st);
         }
     }
     return s;
@@ -1118,7 +1139,7 @@ __device__ UALM_NOINLINE void evaluate(Traj &t, const DevMap &map, const DevPara
         }
         for (int i = lane; i < N; i += 32) {
             R e, gj;
-            jerk_piece(t.cxy + 6 * i, t.cxy + 6 * i + nx, T1, T2, T3, T4, T5, e, gj);
+            jerk_piece(t.cxy + 6 * i, t.cxy + (6 * i + nx), true, T1, T2, T3, T4, T5, e, gj);
             if (p.use_scaling) gj *= UALM_SCALE_TRICK_JERK;
             t.gTxy[i] = gj * scale_fx + t.gTxy[i];
         }
@@ -1133,7 +1154,7 @@ __device__ UALM_NOINLINE void evaluate(Traj &t, const DevMap &map, const DevPara
         }
         for (int i = lane; i < M; i += 32) {
             R e, gj;
-            jerk_piece(t.cyaw + 6 * i, nullptr, T1, T2, T3, T4, T5, e, gj);
+            jerk_piece(t.cyaw + 6 * i, t.cyaw, false, T1, T2, T3, T4, T5, e, gj);
             if (p.use_scaling) gj *= UALM_SCALE_TRICK_JERK;
             t.gTyaw[i] = gj * scale_fx + t.gTyaw[i];
         }
@@ -1142,9 +1163,9 @@ __device__ UALM_NOINLINE void evaluate(Traj &t, const DevMap &map, const DevPara
     prof_mark(t, lane, PF_COMBINE);
     // calGradCTtoQT (se2traj.hpp:751-816): adjoint solves in place in gCxy / gCyaw
     {
-        R *col = lane < 2 ? t.gCxy + lane * nx : t.gCyaw;
-        sweep<2, 1, true>(t.FTxy, N, t.FTyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, nullptr, 1, lane == 2, lane < 3, lane);
-        sweep<3, 1, true>(t.FTxy, N, t.FTyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, nullptr, 1, lane == 2, lane < 3, lane);
+        const SPtr col = lane < 2 ? t.gCxy + lane * nx : t.gCyaw;
+        sweep<2, 1, true, SPtr>(t.FTxy, N, t.FTyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
+        sweep<3, 1, true, SPtr>(t.FTxy, N, t.FTyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
     }
     UALM_SYNC();
     prof_mark(t, lane, PF_ADJ);
@@ -1178,15 +1199,16 @@ __device__ UALM_NOINLINE void evaluate(Traj &t, const DevMap &map, const DevPara
 // ---------------------------------------------------------------------------------------------
 // canonical 32-lane dot product; result on every lane
 // ---------------------------------------------------------------------------------------------
-__device__ UALM_NOINLINE R lane_dot(const R *a, const R *b, int n, int lane)
+template <class PA, class PB>
+__device__ UALM_NOINLINE R lane_dot(PA a, PB b, int n, int lane)
 {
     R pacc = 0.0;
-    for (int i = lane; i < n; i += 32) pacc += a[i] * b[i];
+    for (int i = lane; i < n; i += 32) pacc += at(a, i) * at(b, i);
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) pacc = pacc + __shfl_xor_sync(0xffffffffu, pacc, off);
     return pacc;
 }
-__device__ UALM_NOINLINE R lane_absmax(const R *a, int n, int lane)
+__device__ UALM_NOINLINE R lane_absmax(SPtr a, int n, int lane)
 {
     R m = 0.0;
     for (int i = lane; i < n; i += 32) m = fmax(m, fabs(a[i]));
@@ -1517,10 +1539,10 @@ __device__ UALM_NOINLINE void init_scaling(Traj &t, const DevMap &map, const Dev
                 bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, off));
                 by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, off));
             }
-            sweep<2, 2, false>(t.FTxy, N, nullptr, 0, t.ring, nullptr, wx, wy, st, 0, act, lane, bx0);
-            sweep<3, 2, false>(t.FTxy, N, nullptr, 0, t.ring, nullptr, wx, wy, st, 0, act, lane);
-            sweep<2, 1, false>(t.FTyaw, M, nullptr, 0, t.ring, nullptr, ww, nullptr, st, 0, act, lane, by0);
-            sweep<3, 1, false>(t.FTyaw, M, nullptr, 0, t.ring, nullptr, ww, nullptr, st, 0, act, lane);
+            sweep<2, 2, false, R *>(t.FTxy, N, nullptr, 0, t.ring, t.ring, wx, wy, st, 0, act, lane, bx0);
+            sweep<3, 2, false, R *>(t.FTxy, N, nullptr, 0, t.ring, t.ring, wx, wy, st, 0, act, lane);
+            sweep<2, 1, false, R *>(t.FTyaw, M, nullptr, 0, t.ring, t.ring, ww, ww, st, 0, act, lane, by0);
+            sweep<3, 1, false, R *>(t.FTyaw, M, nullptr, 0, t.ring, t.ring, ww, ww, st, 0, act, lane);
             if (act) {
                 R m1 = 0.0, m2 = 0.0;
                 for (int r = 0; r < N - 1; r++) {
@@ -1561,7 +1583,7 @@ __device__ UALM_NOINLINE void init_scaling(Traj &t, const DevMap &map, const Dev
     }
     for (int i = lane; i < N; i += 32) {
         R e, acc;
-        jerk_piece(t.cxy + 6 * i, t.cxy + 6 * i + nx, Tx1, Tx2, Tx3, Tx4, Tx5, e, acc);
+        jerk_piece(t.cxy + 6 * i, t.cxy + (6 * i + nx), true, Tx1, Tx2, Tx3, Tx4, Tx5, e, acc);
         for (int j = 0; j <= K; j++) {
             const int s = i * (K + 1) + j;
             const R alpha = 1.0 / (R)K * (R)j;
@@ -1574,7 +1596,7 @@ __device__ UALM_NOINLINE void init_scaling(Traj &t, const DevMap &map, const Dev
     for (int m = lane; m < M; m += 32) {
         R acc[6], e, accT;
         for (int k = 0; k < 6; k++) acc[k] = jerk_gc(t.cyaw + 6 * m, k, Ty1, Ty2, Ty3, Ty4, Ty5);
-        jerk_piece(t.cyaw + 6 * m, nullptr, Ty1, Ty2, Ty3, Ty4, Ty5, e, accT);
+        jerk_piece(t.cyaw + 6 * m, t.cyaw, false, Ty1, Ty2, Ty3, Ty4, Ty5, e, accT);
         const R ratio = (R)(K + 1) * (R)N / (R)M;
         int lo = (int)((R)m * ratio) - (K + 3), hi = (int)((R)(m + 1) * ratio) + (K + 3);
         if (lo < 0) lo = 0;
@@ -1592,9 +1614,9 @@ __device__ UALM_NOINLINE void init_scaling(Traj &t, const DevMap &map, const Dev
     }
     UALM_SYNC();
     {
-        R *col = lane < 2 ? t.gCxy + lane * nx : t.gCyaw;
-        sweep<2, 1, true>(t.FTxy, N, t.FTyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, nullptr, 1, lane == 2, lane < 3, lane);
-        sweep<3, 1, true>(t.FTxy, N, t.FTyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, nullptr, 1, lane == 2, lane < 3, lane);
+        const SPtr col = lane < 2 ? t.gCxy + lane * nx : t.gCyaw;
+        sweep<2, 1, true, SPtr>(t.FTxy, N, t.FTyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
+        sweep<3, 1, true, SPtr>(t.FTxy, N, t.FTyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
     }
     UALM_SYNC();
     for (int q = lane; q < N + M; q += 32) {
@@ -1618,16 +1640,17 @@ __device__ UALM_NOINLINE void init_scaling(Traj &t, const DevMap &map, const Dev
 // ---------------------------------------------------------------------------------------------
 // set up the Traj view of one problem
 // ---------------------------------------------------------------------------------------------
-__device__ UALM_NOINLINE void traj_setup(Traj &t, const BatchPtrs &bp, const DevParams &p, const SmemLayout &L, R *sm, int prob)
+__device__ UALM_NOINLINE void traj_setup(Traj &t, const BatchPtrs &bp, const DevParams &p, const SmemLayout &L, int sm, int prob)
 {
     const ProbDesc *pd = bp.desc + prob;
     t.pd = pd; t.N = pd->N; t.M = pd->M; t.n = pd->n; t.S = pd->S; t.K = p.int_K;
-    t.cxy = sm + L.cxy; t.cyaw = sm + L.cyaw; t.gCxy = sm + L.gCxy; t.gCyaw = sm + L.gCyaw; t.gTxy = sm + L.gTxy; t.gTyaw = sm + L.gTyaw;
-    t.x = sm + L.x; t.g = sm + L.g; t.xp = sm + L.xp; t.gp = sm + L.gp; t.d = sm + L.d;
-    t.pf = sm + L.pf; t.s1tab = sm + L.s1tab; t.base = sm + L.base; t.sc = sm + L.sc; t.win = sm + L.win; t.tmpl = sm + L.tmpl; t.ring = sm + L.ring;
-    t.yawidx = reinterpret_cast<unsigned short *>(sm + L.yawidx);
-    t.roles = reinterpret_cast<unsigned short *>(sm + L.roles);
-    lu_build_roles(t.roles, threadIdx.x);
+    t.cxy = SPtr{sm + L.cxy}; t.cyaw = SPtr{sm + L.cyaw}; t.gCxy = SPtr{sm + L.gCxy}; t.gCyaw = SPtr{sm + L.gCyaw}; t.gTxy = SPtr{sm + L.gTxy};
+    t.gTyaw = SPtr{sm + L.gTyaw}; t.x = SPtr{sm + L.x}; t.g = SPtr{sm + L.g}; t.xp = SPtr{sm + L.xp}; t.gp = SPtr{sm + L.gp}; t.d = SPtr{sm + L.d};
+    t.pf = SPtr{sm + L.pf}; t.s1tab = SPtr{sm + L.s1tab}; t.base = SPtr{sm + L.base}; t.sc = SPtr{sm + L.sc}; t.win = SPtr{sm + L.win};
+    t.tmpl = SPtr{sm + L.tmpl}; t.ring = SPtr{sm + L.ring};
+    t.yawidx = SPtrU16{4 * (sm + L.yawidx)};
+    t.roles = SPtrU16{4 * (sm + L.roles)};
+    lu_build_roles(t.roles, threadIdx.x & 31);
     t.lambda = bp.lambda + pd->off_s; t.hx = bp.hx + pd->off_s;
     t.mu = bp.mu + 6 * pd->off_s; t.gx = bp.gx + 6 * pd->off_s;
     t.scale_cx = bp.scale_cx + 7 * pd->off_s;
@@ -1644,11 +1667,13 @@ __device__ UALM_NOINLINE void traj_setup(Traj &t, const BatchPtrs &bp, const Dev
     }
     t.ws = bp.ws_scaling ? bp.ws_scaling + pd->off_ws : nullptr;
     t.n_evals = 0;
-    __shared__ long long s_prof[UALM_NPROF + 1];
-    if (threadIdx.x < UALM_NPROF + 1) s_prof[threadIdx.x] = 0;
+    __shared__ long long s_prof_all[UALM_WPB][UALM_NPROF + 1];
+    long long *s_prof = s_prof_all[threadIdx.x >> 5];
+    const int ln = threadIdx.x & 31;
+    if (ln < UALM_NPROF + 1) s_prof[ln] = 0;
     t.prof = s_prof; t.plast = s_prof + UALM_NPROF;
     UALM_SYNC();
-    if (threadIdx.x == 0) { *t.plast = clock64(); s_prof[PF_TOTAL] = -clock64(); }
+    if (ln == 0) { *t.plast = clock64(); s_prof[PF_TOTAL] = -clock64(); }
 }
 
 // =============================================================================================
@@ -1656,11 +1681,12 @@ __device__ UALM_NOINLINE void traj_setup(Traj &t, const BatchPtrs &bp, const Dev
 // =============================================================================================
 
 // full solve: optimizeSE2Traj (alm_traj_opt.cpp:168-278)
-__global__ void __launch_bounds__(UALM_THREADS) solve_kernel(BatchPtrs bp, DevParams p, DevMap map, SmemLayout L)
+__global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) solve_kernel(BatchPtrs bp, DevParams p, DevMap map, SmemLayout L)
 {
-    extern __shared__ __align__(16) double sm[];
-    const int lane = threadIdx.x;
-    const int prob = bp.order[blockIdx.x];
+    const int lane = threadIdx.x & 31, wslot = blockIdx.x * UALM_WPB + (threadIdx.x >> 5);
+    if (wslot >= bp.B) return;   // whole warp exits; warps never synchronise with each other
+    const int sm = (threadIdx.x >> 5) * L.total_doubles;
+    const int prob = bp.order[wslot];
     Traj t;
     traj_setup(t, bp, p, L, sm, prob);
     const int N = t.N, M = t.M, n = t.n, S = t.S;
@@ -1728,17 +1754,18 @@ __global__ void __launch_bounds__(UALM_THREADS) solve_kernel(BatchPtrs bp, DevPa
         bp.results[prob] = r;
         if (bp.prof) {
             t.prof[PF_TOTAL] += clock64();
-            for (int q = 0; q < UALM_NPROF; q++) bp.prof[(size_t)blockIdx.x * UALM_NPROF + q] = t.prof[q];
+            for (int q = 0; q < UALM_NPROF; q++) bp.prof[(size_t)wslot * UALM_NPROF + q] = t.prof[q];
         }
     }
 }
 
 // one innerCallback evaluation per problem at caller-provided x / duals (kernel-level parity)
-__global__ void __launch_bounds__(UALM_THREADS) eval_kernel(BatchPtrs bp, DevParams p, DevMap map, SmemLayout L, R rho)
+__global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) eval_kernel(BatchPtrs bp, DevParams p, DevMap map, SmemLayout L, R rho)
 {
-    extern __shared__ __align__(16) double sm[];
-    const int lane = threadIdx.x;
-    const int prob = bp.order[blockIdx.x];
+    const int lane = threadIdx.x & 31, wslot = blockIdx.x * UALM_WPB + (threadIdx.x >> 5);
+    if (wslot >= bp.B) return;   // whole warp exits; warps never synchronise with each other
+    const int sm = (threadIdx.x >> 5) * L.total_doubles;
+    const int prob = bp.order[wslot];
     Traj t;
     traj_setup(t, bp, p, L, sm, prob);
     for (int q = lane; q < t.n; q += 32) t.x[q] = bp.x0[t.pd->off_x + q];
@@ -1753,11 +1780,12 @@ __global__ void __launch_bounds__(UALM_THREADS) eval_kernel(BatchPtrs bp, DevPar
 }
 
 // initScaling per problem at x0
-__global__ void __launch_bounds__(UALM_THREADS) scaling_kernel(BatchPtrs bp, DevParams p, DevMap map, SmemLayout L)
+__global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) scaling_kernel(BatchPtrs bp, DevParams p, DevMap map, SmemLayout L)
 {
-    extern __shared__ __align__(16) double sm[];
-    const int lane = threadIdx.x;
-    const int prob = bp.order[blockIdx.x];
+    const int lane = threadIdx.x & 31, wslot = blockIdx.x * UALM_WPB + (threadIdx.x >> 5);
+    if (wslot >= bp.B) return;   // whole warp exits; warps never synchronise with each other
+    const int sm = (threadIdx.x >> 5) * L.total_doubles;
+    const int prob = bp.order[wslot];
     Traj t;
     traj_setup(t, bp, p, L, sm, prob);
     for (int q = lane; q < t.n; q += 32) t.x[q] = bp.x0[t.pd->off_x + q];
@@ -1769,11 +1797,12 @@ __global__ void __launch_bounds__(UALM_THREADS) scaling_kernel(BatchPtrs bp, Dev
 
 // the penalty-sampling phase alone (calConstrainCostGrad, alm_traj_opt.cpp:663-991) for roofline timing:
 // MINCO state is generated once, then `reps` sampling + accumulation passes are run.
-__global__ void __launch_bounds__(UALM_THREADS) penalty_only_kernel(BatchPtrs bp, DevParams p, DevMap map, SmemLayout L, int reps)
+__global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) penalty_only_kernel(BatchPtrs bp, DevParams p, DevMap map, SmemLayout L, int reps)
 {
-    extern __shared__ __align__(16) double sm[];
-    const int lane = threadIdx.x;
-    const int prob = bp.order[blockIdx.x];
+    const int lane = threadIdx.x & 31, wslot = blockIdx.x * UALM_WPB + (threadIdx.x >> 5);
+    if (wslot >= bp.B) return;   // whole warp exits; warps never synchronise with each other
+    const int sm = (threadIdx.x >> 5) * L.total_doubles;
+    const int prob = bp.order[wslot];
     Traj t;
     traj_setup(t, bp, p, L, sm, prob);
     for (int q = lane; q < t.n; q += 32) t.x[q] = bp.x0[t.pd->off_x + q];
