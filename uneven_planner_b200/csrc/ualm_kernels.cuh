@@ -332,16 +332,36 @@ __device__ __forceinline__ int tmpl_index(int r, int n6)
     return (r - 3) % 6;
 }
 
-// rows r0 .. r0+5 of A into the sliding window (entries whose column falls outside the matrix are zero)
+// rows r0 .. r0+5 of A into the sliding window (entries whose column falls outside the matrix are zero).  General version
+// (any r0) for the prologue; lane hl < 13 owns band column q = hl.
 __device__ __forceinline__ void lu_fill6(SPtr W, SPtr TM, int r0, int n6, int hl)
 {
+    if (hl < 13) {
 #pragma unroll 1
-    for (int e = hl; e < 6 * 13; e += 16) {
-        const int rr = e / 13, q = e - 13 * rr, r = r0 + rr;
-        const int c = r - 6 + q;
-        R v = 0.0;
-        if (r < n6 && c >= 0 && c < n6) v = TM[tmpl_index(r, n6) * UALM_FW + q];
-        W[(r & 15) * UALM_FW + q] = v;
+        for (int rr = 0; rr < 6; rr++) {
+            const int r = r0 + rr, c = r - 6 + hl;
+            R v = 0.0;
+            if (r < n6 && c >= 0 && c < n6) v = TM[tmpl_index(r, n6) * UALM_FW + hl];
+            W[(r & 15) * UALM_FW + hl] = v;
+        }
+    }
+}
+// steady-state version: r0 = k + 8 with k a multiple of 6, so the junction-row type of row r0+rr is (5 + rr) mod 6
+__device__ __forceinline__ void lu_fill6_aligned(SPtr W, SPtr TM, int r0, int n6, int hl)
+{
+    if (hl < 13) {
+        if (r0 + 5 < n6 - 3 && r0 >= 9) { // all six rows are junction rows with every band column inside the matrix
+#pragma unroll
+            for (int rr = 0; rr < 6; rr++) W[((r0 + rr) & 15) * UALM_FW + hl] = TM[((5 + rr) % 6) * UALM_FW + hl];
+        } else {
+#pragma unroll 1
+            for (int rr = 0; rr < 6; rr++) {
+                const int r = r0 + rr, c = r - 6 + hl;
+                R v = 0.0;
+                if (r < n6 && c >= 0 && c < n6) v = TM[tmpl_index(r, n6) * UALM_FW + hl];
+                W[(r & 15) * UALM_FW + hl] = v;
+            }
+        }
     }
 }
 
@@ -396,13 +416,15 @@ __device__ UALM_NOINLINE void lu_dual(Traj &t, int lane)
     lu_fill6(W, TM, 6, n6, hl);
     UALM_SYNC();
     const int nmax6 = 6 * (t.N > t.M ? t.N : t.M);
+    const SPtrU16 roles = t.roles;
+    R *Fk = F, *FTk = FT;          // row k of F / FT
     int kmod = 0;
 #pragma unroll 1
-    for (int k = 0; k < nmax6; k++) {
+    for (int k = 0; k < nmax6; k++, Fk += UALM_FW, FTk += UALM_FW) {
         const bool on = k < n6;
-        if (kmod == 0 && on) lu_fill6(W, TM, k + 8, n6, hl);
+        if (kmod == 0 && on) lu_fill6_aligned(W, TM, k + 8, n6, hl);
         const int ty = (k >= n6 - 6) ? 6 + (k - (n6 - 6)) : kmod;
-        const unsigned role = on ? t.roles[(ty << 4) + hl] : 0u;
+        const unsigned role = on ? roles[(ty << 4) + hl] : 0u;
         const int mo = role & 7, uo = (role >> 3) & 7, uc = (role >> 6) & 7, ul = (role >> 9) & 3;
         const SPtr Wk = W + (k & 15) * UALM_FW;
         R m = 0.0;
@@ -416,19 +438,19 @@ __device__ UALM_NOINLINE void lu_dual(Traj &t, int lane)
             if (a != 0.0) m = a / piv;
             if (!isr) {
                 *pa = m;
-                F[(size_t)(k + o) * UALM_FW + 6 - o] = m;
-                FT[(size_t)k * UALM_FW + 6 + o] = m;
+                Fk[o * UALM_FW + 6 - o] = m;       // F[k+o][6-o]
+                FTk[6 + o] = m;                    // FT[k][6+o]
             } else {
                 // a divisor with an all-ones significand is the one case the reciprocal-based division cannot round: flag it
                 if ((__double_as_longlong(piv) & 0xFFFFFFFFFFFFFll) == 0xFFFFFFFFFFFFFll) m = __longlong_as_double(0x7ff8000000000000ll);
-                F[(size_t)k * UALM_FW + 13] = m;
-                FT[(size_t)k * UALM_FW + 13] = m;
+                Fk[13] = m;
+                FTk[13] = m;
             }
         } else if (on && hl >= 5 && hl < 12) {
             const int q = hl - 5;
             const R u = Wk[6 + q];
-            F[(size_t)k * UALM_FW + 6 + q] = u;
-            if (k + q < n6) FT[(size_t)(k + q) * UALM_FW + 6 - q] = u;
+            Fk[6 + q] = u;
+            if (k + q < n6) FTk[q * UALM_FW + 6 - q] = u;   // FT[k+q][6-q]
         }
         const R mr = __shfl_sync(0xffffffffu, m, (lane & 16) + ul);
         if (uc && k + uc < n6) {
