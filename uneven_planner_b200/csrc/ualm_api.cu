@@ -197,7 +197,7 @@ extern "C" int ualm_upload(ualm_ctx_t *c, int B, const int32_t *N, const int32_t
         for (int q = 0; q < d.M - 1; q++) x0.push_back(inner_yaw[oiyaw + q]);
         oixy += 2 * (d.N - 1); oiyaw += d.M - 1;
         ox += d.n; os += d.S; ocx += 12 * d.N; ocy += 6 * d.M; oh += (long long)m * d.n; oscr += (long long)UALM_NFIELD * d.S;
-        ofac += 2LL * UALM_FW * ((6 * d.N + 2 * UALM_FPAD) + (6 * d.M + 2 * UALM_FPAD));
+        ofac += 1LL * UALM_FW * ((6 * d.N + 2 * UALM_FPAD) + (6 * d.M + 2 * UALM_FPAD));
         ows += (long long)(12 * d.N + 6 * d.M) * 32;
         c->Nmax = std::max(c->Nmax, d.N); c->Mmax = std::max(c->Mmax, d.M); c->nmax = std::max(c->nmax, d.n); c->Smax = std::max(c->Smax, d.S);
     }

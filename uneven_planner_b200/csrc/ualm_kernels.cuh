@@ -182,7 +182,7 @@ struct Traj {
     SPtrU16 yawidx, roles;
     // global
     R *lambda, *mu, *scale_cx, *hx, *gx, *lm_s, *lm_y, *lm_alpha, *lm_ys, *scr;
-    R *Fxy, *FTxy, *Fyaw, *FTyaw;   // row 0 of each factor array
+    R *Fxy, *Fyaw;                  // row 0 of each factor array
     R *ws;
     int n_evals;
     long long *prof;   // shared-memory phase counters (lane 0 only)
@@ -396,7 +396,7 @@ __device__ UALM_NOINLINE void lu_dual(Traj &t, int lane)
     const int P = sys ? t.M : t.N, n6 = 6 * P;
     const SPtr W = t.win + sys * (16 * UALM_FW);
     const SPtr TM = t.tmpl + sys * (12 * UALM_FW);
-    R *F = sys ? t.Fyaw : t.Fxy, *FT = sys ? t.FTyaw : t.FTxy;
+    R *F = sys ? t.Fyaw : t.Fxy;
     {
         const R T1 = t.sc[sys ? SC_TY1 : SC_TX1], T2 = t.sc[sys ? SC_TY2 : SC_TX2], T3 = t.sc[sys ? SC_TY3 : SC_TX3],
                 T4 = t.sc[sys ? SC_TY4 : SC_TX4], T5 = t.sc[sys ? SC_TY5 : SC_TX5];
@@ -417,10 +417,10 @@ __device__ UALM_NOINLINE void lu_dual(Traj &t, int lane)
     UALM_SYNC();
     const int nmax6 = 6 * (t.N > t.M ? t.N : t.M);
     const SPtrU16 roles = t.roles;
-    R *Fk = F, *FTk = FT;          // row k of F / FT
+    R *Fk = F;                     // row k of F
     int kmod = 0;
 #pragma unroll 1
-    for (int k = 0; k < nmax6; k++, Fk += UALM_FW, FTk += UALM_FW) {
+    for (int k = 0; k < nmax6; k++, Fk += UALM_FW) {
         const bool on = k < n6;
         if (kmod == 0 && on) lu_fill6_aligned(W, TM, k + 8, n6, hl);
         const int ty = (k >= n6 - 6) ? 6 + (k - (n6 - 6)) : kmod;
@@ -439,18 +439,15 @@ __device__ UALM_NOINLINE void lu_dual(Traj &t, int lane)
             if (!isr) {
                 *pa = m;
                 Fk[o * UALM_FW + 6 - o] = m;       // F[k+o][6-o]
-                FTk[6 + o] = m;                    // FT[k][6+o]
             } else {
                 // a divisor with an all-ones significand is the one case the reciprocal-based division cannot round: flag it
                 if ((__double_as_longlong(piv) & 0xFFFFFFFFFFFFFll) == 0xFFFFFFFFFFFFFll) m = __longlong_as_double(0x7ff8000000000000ll);
                 Fk[13] = m;
-                FTk[13] = m;
             }
         } else if (on && hl >= 5 && hl < 12) {
             const int q = hl - 5;
             const R u = Wk[6 + q];
             Fk[6 + q] = u;
-            if (k + q < n6) FTk[q * UALM_FW + 6 - q] = u;   // FT[k+q][6-q]
         }
         const R mr = __shfl_sync(0xffffffffu, m, (lane & 16) + ul);
         if (uc && k + uc < n6) {
@@ -493,10 +490,11 @@ __host__ __device__ constexpr int sweep_mask(int kind, int t)
 }
 
 template <int KIND, int NCOL, bool FULL, class BP>
-__device__ __forceinline__ void sweep_block(SPtr blk, BP b0, BP b1, int bst, int row0, R (&prev0)[6], R (&prev1)[6])
+__device__ __forceinline__ void sweep_block(SPtr blk, SPtr nb, bool hasnb, BP b0, BP b1, int bst, int row0, R (&prev0)[6], R (&prev1)[6])
 {
     constexpr bool ASC = (KIND == 0 || KIND == 2);
     constexpr bool DIV = (KIND == 1 || KIND == 2);
+    constexpr bool TR = (KIND == 2 || KIND == 3);   // transposed access: the factor entry lives in the neighbour's row
     R cur0[6], cur1[6];
 #pragma unroll
     for (int tt = 0; tt < 6; tt++) {
@@ -507,16 +505,22 @@ __device__ __forceinline__ void sweep_block(SPtr blk, BP b0, BP b1, int bst, int
 #pragma unroll
         for (int d = 6; d >= 1; d--) {
             if (FULL || ((sweep_mask(KIND, t) >> (d - 1)) & 1)) {
-                const R fv = f[ASC ? 6 - d : 6 + d];
-                // neighbour value: ascending kinds use b[i-d], descending kinds x[i+d]
+                // neighbour index: ascending kinds use row i-d, descending kinds row i+d
                 const int tn = ASC ? t - d : t + d;
                 const bool incur = ASC ? (tn >= 0) : (tn <= 5);
+                const int tq = incur ? tn : (ASC ? tn + 6 : tn - 6);
+                // factor entry: KIND 0: L(i,i-d) = F[i][6-d]; KIND 1: U(i,i+d) = F[i][6+d];
+                //               KIND 2: U(i-d,i) = F[i-d][6+d]; KIND 3: L(i+d,i) = F[i+d][6-d]
+                R fv;
+                if (!TR) fv = f[ASC ? 6 - d : 6 + d];
+                else if (incur) fv = blk[tq * UALM_FW + (ASC ? 6 + d : 6 - d)];
+                else fv = hasnb ? nb[tq * UALM_FW + (ASC ? 6 + d : 6 - d)] : 0.0;
                 // the reference skips exact-zero factors (banded_system.hpp:103,112,131,139); subtracting 0 * w instead leaves
                 // every value unchanged (at most the sign of an exact zero differs), so no test is needed here
-                const R w0 = incur ? cur0[tn] : prev0[ASC ? tn + 6 : tn - 6];
+                const R w0 = incur ? cur0[tq] : prev0[tq];
                 v0 = v0 - fv * w0;
                 if (NCOL == 2) {
-                    const R w1 = incur ? cur1[tn] : prev1[ASC ? tn + 6 : tn - 6];
+                    const R w1 = incur ? cur1[tq] : prev1[tq];
                     v1 = v1 - fv * w1;
                 }
             }
@@ -572,8 +576,10 @@ __device__ UALM_NOINLINE void sweep(const R *facA, int PA, const R *facB, int PB
         if (active && c < myP) {
             const int blk = ASC ? c : myP - 1 - c;
             const SPtr chunk = myring + (c & 7) * BLK;
-            if (LKIND && blk == myP - 1) sweep_block<KIND, NCOL, true, BP>(chunk, b0, b1, bst, 6 * blk, prev0, prev1);
-            else sweep_block<KIND, NCOL, false, BP>(chunk, b0, b1, bst, 6 * blk, prev0, prev1);
+            const SPtr nbr = myring + ((c + 7) & 7) * BLK;      // the block processed just before (still in the ring)
+            const bool hasnb = c > cstart;
+            if (LKIND && blk == myP - 1) sweep_block<KIND, NCOL, true, BP>(chunk, nbr, hasnb, b0, b1, bst, 6 * blk, prev0, prev1);
+            else sweep_block<KIND, NCOL, false, BP>(chunk, nbr, hasnb, b0, b1, bst, 6 * blk, prev0, prev1);
         }
         UALM_SYNC();
     }
@@ -1186,8 +1192,8 @@ __device__ UALM_NOINLINE void evaluate(Traj &t, const DevMap &map, const DevPara
     // calGradCTtoQT (se2traj.hpp:751-816): adjoint solves in place in gCxy / gCyaw
     {
         const SPtr col = lane < 2 ? t.gCxy + lane * nx : t.gCyaw;
-        sweep<2, 1, true, SPtr>(t.FTxy, N, t.FTyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
-        sweep<3, 1, true, SPtr>(t.FTxy, N, t.FTyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
+        sweep<2, 1, true, SPtr>(t.Fxy, N, t.Fyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
+        sweep<3, 1, true, SPtr>(t.Fxy, N, t.Fyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
     }
     UALM_SYNC();
     prof_mark(t, lane, PF_ADJ);
@@ -1561,10 +1567,10 @@ __device__ UALM_NOINLINE void init_scaling(Traj &t, const DevMap &map, const Dev
                 bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, off));
                 by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, off));
             }
-            sweep<2, 2, false, R *>(t.FTxy, N, nullptr, 0, t.ring, t.ring, wx, wy, st, 0, act, lane, bx0);
-            sweep<3, 2, false, R *>(t.FTxy, N, nullptr, 0, t.ring, t.ring, wx, wy, st, 0, act, lane);
-            sweep<2, 1, false, R *>(t.FTyaw, M, nullptr, 0, t.ring, t.ring, ww, ww, st, 0, act, lane, by0);
-            sweep<3, 1, false, R *>(t.FTyaw, M, nullptr, 0, t.ring, t.ring, ww, ww, st, 0, act, lane);
+            sweep<2, 2, false, R *>(t.Fxy, N, nullptr, 0, t.ring, t.ring, wx, wy, st, 0, act, lane, bx0);
+            sweep<3, 2, false, R *>(t.Fxy, N, nullptr, 0, t.ring, t.ring, wx, wy, st, 0, act, lane);
+            sweep<2, 1, false, R *>(t.Fyaw, M, nullptr, 0, t.ring, t.ring, ww, ww, st, 0, act, lane, by0);
+            sweep<3, 1, false, R *>(t.Fyaw, M, nullptr, 0, t.ring, t.ring, ww, ww, st, 0, act, lane);
             if (act) {
                 R m1 = 0.0, m2 = 0.0;
                 for (int r = 0; r < N - 1; r++) {
@@ -1637,8 +1643,8 @@ __device__ UALM_NOINLINE void init_scaling(Traj &t, const DevMap &map, const Dev
     UALM_SYNC();
     {
         const SPtr col = lane < 2 ? t.gCxy + lane * nx : t.gCyaw;
-        sweep<2, 1, true, SPtr>(t.FTxy, N, t.FTyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
-        sweep<3, 1, true, SPtr>(t.FTxy, N, t.FTyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
+        sweep<2, 1, true, SPtr>(t.Fxy, N, t.Fyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
+        sweep<3, 1, true, SPtr>(t.Fxy, N, t.Fyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
     }
     UALM_SYNC();
     for (int q = lane; q < N + M; q += 32) {
@@ -1683,9 +1689,8 @@ __device__ UALM_NOINLINE void traj_setup(Traj &t, const BatchPtrs &bp, const Dev
         const long long rx = 6 * pd->N + 2 * UALM_FPAD, ry = 6 * pd->M + 2 * UALM_FPAD;
         R *f = bp.fac + pd->off_fac;
         t.Fxy = f + UALM_FPAD * UALM_FW;
-        t.FTxy = f + rx * UALM_FW + UALM_FPAD * UALM_FW;
-        t.Fyaw = f + 2 * rx * UALM_FW + UALM_FPAD * UALM_FW;
-        t.FTyaw = f + (2 * rx + ry) * UALM_FW + UALM_FPAD * UALM_FW;
+        t.Fyaw = f + rx * UALM_FW + UALM_FPAD * UALM_FW;
+        (void)ry;
     }
     t.ws = bp.ws_scaling ? bp.ws_scaling + pd->off_ws : nullptr;
     t.n_evals = 0;
