@@ -152,23 +152,53 @@ enum {
     SC_SCALE_FX, SC_RHO, SC_F, SC_JERK, SC_CONSTR, SC_TAUCOST, SC_JERKRAW, SC_RTY
 };
 
-// Handles to shared memory: a 32-bit element offset into the kernel's dynamic shared array.  Accesses through them compile to
-// LDS/STS with 32-bit address arithmetic (plain `double*` members would become generic loads: the pointer provenance is lost
-// across the __noinline__ calls).
+// Handles to shared memory: a 32-bit address in the shared state space.  Accesses through them are explicit ld.shared /
+// st.shared with 32-bit address arithmetic.  (Plain `double*` members become generic loads, and C++ references into the
+// `extern __shared__` array make the compiler rebuild the generic shared-window base -- S2UR SR_CgaCtaId + ULEA -- at every
+// use inside the __noinline__ functions: measured at ~20 % of the LU pivot loop in profiles/solve_kernel_r01_summary.md.)
 extern __shared__ __align__(16) double ualm_smem[];
+__device__ __forceinline__ double lds64(unsigned a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+struct SRef {   // proxy "reference" to one shared double
+    unsigned a;
+    __device__ __forceinline__ operator double() const { return lds64(a); }
+    __device__ __forceinline__ const SRef &operator=(double v) const { sts64(a, v); return *this; }
+    __device__ __forceinline__ const SRef &operator=(const SRef &o) const { sts64(a, lds64(o.a)); return *this; }
+    __device__ __forceinline__ const SRef &operator+=(double v) const { sts64(a, lds64(a) + v); return *this; }
+    __device__ __forceinline__ const SRef &operator-=(double v) const { sts64(a, lds64(a) - v); return *this; }
+    __device__ __forceinline__ const SRef &operator*=(double v) const { sts64(a, lds64(a) * v); return *this; }
+};
 struct SPtr {
-    int off;
-    __device__ __forceinline__ double &operator[](int i) const { return ualm_smem[off + i]; }
-    __device__ __forceinline__ double &operator*() const { return ualm_smem[off]; }
-    __device__ __forceinline__ SPtr operator+(int d) const { return SPtr{off + d}; }
-    __device__ __forceinline__ double *ptr() const { return ualm_smem + off; }
+    unsigned a;   // byte address in the shared window
+    __device__ __forceinline__ SRef operator[](int i) const { return SRef{a + 8u * (unsigned)i}; }
+    __device__ __forceinline__ SRef operator*() const { return SRef{a}; }
+    __device__ __forceinline__ SPtr operator+(int d) const { return SPtr{a + 8u * (unsigned)d}; }
+};
+struct SRefU16 {
+    unsigned a;
+    __device__ __forceinline__ operator int() const
+    {
+        unsigned short v;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+        return (int)v;
+    }
+    __device__ __forceinline__ const SRefU16 &operator=(unsigned short v) const
+    {
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory");
+        return *this;
+    }
 };
 struct SPtrU16 {
-    int off;   // in unsigned shorts
-    __device__ __forceinline__ unsigned short &operator[](int i) const { return reinterpret_cast<unsigned short *>(ualm_smem)[off + i]; }
+    unsigned a;
+    __device__ __forceinline__ SRefU16 operator[](int i) const { return SRefU16{a + 2u * (unsigned)i}; }
 };
 // element access that works for both handle kinds
-__device__ __forceinline__ double &at(SPtr p, int i) { return p[i]; }
+__device__ __forceinline__ SRef at(SPtr p, int i) { return p[i]; }
 __device__ __forceinline__ double &at(double *p, int i) { return p[i]; }
 __device__ __forceinline__ const double &at(const double *p, int i) { return p[i]; }
 
@@ -242,10 +272,9 @@ __device__ __forceinline__ R div_by_recip(R a, R b, R rb)
 // cp.async (LDGSTS) helpers: 16-byte global -> shared copies that bypass L1 (factors are produced by this warp and
 // consumed once per sweep: L2 is the right home)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+__device__ __forceinline__ void cp_async16(unsigned smem_addr, const void *gmem)
 {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int NPEND>
@@ -553,13 +582,13 @@ __device__ UALM_NOINLINE void sweep(const R *facA, int PA, const R *facB, int PB
             const int blk = ASC ? c : PA - 1 - c;
             const R *src = facA + (long long)blk * BLK;
             const SPtr dst = ringA + (c & 7) * BLK;
-            for (int p = lane; p < BLK / 2; p += 32) cp_async16(dst.ptr() + 2 * p, src + 2 * p);
+            for (int p = lane; p < BLK / 2; p += 32) cp_async16(dst.a + 16u * (unsigned)p, src + 2 * p);
         }
         if (DUAL && c < PB) {
             const int blk = ASC ? c : PB - 1 - c;
             const R *src = facB + (long long)blk * BLK;
             const SPtr dst = ringB + (c & 7) * BLK;
-            for (int p = lane; p < BLK / 2; p += 32) cp_async16(dst.ptr() + 2 * p, src + 2 * p);
+            for (int p = lane; p < BLK / 2; p += 32) cp_async16(dst.a + 16u * (unsigned)p, src + 2 * p);
         }
         cp_async_commit();
     };
@@ -1668,16 +1697,16 @@ __device__ UALM_NOINLINE void init_scaling(Traj &t, const DevMap &map, const Dev
 // ---------------------------------------------------------------------------------------------
 // set up the Traj view of one problem
 // ---------------------------------------------------------------------------------------------
-__device__ UALM_NOINLINE void traj_setup(Traj &t, const BatchPtrs &bp, const DevParams &p, const SmemLayout &L, int sm, int prob)
+__device__ UALM_NOINLINE void traj_setup(Traj &t, const BatchPtrs &bp, const DevParams &p, const SmemLayout &L, unsigned sm, int prob)
 {
     const ProbDesc *pd = bp.desc + prob;
     t.pd = pd; t.N = pd->N; t.M = pd->M; t.n = pd->n; t.S = pd->S; t.K = p.int_K;
-    t.cxy = SPtr{sm + L.cxy}; t.cyaw = SPtr{sm + L.cyaw}; t.gCxy = SPtr{sm + L.gCxy}; t.gCyaw = SPtr{sm + L.gCyaw}; t.gTxy = SPtr{sm + L.gTxy};
-    t.gTyaw = SPtr{sm + L.gTyaw}; t.x = SPtr{sm + L.x}; t.g = SPtr{sm + L.g}; t.xp = SPtr{sm + L.xp}; t.gp = SPtr{sm + L.gp}; t.d = SPtr{sm + L.d};
-    t.pf = SPtr{sm + L.pf}; t.s1tab = SPtr{sm + L.s1tab}; t.base = SPtr{sm + L.base}; t.sc = SPtr{sm + L.sc}; t.win = SPtr{sm + L.win};
-    t.tmpl = SPtr{sm + L.tmpl}; t.ring = SPtr{sm + L.ring};
-    t.yawidx = SPtrU16{4 * (sm + L.yawidx)};
-    t.roles = SPtrU16{4 * (sm + L.roles)};
+    auto S8 = [&](int o) { return SPtr{sm + 8u * (unsigned)o}; };
+    t.cxy = S8(L.cxy); t.cyaw = S8(L.cyaw); t.gCxy = S8(L.gCxy); t.gCyaw = S8(L.gCyaw); t.gTxy = S8(L.gTxy); t.gTyaw = S8(L.gTyaw);
+    t.x = S8(L.x); t.g = S8(L.g); t.xp = S8(L.xp); t.gp = S8(L.gp); t.d = S8(L.d); t.pf = S8(L.pf); t.s1tab = S8(L.s1tab);
+    t.base = S8(L.base); t.sc = S8(L.sc); t.win = S8(L.win); t.tmpl = S8(L.tmpl); t.ring = S8(L.ring);
+    t.yawidx = SPtrU16{sm + 8u * (unsigned)L.yawidx};
+    t.roles = SPtrU16{sm + 8u * (unsigned)L.roles};
     lu_build_roles(t.roles, threadIdx.x & 31);
     t.lambda = bp.lambda + pd->off_s; t.hx = bp.hx + pd->off_s;
     t.mu = bp.mu + 6 * pd->off_s; t.gx = bp.gx + 6 * pd->off_s;
@@ -1712,7 +1741,7 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) solve_kernel(BatchPtr
 {
     const int lane = threadIdx.x & 31, wslot = blockIdx.x * UALM_WPB + (threadIdx.x >> 5);
     if (wslot >= bp.B) return;   // whole warp exits; warps never synchronise with each other
-    const int sm = (threadIdx.x >> 5) * L.total_doubles;
+    const unsigned sm = (unsigned)__cvta_generic_to_shared(ualm_smem) + 8u * (unsigned)((threadIdx.x >> 5) * L.total_doubles);
     const int prob = bp.order[wslot];
     Traj t;
     traj_setup(t, bp, p, L, sm, prob);
@@ -1791,7 +1820,7 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) eval_kernel(BatchPtrs
 {
     const int lane = threadIdx.x & 31, wslot = blockIdx.x * UALM_WPB + (threadIdx.x >> 5);
     if (wslot >= bp.B) return;   // whole warp exits; warps never synchronise with each other
-    const int sm = (threadIdx.x >> 5) * L.total_doubles;
+    const unsigned sm = (unsigned)__cvta_generic_to_shared(ualm_smem) + 8u * (unsigned)((threadIdx.x >> 5) * L.total_doubles);
     const int prob = bp.order[wslot];
     Traj t;
     traj_setup(t, bp, p, L, sm, prob);
@@ -1811,7 +1840,7 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) scaling_kernel(BatchP
 {
     const int lane = threadIdx.x & 31, wslot = blockIdx.x * UALM_WPB + (threadIdx.x >> 5);
     if (wslot >= bp.B) return;   // whole warp exits; warps never synchronise with each other
-    const int sm = (threadIdx.x >> 5) * L.total_doubles;
+    const unsigned sm = (unsigned)__cvta_generic_to_shared(ualm_smem) + 8u * (unsigned)((threadIdx.x >> 5) * L.total_doubles);
     const int prob = bp.order[wslot];
     Traj t;
     traj_setup(t, bp, p, L, sm, prob);
@@ -1828,7 +1857,7 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) penalty_only_kernel(B
 {
     const int lane = threadIdx.x & 31, wslot = blockIdx.x * UALM_WPB + (threadIdx.x >> 5);
     if (wslot >= bp.B) return;   // whole warp exits; warps never synchronise with each other
-    const int sm = (threadIdx.x >> 5) * L.total_doubles;
+    const unsigned sm = (unsigned)__cvta_generic_to_shared(ualm_smem) + 8u * (unsigned)((threadIdx.x >> 5) * L.total_doubles);
     const int prob = bp.order[wslot];
     Traj t;
     traj_setup(t, bp, p, L, sm, prob);
