@@ -525,12 +525,19 @@ __device__ __forceinline__ void sweep_block(SPtr blk, SPtr nb, bool hasnb, BP b0
     constexpr bool DIV = (KIND == 1 || KIND == 2);
     constexpr bool TR = (KIND == 2 || KIND == 3);   // transposed access: the factor entry lives in the neighbour's row
     R cur0[6], cur1[6];
+    // all right-hand-side entries of the block first: they do not depend on the chain, and issuing them together pays the
+    // memory latency once per block instead of once per row (the stores below would otherwise fence them)
+    R rhs0[6], rhs1[6];
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        rhs0[q] = at(b0, (row0 + q) * bst);
+        rhs1[q] = (NCOL == 2) ? (R)at(b1, (row0 + q) * bst) : 0.0;
+    }
 #pragma unroll
     for (int tt = 0; tt < 6; tt++) {
         const int t = ASC ? tt : 5 - tt;            // row type processed now
         const SPtr f = blk + t * UALM_FW;
-        R v0 = at(b0, (row0 + t) * bst), v1 = 0.0;
-        if (NCOL == 2) v1 = at(b1, (row0 + t) * bst);
+        R v0 = rhs0[t], v1 = rhs1[t];
 #pragma unroll
         for (int d = 6; d >= 1; d--) {
             if (FULL || ((sweep_mask(KIND, t) >> (d - 1)) & 1)) {
@@ -715,7 +722,7 @@ __device__ __forceinline__ bool map_in(const DevMap &m, const R pos[3]) // uneve
     return true;
 }
 
-__device__ UALM_NOINLINE void map_get_all_with_grad(const DevMap &m, const R pos[3], R values[7], R grads[7][3])
+__device__ __forceinline__ void map_get_all_with_grad_impl(const DevMap &m, const R pos[3], R values[7], R grads[7][3])
 {
     R rs[3], rg[4][3];
     if (!map_in(m, pos)) {
@@ -815,6 +822,11 @@ __device__ UALM_NOINLINE void map_get_all_with_grad(const DevMap &m, const R pos
     }
 }
 
+__device__ UALM_NOINLINE void map_get_all_with_grad(const DevMap &m, const R pos[3], R values[7], R grads[7][3])
+{
+    map_get_all_with_grad_impl(m, pos, values, grads);
+}
+
 // kinematics of one constraint sample (alm_traj_opt.cpp:733-817)
 struct SampleK {
     R b0[6], b1[6], b2[6], b3[6], y0[6], y1[6], y2[6];
@@ -825,7 +837,8 @@ struct SampleK {
     int yaw_idx;
 };
 
-__device__ UALM_NOINLINE void sample_kin(const Traj &t, const DevMap &map, R gravity, int i, R s1, R base_time, SampleK &S)
+template <bool INL>
+__device__ __forceinline__ void sample_kin_impl(const Traj &t, const DevMap &map, R gravity, int i, R s1, R base_time, SampleK &S)
 {
     const int nx = 6 * t.N;
     const R s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
@@ -866,12 +879,19 @@ __device__ UALM_NOINLINE void sample_kin(const Traj &t, const DevMap &map, R gra
     S.v_norm = sqrt(S.vel[0] * S.vel[0] + S.vel[1] * S.vel[1]);
     S.lon_acc = S.acc[0] * S.cyaw + S.acc[1] * S.syaw;
     S.lat_acc = S.acc[0] * (-S.syaw) + S.acc[1] * S.cyaw;
-    map_get_all_with_grad(map, se2, S.tv, S.tg);
+    if (INL) map_get_all_with_grad_impl(map, se2, S.tv, S.tg);
+    else map_get_all_with_grad(map, se2, S.tv, S.tg);
     S.vx = S.v_norm * S.tv[0];
     S.wz = dyaw * S.tv[5];
     S.ax = S.lon_acc * S.tv[0] + gravity * S.tv[1];
     S.ay = S.lat_acc * S.tv[2] + gravity * S.tv[3];
     S.curv_snorm = S.wz * S.wz / (S.vx * S.vx + UALM_DELTA_SIGL);
+}
+
+// out-of-line copy (initScaling) and inlined copy (the per-evaluation penalty loop: keeps the sample state in registers)
+__device__ UALM_NOINLINE void sample_kin(const Traj &t, const DevMap &map, R gravity, int i, R s1, R base_time, SampleK &S)
+{
+    sample_kin_impl<false>(t, map, gravity, i, s1, base_time, S);
 }
 
 // sample-time tables: s1tab[j] = j-fold accumulated step, base[i] = i-fold accumulated T (alm_traj_opt.cpp:713-714, 987-989)
@@ -909,7 +929,7 @@ __device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const 
     for (int s = tid; s < S; s += UALM_THREADS) {
         const int i = s / (K + 1), j = s - i * (K + 1);
         SampleK q;
-        sample_kin(t, map, p.gravity, i, t.s1tab[j], t.base[i], q);
+        sample_kin_impl<true>(t, map, p.gravity, i, t.s1tab[j], t.base[i], q);
         t.yawidx[s] = (unsigned short)q.yaw_idx;
         R grad_p[2] = {0, 0}, grad_v[2] = {0, 0}, grad_a[2] = {0, 0}, grad_se2[3] = {0, 0, 0};
         R grad_yaw = 0, grad_dyaw = 0, grad_vx2 = 0, grad_wz = 0, grad_ax = 0, grad_ay = 0, aug_grad = 0;
@@ -1050,22 +1070,27 @@ __device__ UALM_NOINLINE void penalty_accumulate(Traj &t, int lane)
 {
     const int N = t.N, M = t.M, S = t.S, K = t.K, nx = 6 * N;
     const R *scr = t.scr;
-    // gdCxy: one task per (piece, dim): 6 accumulators over the K+1 samples of the piece, in sample order
+    // gdCxy: one task per (piece, dim): 6 accumulators over the K+1 samples of the piece, in sample order; the next sample's
+    // scratch values are fetched while the current one is accumulated
     for (int q = lane; q < 2 * N; q += 32) {
         const int i = q >> 1, d = q & 1;
         R acc[6] = {0, 0, 0, 0, 0, 0};
+        const R *pgp = scr + (size_t)(SF_GP + d) * S + i * (K + 1), *pgv = scr + (size_t)(SF_GV + d) * S + i * (K + 1),
+                *pga = scr + (size_t)(SF_GA + d) * S + i * (K + 1);
+        R gp = pgp[0], gv = pgv[0], ga = pga[0];
 #pragma unroll 1
         for (int j = 0; j <= K; j++) {
-            const int s = i * (K + 1) + j;
+            const int jn = j < K ? j + 1 : K;
+            const R gpn = pgp[jn], gvn = pgv[jn], gan = pga[jn];
             const R s1 = t.s1tab[j];
             const R s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
-            const R gp = scr[(SF_GP + d) * S + s], gv = scr[(SF_GV + d) * S + s], ga = scr[(SF_GA + d) * S + s];
             acc[0] += (1.0 * gp + 0.0 * gv + 0.0 * ga);
             acc[1] += (s1 * gp + 1.0 * gv + 0.0 * ga);
             acc[2] += (s2 * gp + (2.0 * s1) * gv + 2.0 * ga);
             acc[3] += (s3 * gp + (3.0 * s2) * gv + (6.0 * s1) * ga);
             acc[4] += (s4 * gp + (4.0 * s3) * gv + (12.0 * s2) * ga);
             acc[5] += (s5 * gp + (5.0 * s4) * gv + (20.0 * s3) * ga);
+            gp = gpn; gv = gvn; ga = gan;
         }
 #pragma unroll
         for (int k = 0; k < 6; k++) t.gCxy[6 * i + k + d * nx] = acc[k];
@@ -1073,20 +1098,32 @@ __device__ UALM_NOINLINE void penalty_accumulate(Traj &t, int lane)
     // gdTxy(i): three += per sample (alm_traj_opt.cpp:827, 973-975, 984-985)
     for (int i = lane; i < N; i += 32) {
         R acc = 0.0;
+        R v[16], vn[16];
+        auto fetch = [&](int s, R (&o)[16]) {
+            o[0] = scr[SF_USER * S + s];
+            o[1] = scr[(SF_GP + 0) * S + s]; o[2] = scr[(SF_GP + 1) * S + s];
+            o[3] = scr[(SF_GV + 0) * S + s]; o[4] = scr[(SF_GV + 1) * S + s];
+            o[5] = scr[(SF_GA + 0) * S + s]; o[6] = scr[(SF_GA + 1) * S + s];
+            o[7] = scr[(SF_VEL + 0) * S + s]; o[8] = scr[(SF_VEL + 1) * S + s];
+            o[9] = scr[(SF_ACC + 0) * S + s]; o[10] = scr[(SF_ACC + 1) * S + s];
+            o[11] = scr[(SF_JER + 0) * S + s]; o[12] = scr[(SF_JER + 1) * S + s];
+            o[13] = scr[SF_GYAW * S + s]; o[14] = scr[SF_GDYAW * S + s];
+            o[15] = scr[SF_DYAW * S + s];
+        };
+        fetch(i * (K + 1), v);
+        R d2y = scr[SF_D2YAW * S + i * (K + 1)];
 #pragma unroll 1
         for (int j = 0; j <= K; j++) {
-            const int s = i * (K + 1) + j;
+            const int sn = i * (K + 1) + (j < K ? j + 1 : K);
+            fetch(sn, vn);
+            const R d2yn = scr[SF_D2YAW * S + sn];
             const R alpha = 1.0 / (R)K * (R)j;
-            acc += scr[SF_USER * S + s] / (R)K;
-            const R gp0 = scr[(SF_GP + 0) * S + s], gp1 = scr[(SF_GP + 1) * S + s];
-            const R gv0 = scr[(SF_GV + 0) * S + s], gv1 = scr[(SF_GV + 1) * S + s];
-            const R ga0 = scr[(SF_GA + 0) * S + s], ga1 = scr[(SF_GA + 1) * S + s];
-            const R ve0 = scr[(SF_VEL + 0) * S + s], ve1 = scr[(SF_VEL + 1) * S + s];
-            const R ac0 = scr[(SF_ACC + 0) * S + s], ac1 = scr[(SF_ACC + 1) * S + s];
-            const R je0 = scr[(SF_JER + 0) * S + s], je1 = scr[(SF_JER + 1) * S + s];
-            acc += ((gp0 * ve0 + gp1 * ve1) + (gv0 * ac0 + gv1 * ac1) + (ga0 * je0 + ga1 * je1)) * alpha;
-            const R gy = scr[SF_GYAW * S + s], gdy = scr[SF_GDYAW * S + s];
-            acc += (gy * scr[SF_DYAW * S + s] + gdy * scr[SF_D2YAW * S + s]) * (alpha + (R)i);
+            acc += v[0] / (R)K;
+            acc += ((v[1] * v[7] + v[2] * v[8]) + (v[3] * v[9] + v[4] * v[10]) + (v[5] * v[11] + v[6] * v[12])) * alpha;
+            acc += (v[13] * v[15] + v[14] * d2y) * (alpha + (R)i);
+#pragma unroll
+            for (int q = 0; q < 16; q++) v[q] = vn[q];
+            d2y = d2yn;
         }
         t.gTxy[i] = acc;
     }
