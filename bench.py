@@ -36,6 +36,14 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this round."""
+    p = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(p):
+        return json.load(open(p))
+    return {}
+
+
 def get_map(name):
     from uneven_planner_b200 import maps
     m = maps.get_terrain(name)
@@ -146,6 +154,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--ref-sample", type=int, default=512, dest="ref_sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--big-batch", type=int, default=4096, dest="big_batch", help="extra single-launch throughput datapoint (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -253,14 +262,29 @@ def main():
     pen_b, lb_b, mc_b = algorithmic_bytes(pb, res, K)
     alg = pen_b + lb_b + mc_b
     achieved = alg / (solve_ms * 1e-3) / 1e9
-    roof = {"kernel": "ualm::solve_kernel (whole ALM/L-BFGS solve, one CTA per trajectory)", "bound": "hbm", "achieved": achieved, "peak": peak,
-            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": solve_ms,
+    traffic = load_traffic()
+    roof = {"kernel": "ualm::solve_kernel (whole ALM/L-BFGS solve, one warp per trajectory)", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic.get("solve_kernel_bytes_per_launch_b1024") if args.batch == 1024 else None,
+            "peak_source": peak_src, "kernel_ms": solve_ms,
             "algorithmic_bytes": {"penalty": pen_b, "lbfgs": lb_b, "minco_io": mc_b},
-            "note": "latency-bound by design in this round: bit-reproducible sequential reductions (see DESIGN.md)"}
+            "note": "latency-bound: bit-reproducible fp64, one warp per trajectory (DESIGN.md section 4)"}
     pms, pbytes = opt.time_penalty_kernel(5)
     roof_pen = {"kernel": "ualm::penalty_only_kernel (calConstrainCostGrad samples + accumulation, 1 evaluation per trajectory)",
                 "bound": "hbm", "achieved": pbytes / (pms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": pbytes / (pms * 1e-3) / 1e9 / peak, "traffic": None, "kernel_ms": pms}
+                "frac": pbytes / (pms * 1e-3) / 1e9 / peak,
+                "traffic": traffic.get("penalty_only_kernel_bytes_per_launch_b1024") if args.batch == 1024 else None, "kernel_ms": pms}
+
+    # ---------------- throughput with the GPU kept full: 4x the batch in one launch (single GPU only, outside the timed region)
+    big = None
+    if world == 1 and args.big_batch > 0:
+        pbb = problems.generate(m, args.big_batch, seed=args.seed + 1)
+        opt.upload(pbb)
+        opt.solve_resident(); opt.sync()
+        bms, _ = opt.last_solve_ms()
+        rb, _, _ = opt.download()
+        big = {"batch": args.big_batch, "kernel_ms": bms, "solved_per_s": args.big_batch / bms * 1e3,
+               "converged_per_s": sum(1 for r in rb if r.ret_code == 0) / bms * 1e3}
+        opt.upload(pb)
 
     # ---------------- CPU baseline on this box's host cores (rank 0, bounded sample) ----------------
     cpu = None
@@ -289,7 +313,7 @@ def main():
                            "l2": "per-step working set (L-BFGS history + sample scratch, %.0f MB) exceeds the 126 MB L2; the 41 MB map is reused within a step" % ((lb_b and (8.0 * 2 * params.mem_size * float(pb.nvar().sum())) / 1e6))},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
                 "gpu_launches": int((launches + 1) * args.steps),
-                "clocks": clocks, "roofline": roof, "roofline_penalty": roof_pen, "cpu_baseline": cpu,
+                "clocks": clocks, "roofline": roof, "roofline_penalty": roof_pen, "cpu_baseline": cpu, "large_batch": big,
                 "work": {"evals_per_step": int(sum(r.n_evals for r in res)), "lbfgs_iters_per_step": int(sum(r.n_lbfgs_iters for r in res)), "rank0_batch": pb.B}}
         print(json.dumps(line))
     opt.close()
