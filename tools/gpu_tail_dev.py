@@ -14,9 +14,8 @@ raw = (C.c_longlong * (B * 16))()
 opt.L.ualm_profile(opt.h, 2, raw)
 pr = np.array(raw).reshape(B, 16)
 res, _, _ = opt.download()
-order = np.argsort(-pb.nsamples(16), kind="stable")
-tot = pr[:, 15] / 1.965e6  # ms, rows in launch order
-N = pb.N[order]; ev = np.array([res[i].n_evals for i in order]); ret = np.array([res[i].ret_code for i in order])
+tot = pr[:, 15] / 1.965e6  # ms, rows in problem order
+N = pb.N; ev = np.array([res[i].n_evals for i in range(B)]); ret = np.array([res[i].ret_code for i in range(B)])
 print("kernel ms", ms, "mean traj ms", tot.mean(), "max", tot.max(), "p50 p90 p99", np.percentile(tot, [50, 90, 99]))
 idx = np.argsort(-tot)[:12]
 for i in idx: print("slot", i, "N", N[i], "evals", ev[i], "ret", ret[i], "ms %.1f" % tot[i], "ms/eval %.3f" % (tot[i] / ev[i]))

@@ -6,6 +6,8 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -57,6 +59,15 @@ struct ualm_ctx {
     long long tot_x = 0, tot_s = 0, tot_cxy = 0, tot_cyaw = 0, tot_hist = 0, tot_scr = 0, tot_fac = 0, tot_ws = 0;
     DevBuf<ProbDesc> d_desc;
     DevBuf<int> d_order;
+    DevBuf<int4> d_wdesc;
+    std::vector<int4> wdesc;
+    std::vector<int> group;      // warps per problem (1, 2 or 4)
+    int group_mode = 1;
+    struct GClass { int G = 1, n_ctas = 0, r0 = 0, r1 = 0, occ = 1; size_t wd_off = 0, smem = 0; SmemLayout L; };
+    std::vector<GClass> cls;
+    enum { NAUX = 7 };
+    cudaStream_t aux[NAUX] = {};
+    cudaEvent_t evs[NAUX + 1] = {};
     DevBuf<double> d_x0, d_x, d_lambda, d_mu, d_scale_cx, d_hx, d_gx, d_lm_s, d_lm_y, d_lm_aux, d_fac, d_scr, d_ws, d_cxy, d_cyaw, d_f, d_grad, d_sfx;
     DevBuf<ualm_result_t> d_res;
     DevBuf<long long> d_prof;
@@ -80,8 +91,11 @@ extern "C" int ualm_create(ualm_ctx_t **out, int device, int precision)
     CK(cudaSetDevice(device));
     ualm_ctx *c = new ualm_ctx();
     c->device = device; c->precision = precision;
+    if (const char *e = getenv("UALM_GROUPS")) c->group_mode = atoi(e);   // 0 = one warp per trajectory everywhere (developer switch)
     CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
+    for (int q = 0; q < ualm_ctx::NAUX; q++) CK(cudaStreamCreateWithFlags(&c->aux[q], cudaStreamNonBlocking));
+    for (int q = 0; q < ualm_ctx::NAUX + 1; q++) CK(cudaEventCreateWithFlags(&c->evs[q], cudaEventDisableTiming));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
     *out = c;
@@ -93,11 +107,13 @@ extern "C" int ualm_destroy(ualm_ctx_t *c)
     if (!c) return UALM_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->cells.release(); c->d_desc.release(); c->d_order.release();
+    c->cells.release(); c->d_desc.release(); c->d_order.release(); c->d_wdesc.release();
     DevBuf<double> *bufs[] = {&c->d_x0, &c->d_x, &c->d_lambda, &c->d_mu, &c->d_scale_cx, &c->d_hx, &c->d_gx, &c->d_lm_s, &c->d_lm_y, &c->d_lm_aux, &c->d_fac,
                               &c->d_scr, &c->d_ws, &c->d_cxy, &c->d_cyaw, &c->d_f, &c->d_grad, &c->d_sfx};
     for (auto *b : bufs) b->release();
     c->d_res.release(); c->d_prof.release();
+    for (int q = 0; q < ualm_ctx::NAUX; q++) cudaStreamDestroy(c->aux[q]);
+    for (int q = 0; q < ualm_ctx::NAUX + 1; q++) cudaEventDestroy(c->evs[q]);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->own_stream);
     delete c;
@@ -163,6 +179,8 @@ static BatchPtrs batch_ptrs(ualm_ctx *c)
 {
     BatchPtrs b;
     b.B = c->B;
+    b.wdesc = c->d_wdesc.p;
+    b.n_leader_slots = 4;
     b.desc = c->d_desc.p; b.order = c->d_order.p; b.x0 = c->d_x0.p; b.x = c->d_x.p;
     b.lambda = c->d_lambda.p; b.mu = c->d_mu.p; b.scale_cx = c->d_scale_cx.p; b.hx = c->d_hx.p; b.gx = c->d_gx.p;
     b.lm_s = c->d_lm_s.p; b.lm_y = c->d_lm_y.p; b.lm_aux = c->d_lm_aux.p; b.fac = c->d_fac.p; b.scratch = c->d_scr.p; b.ws_scaling = c->d_ws.p;
@@ -179,14 +197,124 @@ extern "C" int ualm_upload(ualm_ctx_t *c, int B, const int32_t *N, const int32_t
     if (!c->have_params) return fail(UALM_ESTATE, "ualm_set_params must be called before ualm_upload");
     CK(cudaSetDevice(c->device));
     const int K = c->dp.int_K, m = c->dp.mem_size;
-    c->B = B; c->desc.resize(B); c->order.resize(B);
+    c->B = B; c->desc.resize(B); c->order.resize(B); c->group.assign(B, 1);
     c->Nmax = c->Mmax = c->nmax = c->Smax = 1;
-    long long ox = 0, os = 0, ocx = 0, ocy = 0, oh = 0, oscr = 0, oixy = 0, oiyaw = 0, ofac = 0, ows = 0;
-    std::vector<double> x0;
     for (int b = 0; b < B; b++) {
         ProbDesc &d = c->desc[b];
         if (N[b] < 1 || M[b] < 1 || N[b] > 64 || M[b] > 128) return fail(UALM_ELIMIT, "piece count outside [1,64] x [1,128]");
         d.N = N[b]; d.M = M[b]; d.n = 1 + 2 * (N[b] - 1) + (M[b] - 1); d.S = N[b] * (K + 1);
+        c->Nmax = std::max(c->Nmax, d.N); c->Mmax = std::max(c->Mmax, d.M); c->nmax = std::max(c->nmax, d.n); c->Smax = std::max(c->Smax, d.S);
+    }
+    // launch order: most samples first (longest-processing-time-first keeps the tail short)
+    std::iota(c->order.begin(), c->order.end(), 0);
+    std::stable_sort(c->order.begin(), c->order.end(), [&](int a, int b2) { return c->desc[a].S > c->desc[b2].S; });
+    int rc0 = prepare_launch(c);
+    if (rc0) return rc0;
+    // Warp groups and size classes.  Problems are sorted by size; the largest get 4 or 2 warps (helpers for the parallel
+    // phases) as far as the whole batch still fits on the device at once.  Every (group size, size bucket) class is its own
+    // launch with its own shared-memory layout sized by the class maxima: a G=4 CTA holds one trajectory slot + 3 helper
+    // rings, a G=2 CTA two slots + 2 rings, a G=1 CTA four slots.  The classes run concurrently on separate streams.
+    {
+        int dev_sms = 0;
+        CK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, c->device));
+        const int RINGD = 2 * UALM_RINGB * 6 * UALM_FW;
+        const long long base_ctas = (B + 3) / 4;
+        int occ0 = 1;   // CTAs per SM the register file allows (shared memory is checked per class below)
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, solve_kernel, UALM_THREADS * UALM_WPB, 16 * 1024));
+        if (getenv("UALM_DEBUG")) {
+            cudaFuncAttributes fa;
+            CK(cudaFuncGetAttributes(&fa, solve_kernel));
+            fprintf(stderr, "[ualm] solve_kernel: %d regs/thread, %zu B local, %zu B static smem, %d CTAs/SM by registers\n", fa.numRegs, fa.localSizeBytes,
+                    fa.sharedSizeBytes, occ0);
+        }
+        const long long W = 4LL * occ0 * dev_sms;   // warp slots on the device
+        long long cap = W / 4;
+        std::vector<ualm_ctx::GClass> best;
+        for (int attempt = 0; attempt < 32; attempt++) {
+            // Policy (measured on B200, tools/gpu_policy_dev.py): helpers shorten the latency of a trajectory without adding to the
+            // L2-resident working set, while more resident trajectories than ~600 thrash the 126 MB L2.  So: everything that fits
+            // gets 4 warps; beyond that 2 warps per trajectory with the largest tenth at 4, run in waves.
+            long long K4 = 0, K2 = 0;
+            if (c->group_mode) {
+                if (4LL * B <= W) K4 = B;
+                else if (2LL * B <= W) { K4 = std::min<long long>(B, (W - 2LL * B) / 2); K2 = (B - K4) & ~1LL; }
+                else { K4 = B / 10; K2 = (B - K4) & ~1LL; }
+                if (attempt > 0) { K4 = (long long)(K4 * std::pow(0.8, attempt)); K2 = std::min<long long>(B - K4, K2) & ~1LL; }
+            }
+            const bool forced = getenv("UALM_F4") || getenv("UALM_F2");   // developer override: fractions of the batch
+            if (forced) {
+                K4 = (long long)(B * (getenv("UALM_F4") ? atof(getenv("UALM_F4")) : 0.0));
+                K2 = std::min<long long>(B - K4, (long long)(B * (getenv("UALM_F2") ? atof(getenv("UALM_F2")) : 0.0))) & ~1LL;
+            }
+            // rank ranges per group size, each split into size buckets (the order is by descending size)
+            std::vector<ualm_ctx::GClass> cls;
+            const long long lim[4] = {0, K4, K4 + K2, B};
+            for (int gi = 0; gi < 3; gi++) {
+                const int G = gi == 0 ? 4 : gi == 1 ? 2 : 1;
+                const long long a = lim[gi], b2 = lim[gi + 1];
+                if (b2 <= a) continue;
+                const int nsplit = (b2 - a) >= 96 ? (gi == 2 ? 3 : 2) : 1;
+                for (int sp = 0; sp < nsplit; sp++) {
+                    ualm_ctx::GClass cl;
+                    cl.G = G;
+                    long long s0 = a + (b2 - a) * sp / nsplit, s1 = a + (b2 - a) * (sp + 1) / nsplit;
+                    const int per = 4 / G;                         // problems per CTA
+                    if (sp > 0) s0 = a + ((s0 - a + per - 1) / per) * per;
+                    if (sp + 1 < nsplit) s1 = a + ((s1 - a + per - 1) / per) * per;
+                    if (s1 <= s0) continue;
+                    cl.r0 = (int)s0; cl.r1 = (int)s1;
+                    int Nm = 1, Mm = 1, nm = 1, Sm = 1;
+                    for (long long r = s0; r < s1; r++) {
+                        const ProbDesc &d = c->desc[c->order[r]];
+                        Nm = std::max(Nm, d.N); Mm = std::max(Mm, d.M); nm = std::max(nm, d.n); Sm = std::max(Sm, d.S);
+                    }
+                    cl.L = make_layout(Nm, Mm, nm, c->dp.mem_size, c->dp.past, c->dp.int_K, Sm);
+                    cl.smem = ((size_t)per * cl.L.total_doubles + (size_t)(4 - per) * RINGD) * sizeof(double);
+                    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cl.occ, solve_kernel, UALM_THREADS * UALM_WPB, cl.smem));
+                    cl.n_ctas = (int)((s1 - s0 + per - 1) / per);
+                    cls.push_back(cl);
+                }
+            }
+            double sm_need = 0.0;
+            for (auto &cl : cls) sm_need += (double)cl.n_ctas / std::max(cl.occ, 1);
+            best = cls;
+            // multi-wave batches need not fit at once; batches meant to be fully resident must
+            if (forced || 2LL * B > W || sm_need <= 0.98 * dev_sms || attempt >= 12) break;
+        }
+        c->cls = best;
+        c->wdesc.clear();
+        for (auto &cl : c->cls) {
+            cl.wd_off = c->wdesc.size();
+            for (int r = cl.r0; r < cl.r1; r++) c->group[c->order[r]] = cl.G;
+            int q = cl.r0;
+            while (q < cl.r1) {
+                if (cl.G == 4) {
+                    for (int w = 0; w < 4; w++) c->wdesc.push_back(make_int4(c->order[q], 0, 4, w | ((w ? w - 1 : 0) << 8)));
+                    q += 1;
+                } else if (cl.G == 2) {
+                    for (int h = 0; h < 2; h++) {
+                        if (q < cl.r1) {
+                            c->wdesc.push_back(make_int4(c->order[q], h, 2, 0));
+                            c->wdesc.push_back(make_int4(c->order[q], h, 2, 1 | (h << 8)));
+                            q += 1;
+                        } else { c->wdesc.push_back(make_int4(-1, 0, 1, 0)); c->wdesc.push_back(make_int4(-1, 0, 1, 0)); }
+                    }
+                } else {
+                    for (int w = 0; w < 4; w++) {
+                        if (q < cl.r1) { c->wdesc.push_back(make_int4(c->order[q], w, 1, 0)); q += 1; }
+                        else c->wdesc.push_back(make_int4(-1, 0, 1, 0));
+                    }
+                }
+            }
+            if ((int)((c->wdesc.size() - cl.wd_off) / 4) != cl.n_ctas) return fail(UALM_EINVAL, "internal: class CTA count mismatch");
+            if (getenv("UALM_DEBUG"))
+                fprintf(stderr, "[ualm] class G=%d: problems [%d,%d) %d CTAs, smem %zu B, %d CTAs/SM\n", cl.G, cl.r0, cl.r1, cl.n_ctas, cl.smem, cl.occ);
+        }
+    }
+    long long ox = 0, os = 0, ocx = 0, ocy = 0, oh = 0, oscr = 0, oixy = 0, oiyaw = 0, ofac = 0, ows = 0;
+    std::vector<double> x0;
+    for (int b = 0; b < B; b++) {
+        ProbDesc &d = c->desc[b];
         d.off_x = ox; d.off_s = os; d.off_cxy = ocx; d.off_cyaw = ocy; d.off_hist = oh; d.off_scr = oscr; d.off_fac = ofac; d.off_ws = ows;
         for (int k = 0; k < 18; k++) d.bnd[k] = bnd[(size_t)b * 18 + k];
         d.total_time = total_time[b];
@@ -198,14 +326,10 @@ extern "C" int ualm_upload(ualm_ctx_t *c, int B, const int32_t *N, const int32_t
         oixy += 2 * (d.N - 1); oiyaw += d.M - 1;
         ox += d.n; os += d.S; ocx += 12 * d.N; ocy += 6 * d.M; oh += (long long)m * d.n; oscr += (long long)UALM_NFIELD * d.S;
         ofac += 1LL * UALM_FW * ((6 * d.N + 2 * UALM_FPAD) + (6 * d.M + 2 * UALM_FPAD));
-        ows += (long long)(12 * d.N + 6 * d.M) * 32;
-        c->Nmax = std::max(c->Nmax, d.N); c->Mmax = std::max(c->Mmax, d.M); c->nmax = std::max(c->nmax, d.n); c->Smax = std::max(c->Smax, d.S);
+        ows += (long long)(12 * d.N + 6 * d.M) * 32 * c->group[b];
     }
     c->tot_x = ox; c->tot_s = os; c->tot_cxy = ocx; c->tot_cyaw = ocy; c->tot_hist = oh; c->tot_scr = oscr; c->tot_fac = ofac; c->tot_ws = ows;
-    // launch order: most samples first (longest-processing-time-first keeps the tail short)
-    std::iota(c->order.begin(), c->order.end(), 0);
-    std::stable_sort(c->order.begin(), c->order.end(), [&](int a, int b2) { return c->desc[a].S > c->desc[b2].S; });
-    CK(c->d_desc.ensure(B)); CK(c->d_order.ensure(B)); CK(c->d_x0.ensure(ox)); CK(c->d_x.ensure(ox)); CK(c->d_grad.ensure(ox));
+    CK(c->d_desc.ensure(B)); CK(c->d_order.ensure(B)); CK(c->d_wdesc.ensure(c->wdesc.size())); CK(c->d_x0.ensure(ox)); CK(c->d_x.ensure(ox)); CK(c->d_grad.ensure(ox));
     CK(c->d_lambda.ensure(os)); CK(c->d_hx.ensure(os)); CK(c->d_mu.ensure(6 * os)); CK(c->d_gx.ensure(6 * os)); CK(c->d_scale_cx.ensure(7 * os));
     CK(c->d_lm_s.ensure(oh)); CK(c->d_lm_y.ensure(oh)); CK(c->d_scr.ensure(oscr));
     CK(c->d_ws.ensure(ows)); CK(c->d_fac.ensure(ofac)); CK(c->d_lm_aux.ensure((size_t)std::max(B, 1) * 2 * m));
@@ -216,11 +340,12 @@ extern "C" int ualm_upload(ualm_ctx_t *c, int B, const int32_t *N, const int32_t
     if (B > 0) {
         CK(cudaMemcpyAsync(c->d_desc.p, c->desc.data(), sizeof(ProbDesc) * B, cudaMemcpyHostToDevice, c->stream));
         CK(cudaMemcpyAsync(c->d_order.p, c->order.data(), sizeof(int) * B, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_wdesc.p, c->wdesc.data(), sizeof(int4) * c->wdesc.size(), cudaMemcpyHostToDevice, c->stream));
         CK(cudaMemcpyAsync(c->d_x0.p, x0.data(), sizeof(double) * ox, cudaMemcpyHostToDevice, c->stream));
         CK(cudaStreamSynchronize(c->stream)); // x0 is a stack-local staging vector
     }
     c->have_batch = true; c->solved = false;
-    return prepare_launch(c);
+    return UALM_OK;
 }
 
 extern "C" int ualm_solve_resident(ualm_ctx_t *c)
@@ -231,9 +356,23 @@ extern "C" int ualm_solve_resident(ualm_ctx_t *c)
     c->last_launches = 0;
     CK(cudaEventRecord(c->ev0, c->stream));
     if (c->B > 0) {
-        solve_kernel<<<(c->B + UALM_WPB - 1) / UALM_WPB, UALM_THREADS * UALM_WPB, c->smem_bytes, c->stream>>>(batch_ptrs(c), c->dp, c->dm, c->L);
-        CK(cudaGetLastError());
-        c->last_launches = 1;
+        // the classes run concurrently: class 0 on the context stream, the others on auxiliary streams
+        const int last = ualm_ctx::NAUX;
+        CK(cudaEventRecord(c->evs[last], c->stream));
+        for (size_t ci = 0; ci < c->cls.size(); ci++) {
+            auto &cl = c->cls[ci];
+            if (cl.n_ctas == 0) continue;
+            const int ai = (int)((ci - 1) % ualm_ctx::NAUX);
+            cudaStream_t st = ci == 0 ? c->stream : c->aux[ai];
+            if (ci > 0) CK(cudaStreamWaitEvent(st, c->evs[last], 0));
+            BatchPtrs bp = batch_ptrs(c);
+            bp.wdesc = c->d_wdesc.p + cl.wd_off;
+            bp.n_leader_slots = 4 / cl.G;
+            solve_kernel<<<cl.n_ctas, UALM_THREADS * UALM_WPB, cl.smem, st>>>(bp, c->dp, c->dm, cl.L);
+            CK(cudaGetLastError());
+            c->last_launches++;
+            if (ci > 0) { CK(cudaEventRecord(c->evs[ai], st)); CK(cudaStreamWaitEvent(c->stream, c->evs[ai], 0)); }
+        }
     }
     CK(cudaEventRecord(c->ev1, c->stream));
     c->solved = true;

@@ -30,6 +30,7 @@
 #define UALM_FW 14              // doubles per factor row (13 band entries + 1 pad -> 112 B = 7 x 16 B)
 #define UALM_FPAD 8             // zero pad rows before and after each factor array (chunked prefetch may overrun)
 #define UALM_SYNC() __syncwarp()
+#define UALM_RINGB 4            // factor-ring depth in 6-row blocks per system (prefetch distance UALM_RINGB - 2)
 
 namespace ualm {
 
@@ -85,6 +86,8 @@ struct ProbDesc {
 
 struct BatchPtrs {
     int B;
+    const int4 *wdesc;       // solve_kernel: per warp slot {problem (-1 = idle), leader slot in CTA, group size, warp in group | helper ring << 8}
+    int n_leader_slots;      // solve_kernel: full per-trajectory slots per CTA (4 / G); helper rings follow them
     const ProbDesc *desc;
     const int *order;        // launch order (largest first); blockIdx.x -> problem index
     const R *x0;             // packed initial decision vectors
@@ -136,9 +139,14 @@ __host__ __device__ inline SmemLayout make_layout(int Nmax, int Mmax, int nmax, 
     L.base = o; o += Nmax;
     L.sc = o; o += 48;                   // scalars
     o = (o + 1) & ~1;                    // 16-byte alignment for the cp.async destinations
-    L.win = o; o += 2 * 16 * UALM_FW;    // LU sliding windows: 16 row slots per system
-    L.tmpl = o; o += 2 * 12 * UALM_FW;   // template rows of A per system
-    L.ring = o; o += 2 * 8 * 6 * UALM_FW; // factor prefetch rings: 8 blocks of 6 rows per system
+    // LU scratch (sliding windows + template rows) and the factor ring of the sweeps are never live at the same time: they alias
+    L.win = o;
+    L.tmpl = o + 2 * 16 * UALM_FW;
+    L.ring = o;
+    {
+        const int lu = 2 * 16 * UALM_FW + 2 * 12 * UALM_FW, rg = 2 * UALM_RINGB * 6 * UALM_FW;
+        o += lu > rg ? lu : rg;
+    }
     L.roles = o; o += (12 * 16 + 3) / 4;  // shorts packed
     L.yawidx = o; o += (Smax + 3) / 4;   // shorts packed
     L.total_doubles = (o + 1) & ~1;
@@ -149,7 +157,7 @@ __host__ __device__ inline SmemLayout make_layout(int Nmax, int Mmax, int nmax, 
 // scalar slots in sm[L.sc + ...]
 enum {
     SC_TX1 = 0, SC_TX2, SC_TX3, SC_TX4, SC_TX5, SC_TY1, SC_TY2, SC_TY3, SC_TY4, SC_TY5,
-    SC_SCALE_FX, SC_RHO, SC_F, SC_JERK, SC_CONSTR, SC_TAUCOST, SC_JERKRAW, SC_RTY
+    SC_SCALE_FX, SC_RHO, SC_F, SC_JERK, SC_CONSTR, SC_TAUCOST, SC_JERKRAW, SC_RTY, SC_CMD
 };
 
 // Handles to shared memory: a 32-bit address in the shared state space.  Accesses through them are explicit ld.shared /
@@ -214,6 +222,11 @@ struct Traj {
     R *lambda, *mu, *scale_cx, *hx, *gx, *lm_s, *lm_y, *lm_alpha, *lm_ys, *scr;
     R *Fxy, *Fyaw;                  // row 0 of each factor array
     R *ws;
+    // warp group of this trajectory: G warps (1, 2 or 4) of one CTA; warp 0 of the group (the leader) runs the whole algorithm,
+    // the others (helpers) only execute the parallel phases the leader posts (samples, gradient accumulation, initScaling)
+    int G, wig, barid;
+    SPtr hring;        // this warp's own factor ring (initScaling sweeps run per warp)
+    R *wsw;            // this warp's own initScaling workspace
     int n_evals;
     long long *prof;   // shared-memory phase counters (lane 0 only)
     long long *plast;
@@ -228,6 +241,23 @@ __device__ __forceinline__ void prof_mark(const Traj &t, int tid, int phase)
         const long long c = clock64();
         t.prof[phase] += c - *t.plast;
         *t.plast = c;
+    }
+}
+
+// ---- leader / helper protocol inside a warp group (named barrier 1 + leader warp index, 32*G participants) ----
+enum { CMD_SAMPLES = 1, CMD_ACCUM = 2, CMD_SCALE = 3, CMD_EXIT = 4 };
+__device__ __forceinline__ void group_bar(const Traj &t)
+{
+    if (t.G > 1) asm volatile("bar.sync %0, %1;" ::"r"(t.barid), "r"(32 * t.G) : "memory");
+    else __syncwarp();
+}
+// leader: publish the next parallel phase and release the helpers (no-op for a single-warp group)
+__device__ __forceinline__ void group_post(const Traj &t, int lane, int cmd)
+{
+    if (t.G > 1) {
+        if (lane == 0) t.sc[SC_CMD] = (R)cmd;
+        __syncwarp();
+        group_bar(t);
     }
 }
 
@@ -588,13 +618,13 @@ __device__ UALM_NOINLINE void sweep(const R *facA, int PA, const R *facB, int PB
         if (c < PA) {
             const int blk = ASC ? c : PA - 1 - c;
             const R *src = facA + (long long)blk * BLK;
-            const SPtr dst = ringA + (c & 7) * BLK;
+            const SPtr dst = ringA + (c % UALM_RINGB) * BLK;
             for (int p = lane; p < BLK / 2; p += 32) cp_async16(dst.a + 16u * (unsigned)p, src + 2 * p);
         }
         if (DUAL && c < PB) {
             const int blk = ASC ? c : PB - 1 - c;
             const R *src = facB + (long long)blk * BLK;
-            const SPtr dst = ringB + (c & 7) * BLK;
+            const SPtr dst = ringB + (c % UALM_RINGB) * BLK;
             for (int p = lane; p < BLK / 2; p += 32) cp_async16(dst.a + 16u * (unsigned)p, src + 2 * p);
         }
         cp_async_commit();
@@ -603,16 +633,16 @@ __device__ UALM_NOINLINE void sweep(const R *facA, int PA, const R *facB, int PB
     const int myP = (DUAL && sel) ? PB : PA;
     const SPtr myring = (DUAL && sel) ? ringB : ringA;
     // cstart (ascending kinds only): blocks before it hold an all-zero right-hand side, whose solution is zero as well
-    issue(cstart); issue(cstart + 1); issue(cstart + 2); issue(cstart + 3);
+    for (int q = 0; q < UALM_RINGB - 2; q++) issue(cstart + q);
 #pragma unroll 1
     for (int c = cstart; c < nb; c++) {
-        issue(c + 4);
-        cp_async_wait<4>();
+        issue(c + UALM_RINGB - 2);
+        cp_async_wait<UALM_RINGB - 2>();
         UALM_SYNC();
         if (active && c < myP) {
             const int blk = ASC ? c : myP - 1 - c;
-            const SPtr chunk = myring + (c & 7) * BLK;
-            const SPtr nbr = myring + ((c + 7) & 7) * BLK;      // the block processed just before (still in the ring)
+            const SPtr chunk = myring + (c % UALM_RINGB) * BLK;
+            const SPtr nbr = myring + ((c + UALM_RINGB - 1) % UALM_RINGB) * BLK;      // the block processed just before (still in the ring)
             const bool hasnb = c > cstart;
             if (LKIND && blk == myP - 1) sweep_block<KIND, NCOL, true, BP>(chunk, nbr, hasnb, b0, b1, bst, 6 * blk, prev0, prev1);
             else sweep_block<KIND, NCOL, false, BP>(chunk, nbr, hasnb, b0, b1, bst, 6 * blk, prev0, prev1);
@@ -662,8 +692,8 @@ __device__ UALM_NOINLINE void minco_generate(Traj &t, int lane)
     // lanes 0/1: x / y columns against the xy factors; lane 2: the yaw column, all in lockstep
     {
         const SPtr col = lane < 2 ? t.cxy + lane * nx : t.cyaw;
-        sweep<0, 1, true, SPtr>(t.Fxy, N, t.Fyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
-        sweep<1, 1, true, SPtr>(t.Fxy, N, t.Fyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
+        sweep<0, 1, true, SPtr>(t.Fxy, N, t.Fyaw, M, t.ring, t.ring + UALM_RINGB * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
+        sweep<1, 1, true, SPtr>(t.Fxy, N, t.Fyaw, M, t.ring, t.ring + UALM_RINGB * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
     }
     UALM_SYNC();
     prof_mark(t, lane, PF_SOLVE);
@@ -919,14 +949,14 @@ __device__ UALM_NOINLINE void sample_tables(Traj &t, int lane)
 // calConstrainCostGrad, phase A: one lane per sample (alm_traj_opt.cpp:710-964).  Writes hx/gx, the 8 cost
 // terms and the per-sample gradients to the scratch; phase B accumulates them in the reference's order.
 // ---------------------------------------------------------------------------------------------
-__device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const DevParams &p, int tid)
+__device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const DevParams &p, int gtid, int GT)
 {
     const int S = t.S, K = t.K;
     const R rho = t.sc[SC_RHO], scale_fx = t.sc[SC_SCALE_FX];
     const R rrho = ((__double_as_longlong(rho) & 0xFFFFFFFFFFFFFll) == 0xFFFFFFFFFFFFFll) ? __longlong_as_double(0x7ff8000000000000ll) : 1.0 / rho;   // RN(1/rho): x / rho below is formed as div_by_recip(x, rho, rrho), bit-identical to the IEEE quotient
     const R step = t.sc[SC_TX1] / (R)K;
     R *scr = t.scr;
-    for (int s = tid; s < S; s += UALM_THREADS) {
+    for (int s = gtid; s < S; s += GT) {
         const int i = s / (K + 1), j = s - i * (K + 1);
         SampleK q;
         sample_kin_impl<true>(t, map, p.gravity, i, t.s1tab[j], t.base[i], q);
@@ -1061,18 +1091,17 @@ __device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const 
         scr[SF_DYAW * S + s] = q.dyaw; scr[SF_D2YAW * S + s] = q.d2yaw;
         scr[SF_S1YAW * S + s] = q.y0[1];
     }
-    UALM_SYNC();
 }
 
 // phase B: accumulate in the reference's order (alm_traj_opt.cpp:825-946 cost; :969-985 gradients).  Homogeneous rounds of
 // 32 tasks: (piece, dim) coefficient-gradient blocks, per-piece time gradients, yaw blocks; then the cost chain.
-__device__ UALM_NOINLINE void penalty_accumulate(Traj &t, int lane)
+__device__ UALM_NOINLINE void accumulate_tasks(Traj &t, int gtid, int GT)
 {
     const int N = t.N, M = t.M, S = t.S, K = t.K, nx = 6 * N;
     const R *scr = t.scr;
     // gdCxy: one task per (piece, dim): 6 accumulators over the K+1 samples of the piece, in sample order; the next sample's
     // scratch values are fetched while the current one is accumulated
-    for (int q = lane; q < 2 * N; q += 32) {
+    for (int q = gtid; q < 2 * N; q += GT) {
         const int i = q >> 1, d = q & 1;
         R acc[6] = {0, 0, 0, 0, 0, 0};
         const R *pgp = scr + (size_t)(SF_GP + d) * S + i * (K + 1), *pgv = scr + (size_t)(SF_GV + d) * S + i * (K + 1),
@@ -1096,7 +1125,7 @@ __device__ UALM_NOINLINE void penalty_accumulate(Traj &t, int lane)
         for (int k = 0; k < 6; k++) t.gCxy[6 * i + k + d * nx] = acc[k];
     }
     // gdTxy(i): three += per sample (alm_traj_opt.cpp:827, 973-975, 984-985)
-    for (int i = lane; i < N; i += 32) {
+    for (int i = gtid; i < N; i += GT) {
         R acc = 0.0;
         R v[16], vn[16];
         auto fetch = [&](int s, R (&o)[16]) {
@@ -1129,7 +1158,7 @@ __device__ UALM_NOINLINE void penalty_accumulate(Traj &t, int lane)
     }
     // gdCyaw block m and gdTyaw(m): the samples with yaw_idx == m in ascending sample order.  yaw_idx is monotone in the
     // sample index up to rounding at piece boundaries, so only a window around the block's time span is scanned.
-    for (int m = lane; m < M; m += 32) {
+    for (int m = gtid; m < M; m += GT) {
         R acc[6] = {0, 0, 0, 0, 0, 0};
         R accT = 0.0;
         const R ratio = (R)(K + 1) * (R)N / (R)M;   // samples per yaw piece
@@ -1154,6 +1183,13 @@ __device__ UALM_NOINLINE void penalty_accumulate(Traj &t, int lane)
         for (int k = 0; k < 6; k++) t.gCyaw[6 * m + k] = acc[k];
         t.gTyaw[m] = accT;
     }
+}
+
+// the cost chain of calConstrainCostGrad (alm_traj_opt.cpp:825-943) on the leader warp
+__device__ UALM_NOINLINE void cost_chain(Traj &t, int lane)
+{
+    const int S = t.S;
+    const R *scr = t.scr;
     // cost chain: 8 terms per sample in sample order on lane 0; the terms are fetched 32 samples at a time by all lanes
     // and handed over by shuffles so the loads stay off the dependent chain
     {
@@ -1171,7 +1207,6 @@ __device__ UALM_NOINLINE void penalty_accumulate(Traj &t, int lane)
         }
         if (lane == 0) t.sc[SC_CONSTR] = cost;
     }
-    UALM_SYNC();
 }
 
 // gdT(i) += B1 . adj  (se2traj.hpp:763-814); adj = solved adjoint vector (element stride st), Dim columns
@@ -1217,9 +1252,19 @@ __device__ UALM_NOINLINE void evaluate(Traj &t, const DevMap &map, const DevPara
     prof_mark(t, lane, PF_JERK);
     sample_tables(t, lane);
     prof_mark(t, lane, PF_TABLES);
-    penalty_samples(t, map, p, lane);
+    group_post(t, lane, CMD_SAMPLES);
+    penalty_samples(t, map, p, lane, 32 * t.G);
+    group_bar(t);
     prof_mark(t, lane, PF_SAMPLES);
-    penalty_accumulate(t, lane);
+    if (t.G > 1) {          // helpers sum the gradient entries while the leader runs the sequential cost chain
+        group_post(t, lane, CMD_ACCUM);
+        cost_chain(t, lane);
+        group_bar(t);
+    } else {
+        accumulate_tasks(t, lane, 32);
+        cost_chain(t, lane);
+        UALM_SYNC();
+    }
     prof_mark(t, lane, PF_ACCUM);
     // combine jerk and constraint gradients (alm_traj_opt.cpp:322-332); the jerk gradient is formed on the fly
     const R scale_fx = t.sc[SC_SCALE_FX];
@@ -1258,8 +1303,8 @@ __device__ UALM_NOINLINE void evaluate(Traj &t, const DevMap &map, const DevPara
     // calGradCTtoQT (se2traj.hpp:751-816): adjoint solves in place in gCxy / gCyaw
     {
         const SPtr col = lane < 2 ? t.gCxy + lane * nx : t.gCyaw;
-        sweep<2, 1, true, SPtr>(t.Fxy, N, t.Fyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
-        sweep<3, 1, true, SPtr>(t.Fxy, N, t.Fyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
+        sweep<2, 1, true, SPtr>(t.Fxy, N, t.Fyaw, M, t.ring, t.ring + UALM_RINGB * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
+        sweep<3, 1, true, SPtr>(t.Fxy, N, t.Fyaw, M, t.ring, t.ring + UALM_RINGB * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
     }
     UALM_SYNC();
     prof_mark(t, lane, PF_ADJ);
@@ -1506,23 +1551,22 @@ __device__ UALM_NOINLINE LbfgsOut lbfgs_optimize(Traj &t, const DevMap &map, con
 // initScaling (alm_traj_opt.cpp:349-661): one task per constraint (sample x 7), 32 tasks at a time, each lane running
 // the reference's adjoint solves on its own interleaved workspace column while the whole warp streams the factors.
 // ---------------------------------------------------------------------------------------------
-__device__ UALM_NOINLINE void init_scaling(Traj &t, const DevMap &map, const DevParams &p, int lane)
+// the per-constraint part of initScaling: GT threads of the warp group take GT constraint samples at a time
+__device__ UALM_NOINLINE void scaling_rounds(Traj &t, const DevMap &map, const DevParams &p, int gtid, int GT, int lane)
 {
     const int N = t.N, M = t.M, S = t.S, K = t.K, nx = 6 * N, ny = 6 * M;
-    minco_generate(t, lane);
-    sample_tables(t, lane);
     const R tau = t.x[0];
     const R dTdtau = getTtoTauGrad(tau);
     const R step = t.sc[SC_TX1] / (R)K;
     const R Tx1 = t.sc[SC_TX1], Tx2 = t.sc[SC_TX2], Tx3 = t.sc[SC_TX3], Tx4 = t.sc[SC_TX4], Tx5 = t.sc[SC_TX5];
     const R Ty1 = t.sc[SC_TY1], Ty2 = t.sc[SC_TY2], Ty3 = t.sc[SC_TY3], Ty4 = t.sc[SC_TY4], Ty5 = t.sc[SC_TY5];
     const int st = 32;
-    R *wx = t.ws + lane;                       // x column: rows 0..nx-1 at stride 32
-    R *wy = t.ws + (size_t)nx * st + lane;     // y column
-    R *ww = t.ws + (size_t)2 * nx * st + lane; // yaw
+    R *wx = t.wsw + lane;                       // x column: rows 0..nx-1 at stride 32
+    R *wy = t.wsw + (size_t)nx * st + lane;     // y column
+    R *ww = t.wsw + (size_t)2 * nx * st + lane; // yaw
     R *scr = t.scr;
-    for (int s0 = 0; s0 < S; s0 += 32) {
-        const int s = s0 + lane;
+    for (int s0 = 0; s0 < S; s0 += GT) {
+        const int s = s0 + gtid;
         const bool act = s < S;
         SampleK q;
         int i = 0, j = 0;
@@ -1633,10 +1677,10 @@ __device__ UALM_NOINLINE void init_scaling(Traj &t, const DevMap &map, const Dev
                 bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, off));
                 by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, off));
             }
-            sweep<2, 2, false, R *>(t.Fxy, N, nullptr, 0, t.ring, t.ring, wx, wy, st, 0, act, lane, bx0);
-            sweep<3, 2, false, R *>(t.Fxy, N, nullptr, 0, t.ring, t.ring, wx, wy, st, 0, act, lane);
-            sweep<2, 1, false, R *>(t.Fyaw, M, nullptr, 0, t.ring, t.ring, ww, ww, st, 0, act, lane, by0);
-            sweep<3, 1, false, R *>(t.Fyaw, M, nullptr, 0, t.ring, t.ring, ww, ww, st, 0, act, lane);
+            sweep<2, 2, false, R *>(t.Fxy, N, nullptr, 0, t.hring, t.hring, wx, wy, st, 0, act, lane, bx0);
+            sweep<3, 2, false, R *>(t.Fxy, N, nullptr, 0, t.hring, t.hring, wx, wy, st, 0, act, lane);
+            sweep<2, 1, false, R *>(t.Fyaw, M, nullptr, 0, t.hring, t.hring, ww, ww, st, 0, act, lane, by0);
+            sweep<3, 1, false, R *>(t.Fyaw, M, nullptr, 0, t.hring, t.hring, ww, ww, st, 0, act, lane);
             if (act) {
                 R m1 = 0.0, m2 = 0.0;
                 for (int r = 0; r < N - 1; r++) {
@@ -1647,7 +1691,7 @@ __device__ UALM_NOINLINE void init_scaling(Traj &t, const DevMap &map, const Dev
                 R sx = 0.0, sy = 0.0;
                 for (int r = 0; r < N; r++) {
                     R gT = (r == i) ? dTx : 0.0;
-                    gT += adj_time_term(t.cxy, nx, t.ws + lane, nx * st, st, 2, r, N, Tx1, Tx2, Tx3, Tx4);
+                    gT += adj_time_term(t.cxy, nx, t.wsw + lane, nx * st, st, 2, r, N, Tx1, Tx2, Tx3, Tx4);
                     sx += gT;
                 }
                 for (int r = 0; r < M; r++) {
@@ -1660,7 +1704,22 @@ __device__ UALM_NOINLINE void init_scaling(Traj &t, const DevMap &map, const Dev
             }
         }
     }
-    UALM_SYNC();
+    }
+
+__device__ UALM_NOINLINE void init_scaling(Traj &t, const DevMap &map, const DevParams &p, int lane)
+{
+    const int N = t.N, M = t.M, S = t.S, K = t.K, nx = 6 * N, ny = 6 * M;
+    minco_generate(t, lane);
+    sample_tables(t, lane);
+    const R tau = t.x[0];
+    const R dTdtau = getTtoTauGrad(tau);
+    const R step = t.sc[SC_TX1] / (R)K;
+    const R Tx1 = t.sc[SC_TX1], Tx2 = t.sc[SC_TX2], Tx3 = t.sc[SC_TX3], Tx4 = t.sc[SC_TX4], Tx5 = t.sc[SC_TX5];
+    const R Ty1 = t.sc[SC_TY1], Ty2 = t.sc[SC_TY2], Ty3 = t.sc[SC_TY3], Ty4 = t.sc[SC_TY4], Ty5 = t.sc[SC_TY5];
+    R *scr = t.scr;
+    group_post(t, lane, CMD_SCALE);
+    scaling_rounds(t, map, p, lane, 32 * t.G, lane);
+    group_bar(t);
     // ---- f gradient: jerk gradient (formed on the fly) + user cost (alm_traj_opt.cpp:507-519), then adjoint ----
     for (int qq = lane; qq < 2 * N; qq += 32) {
         const int i = qq >> 1, d = qq & 1;
@@ -1709,8 +1768,8 @@ __device__ UALM_NOINLINE void init_scaling(Traj &t, const DevMap &map, const Dev
     UALM_SYNC();
     {
         const SPtr col = lane < 2 ? t.gCxy + lane * nx : t.gCyaw;
-        sweep<2, 1, true, SPtr>(t.Fxy, N, t.Fyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
-        sweep<3, 1, true, SPtr>(t.Fxy, N, t.Fyaw, M, t.ring, t.ring + 8 * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
+        sweep<2, 1, true, SPtr>(t.Fxy, N, t.Fyaw, M, t.ring, t.ring + UALM_RINGB * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
+        sweep<3, 1, true, SPtr>(t.Fxy, N, t.Fyaw, M, t.ring, t.ring + UALM_RINGB * 6 * UALM_FW, col, col, 1, lane == 2, lane < 3, lane);
     }
     UALM_SYNC();
     for (int q = lane; q < N + M; q += 32) {
@@ -1734,7 +1793,7 @@ __device__ UALM_NOINLINE void init_scaling(Traj &t, const DevMap &map, const Dev
 // ---------------------------------------------------------------------------------------------
 // set up the Traj view of one problem
 // ---------------------------------------------------------------------------------------------
-__device__ UALM_NOINLINE void traj_setup(Traj &t, const BatchPtrs &bp, const DevParams &p, const SmemLayout &L, unsigned sm, int prob)
+__device__ UALM_NOINLINE void traj_setup(Traj &t, const BatchPtrs &bp, const DevParams &p, const SmemLayout &L, unsigned sm, unsigned sm_own, int prob, int G, int wig, int leader)
 {
     const ProbDesc *pd = bp.desc + prob;
     t.pd = pd; t.N = pd->N; t.M = pd->M; t.n = pd->n; t.S = pd->S; t.K = p.int_K;
@@ -1744,7 +1803,7 @@ __device__ UALM_NOINLINE void traj_setup(Traj &t, const BatchPtrs &bp, const Dev
     t.base = S8(L.base); t.sc = S8(L.sc); t.win = S8(L.win); t.tmpl = S8(L.tmpl); t.ring = S8(L.ring);
     t.yawidx = SPtrU16{sm + 8u * (unsigned)L.yawidx};
     t.roles = SPtrU16{sm + 8u * (unsigned)L.roles};
-    lu_build_roles(t.roles, threadIdx.x & 31);
+    if (wig == 0) lu_build_roles(t.roles, threadIdx.x & 31);
     t.lambda = bp.lambda + pd->off_s; t.hx = bp.hx + pd->off_s;
     t.mu = bp.mu + 6 * pd->off_s; t.gx = bp.gx + 6 * pd->off_s;
     t.scale_cx = bp.scale_cx + 7 * pd->off_s;
@@ -1759,6 +1818,9 @@ __device__ UALM_NOINLINE void traj_setup(Traj &t, const BatchPtrs &bp, const Dev
         (void)ry;
     }
     t.ws = bp.ws_scaling ? bp.ws_scaling + pd->off_ws : nullptr;
+    t.G = G; t.wig = wig; t.barid = 1 + leader;
+    t.hring = SPtr{sm_own + 8u * (unsigned)L.ring};
+    t.wsw = t.ws ? t.ws + (size_t)wig * (12 * pd->N + 6 * pd->M) * 32 : nullptr;
     t.n_evals = 0;
     __shared__ long long s_prof_all[UALM_WPB][UALM_NPROF + 1];
     long long *s_prof = s_prof_all[threadIdx.x >> 5];
@@ -1773,15 +1835,36 @@ __device__ UALM_NOINLINE void traj_setup(Traj &t, const BatchPtrs &bp, const Dev
 // kernels (one warp = one CTA = one trajectory)
 // =============================================================================================
 
+// helper warps of a group: execute the parallel phases the leader posts, nothing else
+__device__ UALM_NOINLINE void helper_loop(Traj &t, const DevMap &map, const DevParams &p, int lane)
+{
+    while (true) {
+        group_bar(t);
+        const int cmd = (int)(R)t.sc[SC_CMD];
+        if (cmd == CMD_EXIT) break;
+        if (cmd == CMD_SAMPLES) penalty_samples(t, map, p, 32 * t.wig + lane, 32 * t.G);
+        else if (cmd == CMD_ACCUM) accumulate_tasks(t, 32 * (t.wig - 1) + lane, 32 * (t.G - 1));
+        else if (cmd == CMD_SCALE) scaling_rounds(t, map, p, 32 * t.wig + lane, 32 * t.G, lane);
+        group_bar(t);
+    }
+}
+
 // full solve: optimizeSE2Traj (alm_traj_opt.cpp:168-278)
 __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) solve_kernel(BatchPtrs bp, DevParams p, DevMap map, SmemLayout L)
 {
-    const int lane = threadIdx.x & 31, wslot = blockIdx.x * UALM_WPB + (threadIdx.x >> 5);
-    if (wslot >= bp.B) return;   // whole warp exits; warps never synchronise with each other
-    const unsigned sm = (unsigned)__cvta_generic_to_shared(ualm_smem) + 8u * (unsigned)((threadIdx.x >> 5) * L.total_doubles);
-    const int prob = bp.order[wslot];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wslot = blockIdx.x * UALM_WPB + w;
+    const int4 wd = bp.wdesc[wslot];
+    if (wd.x < 0) return;   // idle warp slot; warps of different groups never synchronise with each other
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(ualm_smem);
+    const int wig = wd.w & 0xff, hring = wd.w >> 8;
+    const unsigned sm = sbase + 8u * (unsigned)(wd.y * L.total_doubles);
+    // a helper's own shared memory is just a factor ring behind the leader slots; traj_setup adds L.ring to sm_own
+    const unsigned sm_own = wig == 0 ? sm
+                                     : sbase + 8u * (unsigned)(bp.n_leader_slots * L.total_doubles + hring * (2 * UALM_RINGB * 6 * UALM_FW)) - 8u * (unsigned)L.ring;
+    const int prob = wd.x;
     Traj t;
-    traj_setup(t, bp, p, L, sm, prob);
+    traj_setup(t, bp, p, L, sm, sm_own, prob, wd.z, wig, wd.y);
+    if (wig > 0) { helper_loop(t, map, p, lane); return; }
     const int N = t.N, M = t.M, n = t.n, S = t.S;
     // duals and scales (alm_traj_opt.cpp:193-203)
     for (int q = lane; q < S; q += 32) { t.lambda[q] = 0.0; t.hx[q] = 0.0; }
@@ -1832,6 +1915,7 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) solve_kernel(BatchPtr
         if (fmax(rh, rg) < p.epsilon_con) break;
         if ((R)(++iter) > p.max_iter) { ret_code = 2; break; }
     }
+    group_post(t, lane, CMD_EXIT);
     // outputs: coefficients / decision vector of the LAST evaluation's MINCO state (Q1), result record
     const int nx = 6 * N, ny = 6 * M;
     for (int q = lane; q < 2 * nx; q += 32) bp.c_xy[t.pd->off_cxy + q] = t.cxy[q];
@@ -1847,7 +1931,7 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) solve_kernel(BatchPtr
         bp.results[prob] = r;
         if (bp.prof) {
             t.prof[PF_TOTAL] += clock64();
-            for (int q = 0; q < UALM_NPROF; q++) bp.prof[(size_t)wslot * UALM_NPROF + q] = t.prof[q];
+            for (int q = 0; q < UALM_NPROF; q++) bp.prof[(size_t)prob * UALM_NPROF + q] = t.prof[q];
         }
     }
 }
@@ -1860,7 +1944,7 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) eval_kernel(BatchPtrs
     const unsigned sm = (unsigned)__cvta_generic_to_shared(ualm_smem) + 8u * (unsigned)((threadIdx.x >> 5) * L.total_doubles);
     const int prob = bp.order[wslot];
     Traj t;
-    traj_setup(t, bp, p, L, sm, prob);
+    traj_setup(t, bp, p, L, sm, sm, prob, 1, 0, threadIdx.x >> 5);
     for (int q = lane; q < t.n; q += 32) t.x[q] = bp.x0[t.pd->off_x + q];
     if (lane == 0) { t.sc[SC_SCALE_FX] = bp.scale_fx_io[prob]; t.sc[SC_RHO] = rho; }
     UALM_SYNC();
@@ -1880,7 +1964,7 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) scaling_kernel(BatchP
     const unsigned sm = (unsigned)__cvta_generic_to_shared(ualm_smem) + 8u * (unsigned)((threadIdx.x >> 5) * L.total_doubles);
     const int prob = bp.order[wslot];
     Traj t;
-    traj_setup(t, bp, p, L, sm, prob);
+    traj_setup(t, bp, p, L, sm, sm, prob, 1, 0, threadIdx.x >> 5);
     for (int q = lane; q < t.n; q += 32) t.x[q] = bp.x0[t.pd->off_x + q];
     if (lane == 0) { t.sc[SC_SCALE_FX] = 1.0; t.sc[SC_RHO] = p.rho; }
     UALM_SYNC();
@@ -1897,15 +1981,18 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) penalty_only_kernel(B
     const unsigned sm = (unsigned)__cvta_generic_to_shared(ualm_smem) + 8u * (unsigned)((threadIdx.x >> 5) * L.total_doubles);
     const int prob = bp.order[wslot];
     Traj t;
-    traj_setup(t, bp, p, L, sm, prob);
+    traj_setup(t, bp, p, L, sm, sm, prob, 1, 0, threadIdx.x >> 5);
     for (int q = lane; q < t.n; q += 32) t.x[q] = bp.x0[t.pd->off_x + q];
     if (lane == 0) { t.sc[SC_SCALE_FX] = 1.0; t.sc[SC_RHO] = p.rho; }
     UALM_SYNC();
     minco_generate(t, lane);
     sample_tables(t, lane);
     for (int r = 0; r < reps; r++) {
-        penalty_samples(t, map, p, lane);
-        penalty_accumulate(t, lane);
+        penalty_samples(t, map, p, lane, 32);
+        UALM_SYNC();
+        accumulate_tasks(t, lane, 32);
+        cost_chain(t, lane);
+        UALM_SYNC();
     }
     if (lane == 0) bp.f_out[prob] = t.sc[SC_CONSTR];
 }
