@@ -181,6 +181,7 @@ static BatchPtrs batch_ptrs(ualm_ctx *c)
     b.B = c->B;
     b.wdesc = c->d_wdesc.p;
     b.n_leader_slots = 4;
+    b.adopt = getenv("UALM_NOADOPT") ? 0 : 1;
     b.desc = c->d_desc.p; b.order = c->d_order.p; b.x0 = c->d_x0.p; b.x = c->d_x.p;
     b.lambda = c->d_lambda.p; b.mu = c->d_mu.p; b.scale_cx = c->d_scale_cx.p; b.hx = c->d_hx.p; b.gx = c->d_gx.p;
     b.lm_s = c->d_lm_s.p; b.lm_y = c->d_lm_y.p; b.lm_aux = c->d_lm_aux.p; b.fac = c->d_fac.p; b.scratch = c->d_scr.p; b.ws_scaling = c->d_ws.p;
@@ -292,13 +293,19 @@ extern "C" int ualm_upload(ualm_ctx_t *c, int B, const int32_t *N, const int32_t
                     for (int w = 0; w < 4; w++) c->wdesc.push_back(make_int4(c->order[q], 0, 4, w | ((w ? w - 1 : 0) << 8)));
                     q += 1;
                 } else if (cl.G == 2) {
+                    // CTA j of the class pairs its j-th largest with its j-th smallest problem: the small one ends early and its
+                    // two warps then help the large one (adoption, ualm_kernels.cuh)
+                    const int j = (q - cl.r0) / 2, cnt = cl.r1 - cl.r0;
+                    const int pa = cl.r0 + j, pb = cl.r1 - 1 - j;
+                    const int pr[2] = {c->order[pa], pb > pa ? c->order[pb] : -1};
                     for (int h = 0; h < 2; h++) {
-                        if (q < cl.r1) {
-                            c->wdesc.push_back(make_int4(c->order[q], h, 2, 0));
-                            c->wdesc.push_back(make_int4(c->order[q], h, 2, 1 | (h << 8)));
-                            q += 1;
+                        if (pr[h] >= 0) {
+                            c->wdesc.push_back(make_int4(pr[h], h, 2, 0));
+                            c->wdesc.push_back(make_int4(pr[h], h, 2, 1 | (h << 8)));
                         } else { c->wdesc.push_back(make_int4(-1, 0, 1, 0)); c->wdesc.push_back(make_int4(-1, 0, 1, 0)); }
                     }
+                    (void)cnt;
+                    q += 2;
                 } else {
                     for (int w = 0; w < 4; w++) {
                         if (q < cl.r1) { c->wdesc.push_back(make_int4(c->order[q], w, 1, 0)); q += 1; }

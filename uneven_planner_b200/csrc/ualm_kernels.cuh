@@ -88,6 +88,7 @@ struct BatchPtrs {
     int B;
     const int4 *wdesc;       // solve_kernel: per warp slot {problem (-1 = idle), leader slot in CTA, group size, warp in group | helper ring << 8}
     int n_leader_slots;      // solve_kernel: full per-trajectory slots per CTA (4 / G); helper rings follow them
+    int adopt;               // solve_kernel: warps of a finished trajectory join the other trajectory of a two-slot CTA
     const ProbDesc *desc;
     const int *order;        // launch order (largest first); blockIdx.x -> problem index
     const R *x0;             // packed initial decision vectors
@@ -225,6 +226,7 @@ struct Traj {
     // warp group of this trajectory: G warps (1, 2 or 4) of one CTA; warp 0 of the group (the leader) runs the whole algorithm,
     // the others (helpers) only execute the parallel phases the leader posts (samples, gradient accumulation, initScaling)
     int G, wig, barid;
+    int *adopt;        // shared-memory state word of this leader slot (two-slot CTAs only; see "adoption" below), else null
     SPtr hring;        // this warp's own factor ring (initScaling sweeps run per warp)
     R *wsw;            // this warp's own initScaling workspace
     int n_evals;
@@ -245,7 +247,14 @@ __device__ __forceinline__ void prof_mark(const Traj &t, int tid, int phase)
 }
 
 // ---- leader / helper protocol inside a warp group (named barrier 1 + leader warp index, 32*G participants) ----
-enum { CMD_SAMPLES = 1, CMD_ACCUM = 2, CMD_SCALE = 3, CMD_EXIT = 4 };
+enum { CMD_SAMPLES = 1, CMD_ACCUM = 2, CMD_SCALE = 3, CMD_EXIT = 4, CMD_REGROUP = 5, CMD_JOIN = 6 };
+// Adoption (CTAs that hold two trajectories with two warps each): when one trajectory finishes, its two warps join the other
+// trajectory's group as helpers 2 and 3, so the slower of the pair runs its parallel phases on the whole CTA.  Per leader slot
+// one state word: RUNNING -> (mate asks) JOINREQ -> (leader switches its group to the 128-thread barrier) JOINED; -> DONE.
+// The partition of the parallel phases over warps never changes a result bit (every output entry has one owner and a fixed
+// summation order), so the solve stays batch-invariant.
+enum { AD_RUNNING = 0, AD_JOINREQ = 1, AD_JOINED = 2, AD_DONE = 3 };
+#define UALM_BAR_BIG 5
 __device__ __forceinline__ void group_bar(const Traj &t)
 {
     if (t.G > 1) asm volatile("bar.sync %0, %1;" ::"r"(t.barid), "r"(32 * t.G) : "memory");
@@ -258,6 +267,24 @@ __device__ __forceinline__ void group_post(const Traj &t, int lane, int cmd)
         if (lane == 0) t.sc[SC_CMD] = (R)cmd;
         __syncwarp();
         group_bar(t);
+    }
+}
+// leader of a two-warp group: move the group (its helper and the two waiting joiners) onto the CTA-wide barrier
+__device__ __forceinline__ void regroup_now(Traj &t, int lane)
+{
+    group_post(t, lane, CMD_REGROUP);
+    group_bar(t);                       // the helper has read the command word; it may be overwritten now
+    t.G = 4; t.barid = UALM_BAR_BIG;
+}
+__device__ __forceinline__ void maybe_regroup(Traj &t, int lane)
+{
+    if (t.adopt == nullptr || t.G != 2) return;
+    int st = 0;
+    if (lane == 0) st = *(volatile int *)t.adopt;
+    st = __shfl_sync(0xffffffffu, st, 0);
+    if (st == AD_JOINREQ) {
+        regroup_now(t, lane);
+        if (lane == 0) atomicExch(t.adopt, AD_JOINED);
     }
 }
 
@@ -280,7 +307,14 @@ __device__ __forceinline__ void normSO2(R &yaw) // uneven_map.cpp:64-71
 // The kernel is latency bound and eight warps per SM sit in different phases, so instruction-cache footprint matters
 // (L0 ~6 KB, L1.5 32 KB): every large device function is __noinline__ (one copy, called), not inlined per call site.
 #define UALM_NOINLINE __noinline__
-__device__ UALM_NOINLINE void dev_sincos(R x, R *s, R *c) { ualm_sincos(x, s, c); }
+// returned by value: taking the address of a caller's variable for an out-of-line call would pin that variable (or the whole
+// struct it is a member of) in local memory
+__device__ UALM_NOINLINE double2 dev_sincos(R x)
+{
+    R s, c;
+    ualm_sincos(x, &s, &c);
+    return make_double2(s, c);
+}
 __device__ UALM_NOINLINE R dev_atan2(R y, R x) { return ualm_atan2(y, x); }
 
 // a / b given rb = RN(1/b): q0 = a*rb followed by two residual corrections with FMA returns the correctly rounded quotient
@@ -302,6 +336,7 @@ __device__ __forceinline__ R div_by_recip(R a, R b, R rb)
 // cp.async (LDGSTS) helpers: 16-byte global -> shared copies that bypass L1 (factors are produced by this warp and
 // consumed once per sweep: L2 is the right home)
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async16(unsigned smem_addr, const void *gmem)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(gmem) : "memory");
@@ -772,9 +807,23 @@ __device__ __forceinline__ void map_get_all_with_grad_impl(const DevMap &m, cons
         R diff[3];
         diff[0] = (pos[0] - idx_pos[0]) * m.xy_inv;
         diff[1] = (pos[1] - idx_pos[1]) * m.xy_inv;
+        // start the eight corner cells now: the angle difference below costs two out-of-line calls the loads cannot cross
+#pragma unroll
+        for (int x = 0; x < 2; x++)
+#pragma unroll
+            for (int y = 0; y < 2; y++)
+#pragma unroll
+                for (int w = 0; w < 2; w++) {
+                    int c0 = idx[0] + x, c1 = idx[1] + y, c2 = idx[2] + w;
+                    c0 = max(min(c0, m.vn[0] - 1), 0);
+                    c1 = max(min(c1, m.vn[1] - 1), 0);
+                    while (c2 > m.vn[2] - 1) c2 -= m.vn[2];
+                    while (c2 < 0) c2 += m.vn[2];
+                    prefetch_l1(&m.cells[(size_t)c0 * m.vn[1] * m.vn[2] + (size_t)c1 * m.vn[2] + c2]);
+                }
         {
             R sd, cd;
-            dev_sincos(pos[2] - idx_pos[2], &sd, &cd);
+            { const double2 scv = dev_sincos(pos[2] - idx_pos[2]); sd = scv.x; cd = scv.y; }
             diff[2] = dev_atan2(sd, cd) * m.yaw_inv;
         }
         R v[2][2][2][3];
@@ -817,7 +866,7 @@ __device__ __forceinline__ void map_get_all_with_grad_impl(const DevMap &m, cons
     const R c = sqrt(1.0 - rs[1] * rs[1] - rs[2] * rs[2]);
     const R inv_c = 1.0 / c;
     R syaw, cyaw;
-    dev_sincos(pos[2], &syaw, &cyaw);
+    { const double2 scv = dev_sincos(pos[2]); syaw = scv.x; cyaw = scv.y; }
     const R xyaw[2] = {cyaw, syaw};
     const R yyaw[2] = {-syaw, cyaw};
     const R tt = xyaw[0] * rs[1] + xyaw[1] * rs[2];
@@ -905,7 +954,7 @@ __device__ __forceinline__ void sample_kin_impl(const Traj &t, const DevMap &map
     S.yaw = yaw; S.dyaw = dyaw; S.d2yaw = d2yaw;
     R se2[3] = {S.pos[0], S.pos[1], yaw};
     normSO2(se2[2]);
-    dev_sincos(yaw, &S.syaw, &S.cyaw);
+    { const double2 scv = dev_sincos(yaw); S.syaw = scv.x; S.cyaw = scv.y; }
     S.v_norm = sqrt(S.vel[0] * S.vel[0] + S.vel[1] * S.vel[1]);
     S.lon_acc = S.acc[0] * S.cyaw + S.acc[1] * S.syaw;
     S.lat_acc = S.acc[0] * (-S.syaw) + S.acc[1] * S.cyaw;
@@ -958,6 +1007,12 @@ __device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const 
     R *scr = t.scr;
     for (int s = gtid; s < S; s += GT) {
         const int i = s / (K + 1), j = s - i * (K + 1);
+        // the duals and scales of this sample are needed only after the kinematics: start their cache lines now, and read them
+        // in one batch before the first store below (a load placed after a store to a may-alias pointer cannot be hoisted by
+        // the compiler, which would expose one memory latency per constraint)
+        prefetch_l1(t.lambda + s);
+        prefetch_l1(t.mu + 6 * (size_t)s); prefetch_l1(t.mu + 6 * (size_t)s + 5);
+        prefetch_l1(t.scale_cx + 7 * (size_t)s); prefetch_l1(t.scale_cx + 7 * (size_t)s + 6);
         SampleK q;
         sample_kin_impl<true>(t, map, p.gravity, i, t.s1tab[j], t.base[i], q);
         t.yawidx[s] = (unsigned short)q.yaw_idx;
@@ -965,8 +1020,12 @@ __device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const 
         R grad_yaw = 0, grad_dyaw = 0, grad_vx2 = 0, grad_wz = 0, grad_ax = 0, grad_ay = 0, aug_grad = 0;
         const R inv_cos_vphix = q.tv[0], inv_cos_vphiy = q.tv[2], cos_xi = q.tv[4], inv_cos_xi = q.tv[5], sigma = q.tv[6];
         const R vx = q.vx, wz = q.wz, ax = q.ax, ay = q.ay, curv_snorm = q.curv_snorm;
-        const R *sc7 = t.scale_cx + 7 * (size_t)s;
-        const R *mu6 = t.mu + 6 * (size_t)s;
+        R sc7[7], mu6[6];
+#pragma unroll
+        for (int k = 0; k < 7; k++) sc7[k] = t.scale_cx[7 * (size_t)s + k];
+#pragma unroll
+        for (int k = 0; k < 6; k++) mu6[k] = t.mu[6 * (size_t)s + k];
+        const R lambda_s = t.lambda[s];
         R *gx6 = t.gx + 6 * (size_t)s;
 
         R omega;
@@ -979,7 +1038,7 @@ __device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const 
         for (int k = 0; k < 3; k++) grad_se2[k] += omega * q.tg[6][k] * sigma * 2.0;
 
         { // non-holonomic
-            const R nonh_lambda = t.lambda[s];
+            const R nonh_lambda = lambda_s;
             const R nhy0 = q.syaw, nhy1 = -q.cyaw;
             const R h = (q.vel[0] * nhy0 + q.vel[1] * nhy1) * sc7[0];
             t.hx[s] = h;
@@ -1252,6 +1311,7 @@ __device__ UALM_NOINLINE void evaluate(Traj &t, const DevMap &map, const DevPara
     prof_mark(t, lane, PF_JERK);
     sample_tables(t, lane);
     prof_mark(t, lane, PF_TABLES);
+    maybe_regroup(t, lane);
     group_post(t, lane, CMD_SAMPLES);
     penalty_samples(t, map, p, lane, 32 * t.G);
     group_bar(t);
@@ -1818,7 +1878,7 @@ __device__ UALM_NOINLINE void traj_setup(Traj &t, const BatchPtrs &bp, const Dev
         (void)ry;
     }
     t.ws = bp.ws_scaling ? bp.ws_scaling + pd->off_ws : nullptr;
-    t.G = G; t.wig = wig; t.barid = 1 + leader;
+    t.G = G; t.wig = wig; t.barid = 1 + leader; t.adopt = nullptr;
     t.hring = SPtr{sm_own + 8u * (unsigned)L.ring};
     t.wsw = t.ws ? t.ws + (size_t)wig * (12 * pd->N + 6 * pd->M) * 32 : nullptr;
     t.n_evals = 0;
@@ -1836,12 +1896,14 @@ __device__ UALM_NOINLINE void traj_setup(Traj &t, const BatchPtrs &bp, const Dev
 // =============================================================================================
 
 // helper warps of a group: execute the parallel phases the leader posts, nothing else
-__device__ UALM_NOINLINE void helper_loop(Traj &t, const DevMap &map, const DevParams &p, int lane)
+__device__ UALM_NOINLINE int helper_loop(Traj &t, const DevMap &map, const DevParams &p, int lane)
 {
     while (true) {
         group_bar(t);
         const int cmd = (int)(R)t.sc[SC_CMD];
-        if (cmd == CMD_EXIT) break;
+        if (cmd == CMD_EXIT) return 0;
+        if (cmd == CMD_JOIN) return 1;
+        if (cmd == CMD_REGROUP) { group_bar(t); t.G = 4; t.barid = UALM_BAR_BIG; continue; }
         if (cmd == CMD_SAMPLES) penalty_samples(t, map, p, 32 * t.wig + lane, 32 * t.G);
         else if (cmd == CMD_ACCUM) accumulate_tasks(t, 32 * (t.wig - 1) + lane, 32 * (t.G - 1));
         else if (cmd == CMD_SCALE) scaling_rounds(t, map, p, 32 * t.wig + lane, 32 * t.G, lane);
@@ -1849,12 +1911,29 @@ __device__ UALM_NOINLINE void helper_loop(Traj &t, const DevMap &map, const DevP
     }
 }
 
+// warps of a finished two-warp group: serve the other trajectory of the CTA as helpers 2 and 3 until it ends
+__device__ UALM_NOINLINE void join_mate(Traj &t, const BatchPtrs &bp, const DevParams &p, const DevMap &map, const SmemLayout &L, unsigned sbase, int mate,
+                                        int wig, int lane)
+{
+    const int4 wm = bp.wdesc[blockIdx.x * UALM_WPB + 2 * mate];
+    const unsigned smm = sbase + 8u * (unsigned)(mate * L.total_doubles);
+    traj_setup(t, bp, p, L, smm, smm, wm.x, 4, wig, mate);
+    t.barid = UALM_BAR_BIG;
+    helper_loop(t, map, p, lane);
+}
+
 // full solve: optimizeSE2Traj (alm_traj_opt.cpp:168-278)
 __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) solve_kernel(BatchPtrs bp, DevParams p, DevMap map, SmemLayout L)
 {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wslot = blockIdx.x * UALM_WPB + w;
     const int4 wd = bp.wdesc[wslot];
-    if (wd.x < 0) return;   // idle warp slot; warps of different groups never synchronise with each other
+    __shared__ int s_adopt[2];
+    const bool adoptable = (bp.n_leader_slots == 2 && bp.adopt);
+    if (adoptable) {
+        if (threadIdx.x < 2) s_adopt[threadIdx.x] = bp.wdesc[blockIdx.x * UALM_WPB + 2 * threadIdx.x].x < 0 ? AD_DONE : AD_RUNNING;
+        __syncthreads();
+    }
+    if (wd.x < 0) return;   // idle warp slot
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(ualm_smem);
     const int wig = wd.w & 0xff, hring = wd.w >> 8;
     const unsigned sm = sbase + 8u * (unsigned)(wd.y * L.total_doubles);
@@ -1864,7 +1943,10 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) solve_kernel(BatchPtr
     const int prob = wd.x;
     Traj t;
     traj_setup(t, bp, p, L, sm, sm_own, prob, wd.z, wig, wd.y);
-    if (wig > 0) { helper_loop(t, map, p, lane); return; }
+    if (wig > 0) {
+        if (helper_loop(t, map, p, lane)) join_mate(t, bp, p, map, L, sbase, 1 - wd.y, 3, lane);
+        return;
+    }
     const int N = t.N, M = t.M, n = t.n, S = t.S;
     // duals and scales (alm_traj_opt.cpp:193-203)
     for (int q = lane; q < S; q += 32) { t.lambda[q] = 0.0; t.hx[q] = 0.0; }
@@ -1875,6 +1957,7 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) solve_kernel(BatchPtr
     UALM_SYNC();
     if (p.use_scaling) init_scaling(t, map, p, lane);
     prof_mark(t, lane, PF_SCALING);
+    if (adoptable && wd.z == 2) t.adopt = &s_adopt[wd.y];   // joiners only take part in the evaluation phases
 
     int ret_code = 0, iter = 0, last = 0, iters_total = 0, max_bound = 0, sum_bound = 0;
     R inner_cost = 0.0, rh = 0.0, rg = 0.0;
@@ -1915,7 +1998,18 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) solve_kernel(BatchPtr
         if (fmax(rh, rg) < p.epsilon_con) break;
         if ((R)(++iter) > p.max_iter) { ret_code = 2; break; }
     }
-    group_post(t, lane, CMD_EXIT);
+    int join = 0;
+    if (t.adopt) {
+        int old = 0;
+        if (lane == 0) old = atomicExch(t.adopt, AD_DONE);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old == AD_JOINREQ) regroup_now(t, lane);         // the mate's warps already wait on the CTA-wide barrier: release them below
+        if (t.G == 2) {                                      // nobody joined this group: offer its warps to the mate
+            if (lane == 0) join = atomicCAS(&s_adopt[1 - wd.y], AD_RUNNING, AD_JOINREQ) == AD_RUNNING;
+            join = __shfl_sync(0xffffffffu, join, 0);
+        }
+    }
+    group_post(t, lane, join ? CMD_JOIN : CMD_EXIT);
     // outputs: coefficients / decision vector of the LAST evaluation's MINCO state (Q1), result record
     const int nx = 6 * N, ny = 6 * M;
     for (int q = lane; q < 2 * nx; q += 32) bp.c_xy[t.pd->off_cxy + q] = t.cxy[q];
@@ -1933,6 +2027,10 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) solve_kernel(BatchPtr
             t.prof[PF_TOTAL] += clock64();
             for (int q = 0; q < UALM_NPROF; q++) bp.prof[(size_t)prob * UALM_NPROF + q] = t.prof[q];
         }
+    }
+    if (join) {
+        UALM_SYNC();
+        join_mate(t, bp, p, map, L, sbase, 1 - wd.y, 2, lane);
     }
 }
 
