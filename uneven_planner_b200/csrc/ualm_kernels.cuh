@@ -332,6 +332,18 @@ __device__ __forceinline__ R div_by_recip(R a, R b, R rb)
     return q;
 }
 
+// IEEE a / b for callers whose numerator is often exactly zero.  The inline fast path of the fp64 division hands a zero (or
+// denormal) quotient to an out-of-line slow path, and it does so for the whole warp when a single lane needs it; here a zero
+// numerator is replaced by 1 for the division and the signed zero (NaN for b = 0 or NaN) is put back afterwards.
+__device__ __forceinline__ R div_nz(R a, R b)
+{
+    const bool z = (a == 0.0);
+    const R q = (z ? 1.0 : a) / b;
+    const long long sz = (__double_as_longlong(a) ^ __double_as_longlong(b)) & (long long)0x8000000000000000ull;
+    const R zq = (b != b || b == 0.0) ? __longlong_as_double(0x7ff8000000000000ll) : __longlong_as_double(sz);
+    return z ? zq : q;
+}
+
 // ---------------------------------------------------------------------------------------------
 // cp.async (LDGSTS) helpers: 16-byte global -> shared copies that bypass L1 (factors are produced by this warp and
 // consumed once per sweep: L2 is the right home)
@@ -513,46 +525,56 @@ __device__ UALM_NOINLINE void lu_dual(Traj &t, int lane)
     const SPtrU16 roles = t.roles;
     R *Fk = F;                     // row k of F
     int kmod = 0;
+    // The pivot step is written without data-dependent branches (a taken branch costs a lone warp ~20 cycles, the step had
+    // eight): every lane loads its operands from always-valid window addresses up front, divides a sanitised pair, and only the
+    // stores are predicated.  The role word of step k+1 is fetched during step k.
+    auto role_of = [&](int kk, int km) -> unsigned {
+        const int ty = (kk >= n6 - 6) ? 6 + (kk - (n6 - 6)) : km;
+        const int idx = (kk < n6) ? ((ty << 4) + hl) : hl;
+        const unsigned r = (unsigned)(int)roles[idx];
+        return (kk < n6) ? r : 0u;
+    };
+    unsigned role_next = role_of(0, 0);
+    const bool ulane = (hl >= 5 && hl < 12);
+    const int uq = ulane ? hl - 5 : 0;
 #pragma unroll 1
     for (int k = 0; k < nmax6; k++, Fk += UALM_FW) {
         const bool on = k < n6;
         if (kmod == 0 && on) lu_fill6_aligned(W, TM, k + 8, n6, hl);
-        const int ty = (k >= n6 - 6) ? 6 + (k - (n6 - 6)) : kmod;
-        const unsigned role = on ? roles[(ty << 4) + hl] : 0u;
+        const unsigned role = role_next;
+        const int kmod1 = (kmod == 5) ? 0 : kmod + 1;
+        role_next = role_of(k + 1, kmod1);
         const int mo = role & 7, uo = (role >> 3) & 7, uc = (role >> 6) & 7, ul = (role >> 9) & 3;
         const SPtr Wk = W + (k & 15) * UALM_FW;
-        R m = 0.0;
-        if (mo) {
-            const bool isr = (mo == 7);
-            const int o = isr ? 0 : mo;
-            const SPtr pa = W + (((k + o) & 15) * UALM_FW + 6 - o);
-            const R piv = Wk[6];
-            const R a = isr ? 1.0 : *pa;
-            m = a;
-            if (a != 0.0) m = a / piv;
-            if (!isr) {
-                *pa = m;
-                Fk[o * UALM_FW + 6 - o] = m;       // F[k+o][6-o]
-            } else {
-                // a divisor with an all-ones significand is the one case the reciprocal-based division cannot round: flag it
-                if ((__double_as_longlong(piv) & 0xFFFFFFFFFFFFFll) == 0xFFFFFFFFFFFFFll) m = __longlong_as_double(0x7ff8000000000000ll);
-                Fk[13] = m;
-            }
-        } else if (on && hl >= 5 && hl < 12) {
-            const int q = hl - 5;
-            const R u = Wk[6 + q];
-            Fk[6 + q] = u;
+        const bool act = (mo != 0), isr = (mo == 7);
+        const int o = isr ? 0 : mo;
+        const SPtr pa = W + (((k + o) & 15) * UALM_FW + 6 - o);                 // o = 0: the pivot itself
+        const SPtr pw = W + (((k + uo) & 15) * UALM_FW + 6 + uc - uo);          // uo = uc = 0: the pivot itself
+        const R piv = Wk[6];
+        const R av = *pa;
+        const R urow = Wk[6 + uq];
+        const R u = Wk[6 + uc];
+        const R w = *pw;
+        const R a = isr ? 1.0 : av;
+        const bool nz = act && (a != 0.0);
+        // exact zeros are skipped by the reference (banded_system.hpp:74) and would push the division onto its slow path
+        R m = (nz ? a : 1.0) / (act ? piv : 1.0);
+        m = nz ? m : (act ? a : 0.0);
+        if (act && !isr) {
+            *pa = m;
+            Fk[o * UALM_FW + 6 - o] = m;       // F[k+o][6-o]
         }
+        if (isr) {
+            // a divisor with an all-ones significand is the one case the reciprocal-based division cannot round: flag it
+            R mf = m;
+            if ((__double_as_longlong(piv) & 0xFFFFFFFFFFFFFll) == 0xFFFFFFFFFFFFFll) mf = __longlong_as_double(0x7ff8000000000000ll);
+            Fk[13] = mf;
+        }
+        if (on && !act && ulane) Fk[6 + uq] = urow;
         const R mr = __shfl_sync(0xffffffffu, m, (lane & 16) + ul);
-        if (uc && k + uc < n6) {
-            const R u = Wk[6 + uc];
-            if (u != 0.0 && mr != 0.0) {
-                const SPtr pw = W + (((k + uo) & 15) * UALM_FW + 6 + uc - uo);
-                *pw = *pw - mr * u;
-            }
-        }
+        if (uc != 0 && k + uc < n6 && u != 0.0 && mr != 0.0) *pw = w - mr * u;
         UALM_SYNC();
-        if (++kmod == 6) kmod = 0;
+        kmod = kmod1;
     }
 }
 
@@ -861,7 +883,7 @@ __device__ __forceinline__ void map_get_all_with_grad_impl(const DevMap &m, cons
         }
         const R cc = sqrt(1.0 - rs[1] * rs[1] - rs[2] * rs[2]);
 #pragma unroll
-        for (int k = 0; k < 3; k++) rg[3][k] = -(rg[1][k] * rs[1] + rg[2][k] * rs[2]) / cc;
+        for (int k = 0; k < 3; k++) rg[3][k] = div_nz(-(rg[1][k] * rs[1] + rg[2][k] * rs[2]), cc);
     }
     const R c = sqrt(1.0 - rs[1] * rs[1] - rs[2] * rs[2]);
     const R inv_c = 1.0 / c;
@@ -964,7 +986,7 @@ __device__ __forceinline__ void sample_kin_impl(const Traj &t, const DevMap &map
     S.wz = dyaw * S.tv[5];
     S.ax = S.lon_acc * S.tv[0] + gravity * S.tv[1];
     S.ay = S.lat_acc * S.tv[2] + gravity * S.tv[3];
-    S.curv_snorm = S.wz * S.wz / (S.vx * S.vx + UALM_DELTA_SIGL);
+    S.curv_snorm = div_nz(S.wz * S.wz, S.vx * S.vx + UALM_DELTA_SIGL);
 }
 
 // out-of-line copy (initScaling) and inlined copy (the per-evaluation penalty loop: keeps the sample state in registers)
@@ -1206,7 +1228,7 @@ __device__ UALM_NOINLINE void accumulate_tasks(Traj &t, int gtid, int GT)
             fetch(sn, vn);
             const R d2yn = scr[SF_D2YAW * S + sn];
             const R alpha = 1.0 / (R)K * (R)j;
-            acc += v[0] / (R)K;
+            acc += div_nz(v[0], (R)K);
             acc += ((v[1] * v[7] + v[2] * v[8]) + (v[3] * v[9] + v[4] * v[10]) + (v[5] * v[11] + v[6] * v[12])) * alpha;
             acc += (v[13] * v[15] + v[14] * d2y) * (alpha + (R)i);
 #pragma unroll
@@ -1800,7 +1822,7 @@ __device__ UALM_NOINLINE void init_scaling(Traj &t, const DevMap &map, const Dev
         for (int j = 0; j <= K; j++) {
             const int s = i * (K + 1) + j;
             const R alpha = 1.0 / (R)K * (R)j;
-            acc += scr[SF_USER * S + s] / (R)K;
+            acc += div_nz(scr[SF_USER * S + s], (R)K);
             acc += (scr[(SF_GP + 0) * S + s] * scr[(SF_VEL + 0) * S + s] + scr[(SF_GP + 1) * S + s] * scr[(SF_VEL + 1) * S + s]) * alpha;
             acc += (scr[SF_GYAW * S + s] * scr[SF_DYAW * S + s]) * (alpha + (R)i);
         }
@@ -1923,7 +1945,8 @@ __device__ UALM_NOINLINE void join_mate(Traj &t, const BatchPtrs &bp, const DevP
 }
 
 // full solve: optimizeSE2Traj (alm_traj_opt.cpp:168-278)
-__global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) solve_kernel(BatchPtrs bp, DevParams p, DevMap map, SmemLayout L)
+__global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) solve_kernel(const __grid_constant__ BatchPtrs bp, const __grid_constant__ DevParams p, const __grid_constant__ DevMap map,
+        const __grid_constant__ SmemLayout L)
 {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wslot = blockIdx.x * UALM_WPB + w;
     const int4 wd = bp.wdesc[wslot];
@@ -1983,7 +2006,7 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) solve_kernel(BatchPtr
             const R gq = t.gx[q];
             const R mq = fmax(t.mu[q] + rho * gq, 0.0);
             t.mu[q] = mq;
-            mg = fmax(mg, fabs(fmax(gq, -mq / rho_new)));
+            mg = fmax(mg, fabs(fmax(gq, div_nz(-mq, rho_new))));
         }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
@@ -2035,7 +2058,8 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) solve_kernel(BatchPtr
 }
 
 // one innerCallback evaluation per problem at caller-provided x / duals (kernel-level parity)
-__global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) eval_kernel(BatchPtrs bp, DevParams p, DevMap map, SmemLayout L, R rho)
+__global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) eval_kernel(const __grid_constant__ BatchPtrs bp, const __grid_constant__ DevParams p, const __grid_constant__ DevMap map,
+        const __grid_constant__ SmemLayout L, R rho)
 {
     const int lane = threadIdx.x & 31, wslot = blockIdx.x * UALM_WPB + (threadIdx.x >> 5);
     if (wslot >= bp.B) return;   // whole warp exits; warps never synchronise with each other
@@ -2055,7 +2079,8 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) eval_kernel(BatchPtrs
 }
 
 // initScaling per problem at x0
-__global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) scaling_kernel(BatchPtrs bp, DevParams p, DevMap map, SmemLayout L)
+__global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) scaling_kernel(const __grid_constant__ BatchPtrs bp, const __grid_constant__ DevParams p, const __grid_constant__ DevMap map,
+        const __grid_constant__ SmemLayout L)
 {
     const int lane = threadIdx.x & 31, wslot = blockIdx.x * UALM_WPB + (threadIdx.x >> 5);
     if (wslot >= bp.B) return;   // whole warp exits; warps never synchronise with each other
@@ -2072,7 +2097,8 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) scaling_kernel(BatchP
 
 // the penalty-sampling phase alone (calConstrainCostGrad, alm_traj_opt.cpp:663-991) for roofline timing:
 // MINCO state is generated once, then `reps` sampling + accumulation passes are run.
-__global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) penalty_only_kernel(BatchPtrs bp, DevParams p, DevMap map, SmemLayout L, int reps)
+__global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) penalty_only_kernel(const __grid_constant__ BatchPtrs bp, const __grid_constant__ DevParams p, const __grid_constant__ DevMap map,
+        const __grid_constant__ SmemLayout L, int reps)
 {
     const int lane = threadIdx.x & 31, wslot = blockIdx.x * UALM_WPB + (threadIdx.x >> 5);
     if (wslot >= bp.B) return;   // whole warp exits; warps never synchronise with each other
