@@ -331,6 +331,19 @@ __device__ __forceinline__ R div_by_recip(R a, R b, R rb)
     if (!(aq < 1.0e290) || (aq < 1.0e-290 && a != 0.0)) q = a / b;
     return q;
 }
+// the same quotient without the fallback: `bad` collects the cases that need the IEEE division, so that a chain of quotients
+// (a sweep block) pays one branch at its end instead of one per row
+__device__ __forceinline__ R div_by_recip_flag(R a, R b, R rb, bool &bad)
+{
+    R q = a * rb;
+    R e = fma(-q, b, a);
+    q = fma(e, rb, q);
+    e = fma(-q, b, a);
+    q = fma(e, rb, q);
+    const R aq = fabs(q);
+    bad = bad || !(aq < 1.0e290) || (aq < 1.0e-290 && a != 0.0);
+    return q;
+}
 
 // IEEE a / b for callers whose numerator is often exactly zero.  The inline fast path of the fp64 division hands a zero (or
 // denormal) quotient to an out-of-line slow path, and it does so for the whole warp when a single lane needs it; here a zero
@@ -605,21 +618,14 @@ __host__ __device__ constexpr int sweep_mask(int kind, int t)
                   >> (6 * t)) & 0x3f);
 }
 
-template <int KIND, int NCOL, bool FULL, class BP>
-__device__ __forceinline__ void sweep_block(SPtr blk, SPtr nb, bool hasnb, BP b0, BP b1, int bst, int row0, R (&prev0)[6], R (&prev1)[6])
+template <int KIND, int NCOL, bool FULL, bool EXACT, class BP>
+__device__ __forceinline__ bool sweep_rows(SPtr blk, SPtr nb, bool hasnb, BP b0, BP b1, int bst, int row0, const R (&rhs0)[6], const R (&rhs1)[6],
+                                           const R (&prev0)[6], const R (&prev1)[6], R (&cur0)[6], R (&cur1)[6])
 {
     constexpr bool ASC = (KIND == 0 || KIND == 2);
     constexpr bool DIV = (KIND == 1 || KIND == 2);
     constexpr bool TR = (KIND == 2 || KIND == 3);   // transposed access: the factor entry lives in the neighbour's row
-    R cur0[6], cur1[6];
-    // all right-hand-side entries of the block first: they do not depend on the chain, and issuing them together pays the
-    // memory latency once per block instead of once per row (the stores below would otherwise fence them)
-    R rhs0[6], rhs1[6];
-#pragma unroll
-    for (int q = 0; q < 6; q++) {
-        rhs0[q] = at(b0, (row0 + q) * bst);
-        rhs1[q] = (NCOL == 2) ? (R)at(b1, (row0 + q) * bst) : 0.0;
-    }
+    bool bad = false;
 #pragma unroll
     for (int tt = 0; tt < 6; tt++) {
         const int t = ASC ? tt : 5 - tt;            // row type processed now
@@ -649,14 +655,40 @@ __device__ __forceinline__ void sweep_block(SPtr blk, SPtr nb, bool hasnb, BP b0
             }
         }
         if (DIV) {
-            const R dg = f[6], rdg = f[13];
-            v0 = div_by_recip(v0, dg, rdg);
-            if (NCOL == 2) v1 = div_by_recip(v1, dg, rdg);
+            const R dg = f[6];
+            if (EXACT) {
+                v0 = v0 / dg;
+                if (NCOL == 2) v1 = v1 / dg;
+            } else {
+                const R rdg = f[13];
+                v0 = div_by_recip_flag(v0, dg, rdg, bad);
+                if (NCOL == 2) v1 = div_by_recip_flag(v1, dg, rdg, bad);
+            }
         }
         at(b0, (row0 + t) * bst) = v0;
         cur0[t] = v0;
         if (NCOL == 2) { at(b1, (row0 + t) * bst) = v1; cur1[t] = v1; }
     }
+    return bad;
+}
+
+template <int KIND, int NCOL, bool FULL, class BP>
+__device__ __forceinline__ void sweep_block(SPtr blk, SPtr nb, bool hasnb, BP b0, BP b1, int bst, int row0, R (&prev0)[6], R (&prev1)[6])
+{
+    constexpr bool DIV = (KIND == 1 || KIND == 2);
+    R cur0[6], cur1[6];
+    // all right-hand-side entries of the block first: they do not depend on the chain, and issuing them together pays the
+    // memory latency once per block instead of once per row (the stores below would otherwise fence them)
+    R rhs0[6], rhs1[6];
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        rhs0[q] = at(b0, (row0 + q) * bst);
+        rhs1[q] = (NCOL == 2) ? (R)at(b1, (row0 + q) * bst) : 0.0;
+    }
+    // the divisions use the stored reciprocals; a quotient the reciprocal route cannot round (flag) makes the lane redo the
+    // block with IEEE divisions -- one branch per block instead of one per row on the dependent chain
+    const bool bad = sweep_rows<KIND, NCOL, FULL, false, BP>(blk, nb, hasnb, b0, b1, bst, row0, rhs0, rhs1, prev0, prev1, cur0, cur1);
+    if (DIV && bad) sweep_rows<KIND, NCOL, FULL, true, BP>(blk, nb, hasnb, b0, b1, bst, row0, rhs0, rhs1, prev0, prev1, cur0, cur1);
 #pragma unroll
     for (int q = 0; q < 6; q++) { prev0[q] = cur0[q]; if (NCOL == 2) prev1[q] = cur1[q]; }
 }
