@@ -117,7 +117,7 @@ enum {
 // shared-memory layout (doubles), sized on the host from the batch maxima
 // ---------------------------------------------------------------------------------------------
 struct SmemLayout {
-    int cxy, cyaw, gCxy, gCyaw, gTxy, gTyaw, x, g, xp, gp, d, pf, s1tab, base, sc, win, tmpl, ring, roles /* shorts */, yawidx /* shorts */, total_doubles;
+    int cxy, cyaw, gCxy, gCyaw, gTxy, gTyaw, x, g, xp, gp, d, pf, s1tab, base, sc, win, tmpl, ring, lutab /* 13 x 16 uint4 */, yawidx /* shorts */, total_doubles;
 };
 
 __host__ __device__ inline SmemLayout make_layout(int Nmax, int Mmax, int nmax, int m, int past, int K, int Smax)
@@ -148,7 +148,7 @@ __host__ __device__ inline SmemLayout make_layout(int Nmax, int Mmax, int nmax, 
         const int lu = 2 * 16 * UALM_FW + 2 * 12 * UALM_FW, rg = 2 * UALM_RINGB * 6 * UALM_FW;
         o += lu > rg ? lu : rg;
     }
-    L.roles = o; o += (12 * 16 + 3) / 4;  // shorts packed
+    L.lutab = o; o += 13 * 16 * 2;        // LU step constants: 13 pivot types x 16 half-warp lanes x 16 bytes
     L.yawidx = o; o += (Smax + 3) / 4;   // shorts packed
     L.total_doubles = (o + 1) & ~1;
     (void)m;
@@ -218,7 +218,8 @@ struct Traj {
     // smem
     SPtr cxy, cyaw, gCxy, gCyaw, gTxy, gTyaw;
     SPtr x, g, xp, gp, d, pf, s1tab, base, sc, win, tmpl, ring;
-    SPtrU16 yawidx, roles;
+    SPtrU16 yawidx;
+    unsigned lutab;    // shared-memory byte address of the LU step-constant table
     // global
     R *lambda, *mu, *scale_cx, *hx, *gx, *lm_s, *lm_y, *lm_alpha, *lm_ys, *scr;
     R *Fxy, *Fyaw;                  // row 0 of each factor array
@@ -451,75 +452,73 @@ __device__ __forceinline__ int tmpl_index(int r, int n6)
     return (r - 3) % 6;
 }
 
-// rows r0 .. r0+5 of A into the sliding window (entries whose column falls outside the matrix are zero).  General version
-// (any r0) for the prologue; lane hl < 13 owns band column q = hl.
-__device__ __forceinline__ void lu_fill6(SPtr W, SPtr TM, int r0, int n6, int hl)
+// Constants of one pivot step per pivot type (0..5 = k mod 6, 6..11 = the last six pivots, 12 = no work) and half-warp lane,
+// 16 bytes each: byte offsets into the 12-row window (UALM_WROW doubles per row; the pivot of type ty sits in row ty mod 6) of
+//   .x the multiplier entry this lane divides (the pivot itself for the reciprocal lane and for idle lanes),
+//   .y the entry this lane updates, .z the pivot-row entry of that update,
+//   .w control: bits 0-1 lane holding the update's multiplier, 2 multiplier/reciprocal lane, 3 reciprocal lane, 4 update
+//      enabled, 5 factor store enabled, bits 8.. offset of this lane's factor entry in row k of F.
+// Built once per trajectory slot (3.3 KB of shared memory).
+#define UALM_WROW 16
+__device__ __forceinline__ void sts128(unsigned a, uint4 v)
 {
-    if (hl < 13) {
-#pragma unroll 1
-        for (int rr = 0; rr < 6; rr++) {
-            const int r = r0 + rr, c = r - 6 + hl;
-            R v = 0.0;
-            if (r < n6 && c >= 0 && c < n6) v = TM[tmpl_index(r, n6) * UALM_FW + hl];
-            W[(r & 15) * UALM_FW + hl] = v;
-        }
-    }
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-// steady-state version: r0 = k + 8 with k a multiple of 6, so the junction-row type of row r0+rr is (5 + rr) mod 6
-__device__ __forceinline__ void lu_fill6_aligned(SPtr W, SPtr TM, int r0, int n6, int hl)
+__device__ __forceinline__ uint4 lds128(unsigned a)
 {
-    if (hl < 13) {
-        if (r0 + 5 < n6 - 3 && r0 >= 9) { // all six rows are junction rows with every band column inside the matrix
-#pragma unroll
-            for (int rr = 0; rr < 6; rr++) W[((r0 + rr) & 15) * UALM_FW + hl] = TM[((5 + rr) % 6) * UALM_FW + hl];
-        } else {
-#pragma unroll 1
-            for (int rr = 0; rr < 6; rr++) {
-                const int r = r0 + rr, c = r - 6 + hl;
-                R v = 0.0;
-                if (r < n6 && c >= 0 && c < n6) v = TM[tmpl_index(r, n6) * UALM_FW + hl];
-                W[(r & 15) * UALM_FW + hl] = v;
-            }
-        }
-    }
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
 }
-
-// lane roles of one pivot step, per pivot type and half-warp lane, packed: bits 0-2 multiplier-row offset (7 = the lane that
-// forms the reciprocal of the pivot, 0 = none), bits 3-5 / 6-8 row / column offset of this lane's update entry (column 0 =
-// none), bits 9-10 the lane holding that update's multiplier.  Built once per kernel in shared memory (768 B).
-__device__ __forceinline__ void lu_build_roles(SPtrU16 roles, int lane)
+__device__ __forceinline__ void lu_build_consts(unsigned tab, int lane)
 {
-    for (int e = lane; e < 12 * 16; e += 32) {
+    for (int e = lane; e < 13 * 16; e += 32) {
         const int ty = e >> 4, hl = e & 15;
-        const int nm = lu_nm(ty), nu = lu_nu(ty);
-        int mo = 0, uo = 0, uc = 0, ul = 0;
-        if (hl < nm) mo = lu_mult(ty, hl);
-        else if (hl == nm) mo = 7;
-        if (hl < nm * nu) {
-            ul = hl / nu;
-            uo = lu_mult(ty, ul);
-            uc = lu_ucol(ty, hl - ul * nu);
+        uint4 c = make_uint4(8u * 6u, 8u * 6u, 8u * 6u, 0u);
+        if (ty < 12) {
+            const int tt = ty % 6;
+            const int nm = lu_nm(ty), nu = lu_nu(ty);
+            int mo = 0, uo = 0, uc = 0, ul = 0;
+            if (hl < nm) mo = lu_mult(ty, hl);
+            else if (hl == nm) mo = 7;
+            if (hl < nm * nu) {
+                ul = hl / nu;
+                uo = lu_mult(ty, ul);
+                uc = lu_ucol(ty, hl - ul * nu);
+            }
+            const bool act = (mo != 0), isr = (mo == 7), ulane = (hl >= 5 && hl < 12);
+            const int o = isr ? 0 : mo;
+            const bool upd = (uc != 0) && (ty < 6 || tt + uc < 6);       // the last six pivots: column k + uc must exist
+            const int so = act ? (isr ? 13 : o * UALM_FW + 6 - o) : 6 + (ulane ? hl - 5 : 0);
+            c.x = 8u * (unsigned)((tt + o) * UALM_WROW + 6 - o);
+            c.y = 8u * (unsigned)((tt + uo) * UALM_WROW + 6 + uc - uo);
+            c.z = 8u * (unsigned)(tt * UALM_WROW + 6 + uc);
+            c.w = (unsigned)ul | (act ? 4u : 0u) | (isr ? 8u : 0u) | (upd ? 16u : 0u) | ((act || ulane) ? 32u : 0u) | ((unsigned)so << 8);
         }
-        roles[e] = (unsigned short)(mo | (uo << 3) | (uc << 6) | (ul << 9));
+        sts128(tab + 16u * (unsigned)e, c);
     }
 }
 
 // Banded LU without pivoting (banded_system.hpp:66-91) of the xy system (lanes 0..15) and the yaw system (lanes 16..31) in
-// lockstep on two 16-row sliding windows in shared memory.  Element-wise the update sequence is the reference's; within one
-// pivot step the <=4 multipliers, the reciprocal of the pivot and the <=12 updates run on different lanes.  Final factors
-// stream to global memory: F[row][q] = LU(row, row-6+q), FT[col][q] = LU(col-6+q, col), F[row][13] = FT[row][13] =
-// RN(1 / LU(row,row)) for the division-free sweeps.  The loop body is kept small on purpose (instruction cache).
+// lockstep.  Element-wise the update sequence is the reference's; within one pivot step the <=4 multipliers, the reciprocal of
+// the pivot and the <=12 updates run on different lanes.  Final factors stream to global memory: F[row][q] = LU(row, row-6+q),
+// F[row][13] = RN(1 / LU(row,row)) for the division-free sweeps.
+//
+// Six pivots (one period of the structure) form a super-step on a 12-row shared-memory window: rows 0..5 are the pivot rows,
+// rows 6..11 the rows below them; after the six steps rows 6..11 move up and fresh template rows enter.  Because the window
+// never slides inside a super-step, every operand address of a lane is a constant of (lane, pivot type), read from the table
+// of lu_build_consts one step ahead; a pivot step is ~50 instructions without data-dependent branches (a taken branch costs a
+// lone warp ~20 cycles) in a loop small enough for the instruction cache (an unrolled super-step measured slower).
 __device__ UALM_NOINLINE void lu_dual(Traj &t, int lane)
 {
     const int sys = lane >> 4, hl = lane & 15;
     const int P = sys ? t.M : t.N, n6 = 6 * P;
-    const SPtr W = t.win + sys * (16 * UALM_FW);
+    const unsigned Wb = (t.win + sys * (12 * UALM_WROW)).a;
     const SPtr TM = t.tmpl + sys * (12 * UALM_FW);
     R *F = sys ? t.Fyaw : t.Fxy;
     {
         const R T1 = t.sc[sys ? SC_TY1 : SC_TX1], T2 = t.sc[sys ? SC_TY2 : SC_TX2], T3 = t.sc[sys ? SC_TY3 : SC_TX3],
                 T4 = t.sc[sys ? SC_TY4 : SC_TX4], T5 = t.sc[sys ? SC_TY5 : SC_TX5];
-        const SPtr TMw = t.tmpl + sys * (12 * UALM_FW);
 #pragma unroll 1
         for (int e = hl; e < 12 * 13; e += 16) {
             const int row = e / 13, q = e - 13 * row;
@@ -527,67 +526,90 @@ __device__ UALM_NOINLINE void lu_dual(Traj &t, int lane)
             if (row < 6) v = a_entry(4, 9 + row, q, T1, T2, T3, T4, T5);          // junction 1 of a 4-piece system
             else if (row < 9) v = (q == 6) ? (row == 8 ? 2.0 : 1.0) : 0.0;        // head rows
             else v = a_entry(4, 21 + (row - 9), q, T1, T2, T3, T4, T5);          // tail rows of a 4-piece system
-            TMw[row * UALM_FW + q] = v;
+            TM[row * UALM_FW + q] = v;
         }
     }
     UALM_SYNC();
-    lu_fill6(W, TM, 0, n6, hl);
-    lu_fill6(W, TM, 6, n6, hl);
-    UALM_SYNC();
-    const int nmax6 = 6 * (t.N > t.M ? t.N : t.M);
-    const SPtrU16 roles = t.roles;
-    R *Fk = F;                     // row k of F
-    int kmod = 0;
-    // The pivot step is written without data-dependent branches (a taken branch costs a lone warp ~20 cycles, the step had
-    // eight): every lane loads its operands from always-valid window addresses up front, divides a sanitised pair, and only the
-    // stores are predicated.  The role word of step k+1 is fetched during step k.
-    auto role_of = [&](int kk, int km) -> unsigned {
-        const int ty = (kk >= n6 - 6) ? 6 + (kk - (n6 - 6)) : km;
-        const int idx = (kk < n6) ? ((ty << 4) + hl) : hl;
-        const unsigned r = (unsigned)(int)roles[idx];
-        return (kk < n6) ? r : 0u;
+    // rows r0 .. r0+5 of A into window rows wr0 .. wr0+5 (entries whose column falls outside the matrix are zero); lane hl < 13
+    // owns band column q = hl
+    auto fill6 = [&](int r0, int wr0) {
+        if (hl < 13) {
+#pragma unroll 1
+            for (int rr = 0; rr < 6; rr++) {
+                const int r = r0 + rr, c = r - 6 + hl;
+                R v = 0.0;
+                if (r < n6 && c >= 0 && c < n6) v = TM[tmpl_index(r, n6) * UALM_FW + hl];
+                sts64(Wb + 8u * (unsigned)((wr0 + rr) * UALM_WROW + hl), v);
+            }
+        }
     };
-    unsigned role_next = role_of(0, 0);
+    fill6(0, 0);
+    fill6(6, 6);
+    // this lane's entries of the six interior junction rows in the order they enter the window (row r0 + rr, r0 a multiple of 6)
+    R tmv[6];
+#pragma unroll
+    for (int rr = 0; rr < 6; rr++) tmv[rr] = (hl < 13) ? (R)TM[((rr + 3) % 6) * UALM_FW + hl] : 0.0;
     const bool ulane = (hl >= 5 && hl < 12);
     const int uq = ulane ? hl - 5 : 0;
+    UALM_SYNC();
+    const int Pmax = t.N > t.M ? t.N : t.M;
+    const unsigned tab = t.lutab + 16u * (unsigned)hl;
+    R *Fk = F;                     // row k of F
 #pragma unroll 1
-    for (int k = 0; k < nmax6; k++, Fk += UALM_FW) {
-        const bool on = k < n6;
-        if (kmod == 0 && on) lu_fill6_aligned(W, TM, k + 8, n6, hl);
-        const unsigned role = role_next;
-        const int kmod1 = (kmod == 5) ? 0 : kmod + 1;
-        role_next = role_of(k + 1, kmod1);
-        const int mo = role & 7, uo = (role >> 3) & 7, uc = (role >> 6) & 7, ul = (role >> 9) & 3;
-        const SPtr Wk = W + (k & 15) * UALM_FW;
-        const bool act = (mo != 0), isr = (mo == 7);
-        const int o = isr ? 0 : mo;
-        const SPtr pa = W + (((k + o) & 15) * UALM_FW + 6 - o);                 // o = 0: the pivot itself
-        const SPtr pw = W + (((k + uo) & 15) * UALM_FW + 6 + uc - uo);          // uo = uc = 0: the pivot itself
-        const R piv = Wk[6];
-        const R av = *pa;
-        const R urow = Wk[6 + uq];
-        const R u = Wk[6 + uc];
-        const R w = *pw;
-        const R a = isr ? 1.0 : av;
-        const bool nz = act && (a != 0.0);
-        // exact zeros are skipped by the reference (banded_system.hpp:74) and would push the division onto its slow path
-        R m = (nz ? a : 1.0) / (act ? piv : 1.0);
-        m = nz ? m : (act ? a : 0.0);
-        if (act && !isr) {
-            *pa = m;
-            Fk[o * UALM_FW + 6 - o] = m;       // F[k+o][6-o]
-        }
-        if (isr) {
+    for (int j = 0; j < Pmax; j++) {
+        // pivot types of this super-step: the last six pivots have their own patterns; a finished system idles on type 12
+        const int ty0 = (j >= P) ? 12 : (j == P - 1 ? 6 : 0);
+        unsigned ctab = tab + 256u * (unsigned)ty0, apiv = Wb + 8u * 6u, aurow = Wb + 8u * (unsigned)(6 + uq);
+        uint4 cn = lds128(ctab);
+#pragma unroll 1
+        for (int tt = 0; tt < 6; tt++) {
+            const uint4 c = cn;
+            if (ty0 != 12) ctab += 256u;
+            cn = lds128(ctab);                                   // constants of the next step (tt = 5 reads one entry ahead: unused)
+            const bool act = (c.w & 4u) != 0, isr = (c.w & 8u) != 0;
+            const R piv = lds64(apiv);
+            const R av = lds64(Wb + c.x);
+            const R urow = lds64(aurow);
+            const R u = lds64(Wb + c.z);
+            const R w = lds64(Wb + c.y);
+            const R a = isr ? 1.0 : av;
+            const bool nz = act && (a != 0.0);
+            // exact zeros are skipped by the reference (banded_system.hpp:74) and would push the division onto its slow path
+            R m = (nz ? a : 1.0) / (act ? piv : 1.0);
+            m = nz ? m : (act ? a : 0.0);
+            if (act && !isr) sts64(Wb + c.x, m);
+            R val = act ? m : urow;
             // a divisor with an all-ones significand is the one case the reciprocal-based division cannot round: flag it
-            R mf = m;
-            if ((__double_as_longlong(piv) & 0xFFFFFFFFFFFFFll) == 0xFFFFFFFFFFFFFll) mf = __longlong_as_double(0x7ff8000000000000ll);
-            Fk[13] = mf;
+            if (isr && (__double_as_longlong(piv) & 0xFFFFFFFFFFFFFll) == 0xFFFFFFFFFFFFFll) val = __longlong_as_double(0x7ff8000000000000ll);
+            if (c.w & 32u) Fk[(c.w >> 8) & 127u] = val;
+            const R mr = __shfl_sync(0xffffffffu, m, (lane & 16) + (int)(c.w & 3u));
+            if ((c.w & 16u) && u != 0.0 && mr != 0.0) sts64(Wb + c.y, w - mr * u);
+            UALM_SYNC();
+            Fk += UALM_FW;
+            apiv += 8u * UALM_WROW; aurow += 8u * UALM_WROW;
         }
-        if (on && !act && ulane) Fk[6 + uq] = urow;
-        const R mr = __shfl_sync(0xffffffffu, m, (lane & 16) + ul);
-        if (uc != 0 && k + uc < n6 && u != 0.0 && mr != 0.0) *pw = w - mr * u;
+        // rows 6..11 move up; the next six rows of A enter (each lane moves its own band column: no hazard between lanes)
+        if (j + 1 < P && hl < 13) {
+            R mv[6];
+#pragma unroll
+            for (int rr = 0; rr < 6; rr++) mv[rr] = lds64(Wb + 8u * (unsigned)((6 + rr) * UALM_WROW + hl));
+#pragma unroll
+            for (int rr = 0; rr < 6; rr++) sts64(Wb + 8u * (unsigned)(rr * UALM_WROW + hl), mv[rr]);
+            const int r0 = 6 * (j + 1) + 6;
+            if (r0 + 5 < n6 - 3) {      // six interior junction rows, every band column inside the matrix
+#pragma unroll
+                for (int rr = 0; rr < 6; rr++) sts64(Wb + 8u * (unsigned)((6 + rr) * UALM_WROW + hl), tmv[rr]);
+            } else {
+#pragma unroll 1
+                for (int rr = 0; rr < 6; rr++) {
+                    const int r = r0 + rr, cc = r - 6 + hl;
+                    R v = 0.0;
+                    if (r < n6 && cc >= 0 && cc < n6) v = TM[tmpl_index(r, n6) * UALM_FW + hl];
+                    sts64(Wb + 8u * (unsigned)((6 + rr) * UALM_WROW + hl), v);
+                }
+            }
+        }
         UALM_SYNC();
-        kmod = kmod1;
     }
 }
 
@@ -1916,8 +1938,8 @@ __device__ UALM_NOINLINE void traj_setup(Traj &t, const BatchPtrs &bp, const Dev
     t.x = S8(L.x); t.g = S8(L.g); t.xp = S8(L.xp); t.gp = S8(L.gp); t.d = S8(L.d); t.pf = S8(L.pf); t.s1tab = S8(L.s1tab);
     t.base = S8(L.base); t.sc = S8(L.sc); t.win = S8(L.win); t.tmpl = S8(L.tmpl); t.ring = S8(L.ring);
     t.yawidx = SPtrU16{sm + 8u * (unsigned)L.yawidx};
-    t.roles = SPtrU16{sm + 8u * (unsigned)L.roles};
-    if (wig == 0) lu_build_roles(t.roles, threadIdx.x & 31);
+    t.lutab = sm + 8u * (unsigned)L.lutab;
+    if (wig == 0) lu_build_consts(t.lutab, threadIdx.x & 31);
     t.lambda = bp.lambda + pd->off_s; t.hx = bp.hx + pd->off_s;
     t.mu = bp.mu + 6 * pd->off_s; t.gx = bp.gx + 6 * pd->off_s;
     t.scale_cx = bp.scale_cx + 7 * pd->off_s;
