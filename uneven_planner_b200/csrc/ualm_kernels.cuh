@@ -334,16 +334,19 @@ __device__ __forceinline__ R div_by_recip(R a, R b, R rb)
 }
 // the same quotient without the fallback: `bad` collects the cases that need the IEEE division, so that a chain of quotients
 // (a sweep block) pays one branch at its end instead of one per row
+// With rb = RN(1/b) one correction step already yields the correctly rounded quotient (Markstein's theorem; 0 mismatches in
+// 1.8e10 pairs, tools/microbench/fastdiv.cu), so the caller's dependent chain continues from q1 (three fp64 operations, ~20
+// cycles each on B200) while the second step only verifies it off the chain: any disagreement raises `bad`.
 __device__ __forceinline__ R div_by_recip_flag(R a, R b, R rb, bool &bad)
 {
-    R q = a * rb;
-    R e = fma(-q, b, a);
-    q = fma(e, rb, q);
-    e = fma(-q, b, a);
-    q = fma(e, rb, q);
-    const R aq = fabs(q);
-    bad = bad || !(aq < 1.0e290) || (aq < 1.0e-290 && a != 0.0);
-    return q;
+    const R q0 = a * rb;
+    const R e0 = fma(-q0, b, a);
+    const R q1 = fma(e0, rb, q0);
+    const R e1 = fma(-q1, b, a);
+    const R q2 = fma(e1, rb, q1);
+    const R aq = fabs(q1);
+    bad = bad || !(q2 == q1) || !(aq < 1.0e290) || (aq < 1.0e-290 && a != 0.0);
+    return q1;
 }
 
 // IEEE a / b for callers whose numerator is often exactly zero.  The inline fast path of the fp64 division hands a zero (or
@@ -583,7 +586,10 @@ __device__ UALM_NOINLINE void lu_dual(Traj &t, int lane)
             if (isr && (__double_as_longlong(piv) & 0xFFFFFFFFFFFFFll) == 0xFFFFFFFFFFFFFll) val = __longlong_as_double(0x7ff8000000000000ll);
             if (c.w & 32u) Fk[(c.w >> 8) & 127u] = val;
             const R mr = __shfl_sync(0xffffffffu, m, (lane & 16) + (int)(c.w & 3u));
-            if ((c.w & 16u) && u != 0.0 && mr != 0.0) sts64(Wb + c.y, w - mr * u);
+            // zero tests on the bit patterns (an fp64 compare has the latency of an fp64 add, and this one sits on the chain)
+            const bool unz = ((unsigned long long)__double_as_longlong(u) << 1) != 0ull;
+            const bool mnz = ((unsigned long long)__double_as_longlong(mr) << 1) != 0ull;
+            if ((c.w & 16u) && unz && mnz) sts64(Wb + c.y, w - mr * u);
             UALM_SYNC();
             Fk += UALM_FW;
             apiv += 8u * UALM_WROW; aurow += 8u * UALM_WROW;
