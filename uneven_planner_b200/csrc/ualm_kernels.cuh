@@ -1,7 +1,8 @@
 // ualm_kernels.cuh -- sm_100a device code of the batched MINCO / PHR-ALM / L-BFGS trajectory optimizer.
 //
-// ONE WARP owns one optimizeSE2Traj problem from the first evaluation to the last dual update (no host round trips);
-// a launch is B independent warps (CTA = 32 threads), so a whole batch of ~10^3 problems is resident on the 148 SMs.
+// A WARP GROUP (1, 2 or 4 warps of a 4-warp CTA) owns one optimizeSE2Traj problem from the first evaluation to the last dual
+// update (no host round trips): its first warp runs the whole algorithm, the others serve its parallel phases; a batch of
+// ~10^3 problems is resident on the 148 SMs (8 warps per SM).
 // The arithmetic is IEEE double with contraction OFF (-fmad=false) and is ordered so that every floating-point result is
 // bit-identical to the CPU oracle (oracle/oracle.cpp):
 //   * work that is independent per element (band-matrix entries inside one pivot step, constraint samples,
@@ -10,9 +11,9 @@
 //     alm_traj_opt.cpp:825-943, gdC/gdT accumulation :969-985, triangular sweeps banded_system.hpp:96-145);
 //   * dot products / norms of the L-BFGS driver (order left to Eigen in the reference) use the canonical 32-lane order:
 //     lane-strided partial sums + xor-butterfly 16,8,4,2,1 (warp shuffles).
-// Memory plan per trajectory: coefficients, gradients and the decision vectors live in shared memory (~17 KB); the band
-// LU runs on a 16-row sliding window in shared memory and streams its factors to global memory (L2) in row-major (F) and
-// column-major (FT) form; the four triangular sweeps read them back through cp.async rings with the last six solution
+// Memory plan per trajectory: coefficients, gradients and the decision vectors live in shared memory (20-36 KB); the band
+// LU runs on a 12-row window in shared memory and streams its factors to global memory (L2), row-major with the reciprocal
+// of the diagonal in column 13; the four triangular sweeps read them back through cp.async rings with the last six solution
 // values in registers; L-BFGS history, duals, constraint values and the per-sample scratch are coalesced global arrays.
 // Reference citations are relative to /root/reference/src/uneven_planner/.
 #pragma once
@@ -23,8 +24,8 @@
 #include "ualm.h"
 #include "ualm_detmath.h"
 
-#define UALM_THREADS 32         // one warp per trajectory
-#define UALM_WPB 4              // independent trajectories (warps) per CTA: spreads them over the 4 SM sub-partitions
+#define UALM_THREADS 32         // threads per warp slot
+#define UALM_WPB 4              // warp slots per CTA (4 / 2 / 1 trajectories with 1 / 2 / 4 warps each)
 #define UALM_NFIELD 26          // per-sample scratch fields (see SF_* below)
 #define UALM_NPROF 16
 #define UALM_FW 14              // doubles per factor row (13 band entries + 1 pad -> 112 B = 7 x 16 B)
@@ -78,7 +79,7 @@ struct ProbDesc {
     long long off_cyaw;   // 6 M
     long long off_hist;   // mem_size * n  (lm_s, lm_y)
     long long off_scr;    // UALM_NFIELD * S per-sample scratch
-    long long off_fac;    // factor arrays: Fxy, FTxy ((6N + 2 pad) rows each), Fyaw, FTyaw, UALM_FW doubles per row
+    long long off_fac;    // factor arrays: Fxy ((6N + 2 pad) rows), Fyaw ((6M + 2 pad) rows), UALM_FW doubles per row
     long long off_ws;     // initScaling adjoint workspace (12 N + 6 M) * 32
     R bnd[18];
     R total_time;
@@ -625,11 +626,11 @@ __device__ UALM_NOINLINE void lu_dual(Traj &t, int lane)
 // division).
 //   KIND 0: L y = b      blocks ascending,  entries F[i][6-d]
 //   KIND 1: U x = y      blocks descending, entries F[i][6+d],  then / F[i][6]
-//   KIND 2: U^T y = b    blocks ascending,  entries FT[i][6-d], then / FT[i][6]
-//   KIND 3: L^T x = y    blocks descending, entries FT[i][6+d]
+//   KIND 2: U^T y = b    blocks ascending,  entries U(i-d,i) = F[i-d][6+d] (the neighbour block's rows), then / F[i][6]
+//   KIND 3: L^T x = y    blocks descending, entries L(i+d,i) = F[i+d][6-d]
 // Bit d-1 of the mask of row type t (= row mod 6) says whether term d can be non-zero; the last block of a system (tail
-// rows) uses the full mask for the L-based kinds.  Factor blocks arrive through an 8-block cp.async ring per system
-// (prefetch distance 4 blocks); the previous block's six results stay in registers, so no window shifting is needed.
+// rows) uses the full mask for the L-based kinds.  Factor blocks arrive through a UALM_RINGB-block cp.async ring per system
+// (prefetch distance UALM_RINGB - 2 blocks); the previous block's six results stay in registers, so no window shifting is needed.
 // ---------------------------------------------------------------------------------------------
 // six 6-bit masks packed per kind (row type t at bits 6t..6t+5)
 __host__ __device__ constexpr unsigned long long pack6(int a, int b, int c, int d, int e, int f)
