@@ -39,6 +39,19 @@ def hill_map(built):
 
 
 @pytest.fixture(scope="session")
+def terrain(built):
+    """terrain(name) -> UnevenMapData of one of the reference's terrains (skips when its .umap did not travel)."""
+    from uneven_planner_b200 import maps
+
+    def get(name):
+        m = maps.get_terrain(name)
+        if m is None:
+            pytest.skip(f"maps_built/{name}.umap not present (built by __graft_entry__.build() where the reference clouds exist)")
+        return m
+    return get
+
+
+@pytest.fixture(scope="session")
 def oparams(built):
     import pyoracle as po
     from uneven_planner_b200 import _lib

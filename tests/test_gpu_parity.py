@@ -118,14 +118,18 @@ def test_full_solve_matches_oracle_hill(gpu, hill_map):
     assert sum(1 for r in res if r.ret_code == 0) >= pb.B // 2
 
 
-def test_full_solve_matches_golden_fixture(gpu, hill_map):
-    """committed oracle outputs (tests/golden/make_golden.py)"""
-    from uneven_planner_b200 import _lib, problems
-    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "hill_oracle_golden.npz"))
-    if hashlib.sha256(hill_map.cells.tobytes()).hexdigest() != str(gold["map_sha256"]):
-        pytest.skip("hill.umap differs from the golden's")
-    pb = problems.generate(hill_map, int(gold["B"]), seed=int(gold["seed"]))
-    opt = gpu.BatchALMTrajOpt().init(_lib.default_params()).set_environment(hill_map)
+@pytest.mark.parametrize("name", ["hill", "desert", "volcano", "forest"])
+def test_full_solve_matches_golden_fixture(gpu, terrain, name):
+    """committed oracle outputs per terrain with the parameter sets of BASELINE configs 1-5 (tests/golden/make_golden.py,
+    uneven_planner_b200/configs.py): hill; desert (max_sig 0.08); volcano (no scaling, rho_T 500, max_kap 0.3, 64 samples per
+    piece); forest"""
+    from uneven_planner_b200 import configs, problems
+    m = terrain(name)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{name}_oracle_golden.npz"))
+    if hashlib.sha256(m.cells.tobytes()).hexdigest() != str(gold["map_sha256"]):
+        pytest.skip(f"{name}.umap differs from the golden's")
+    pb = problems.generate(m, int(gold["B"]), seed=int(gold["seed"]), **configs.gen_kwargs(name))
+    opt = gpu.BatchALMTrajOpt().init(configs.params_for(name)).set_environment(m)
     res, cxy, cyaw = opt.optimize(pb)
     assert np.array_equal(np.array([r.ret_code for r in res]), gold["ret_code"])
     assert np.array_equal(np.array([r.n_evals for r in res]), gold["n_evals"])
@@ -133,6 +137,16 @@ def test_full_solve_matches_golden_fixture(gpu, hill_map):
     assert np.all(np.abs(cost - gold["inner_cost"]) <= NORTH_STAR_TOL * np.abs(gold["inner_cost"])) and np.array_equal(cost, gold["inner_cost"])
     assert np.array_equal(cxy, gold["c_xy"]) and np.array_equal(cyaw, gold["c_yaw"])
     opt.close()
+
+
+@pytest.mark.parametrize("name", ["desert", "volcano", "forest"])
+def test_full_solve_matches_oracle_other_terrains(gpu, terrain, name):
+    """a larger seeded batch per terrain against the oracle run on the box's host cores (configs 3-5 inputs)"""
+    from uneven_planner_b200 import configs, problems
+    m = terrain(name)
+    pb = problems.generate(m, 32, seed=5, **configs.gen_kwargs(name))
+    res, cxy, cyaw, ores = _solve_both(gpu, m, pb, configs.params_for(name))
+    _assert_solve_parity(pb, res, cxy, cyaw, ores)
 
 
 def test_full_solve_without_scaling_volcano_parameters(gpu, bumps_map):

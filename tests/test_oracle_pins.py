@@ -274,15 +274,18 @@ def test_init_scaling_definition(bumps_map):
 
 
 # ---------------------------------------------------------------- (8) frozen outputs
-def test_oracle_matches_golden_fixture(hill_map):
+@pytest.mark.parametrize("name", ["hill", "desert", "volcano", "forest"])
+def test_oracle_matches_golden_fixture(terrain, name):
+    """frozen oracle outputs per terrain / BASELINE config parameter set (tests/golden/make_golden.py)"""
     import hashlib, os
-    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "hill_oracle_golden.npz"))
-    if hashlib.sha256(hill_map.cells.tobytes()).hexdigest() != str(gold["map_sha256"]):
-        pytest.skip("hill.umap differs from the one the golden file was generated on")
-    pb = problems.generate(hill_map, int(gold["B"]), seed=int(gold["seed"]))
-    prm = po.params_from(_lib.default_params())
-    om = po.OracleMap(hill_map)
-    out = po.solve_batch(prm, om, pb, threads=4)
+    from uneven_planner_b200 import configs
+    m = terrain(name)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{name}_oracle_golden.npz"))
+    if hashlib.sha256(m.cells.tobytes()).hexdigest() != str(gold["map_sha256"]):
+        pytest.skip(f"{name}.umap differs from the one the golden file was generated on")
+    pb = problems.generate(m, int(gold["B"]), seed=int(gold["seed"]), **configs.gen_kwargs(name))
+    prm = po.params_from(configs.params_for(name))
+    out = po.solve_batch(prm, po.OracleMap(m), pb, threads=4)
     assert np.array_equal(np.array([r[0].ret_code for r in out]), gold["ret_code"])
     assert np.array_equal(np.array([r[0].n_evals for r in out]), gold["n_evals"])
     assert np.array_equal(np.array([r[0].inner_cost for r in out]), gold["inner_cost"])
