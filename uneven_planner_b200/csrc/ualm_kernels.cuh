@@ -655,10 +655,31 @@ __device__ __forceinline__ bool sweep_rows(SPtr blk, SPtr nb, bool hasnb, BP b0,
     constexpr bool DIV = (KIND == 1 || KIND == 2);
     constexpr bool TR = (KIND == 2 || KIND == 3);   // transposed access: the factor entry lives in the neighbour's row
     bool bad = false;
+    // every factor entry of the block first: the shared-memory proxies are ordered (asm volatile), so a load placed after the
+    // store of the previous row's result would expose one shared-memory latency per row on the dependent chain
+    R fv[6][7], dgv[6], rdgv[6];
+#pragma unroll
+    for (int t = 0; t < 6; t++) {
+        const SPtr f = blk + t * UALM_FW;
+#pragma unroll
+        for (int d = 6; d >= 1; d--) {
+            fv[t][d] = 0.0;
+            if (FULL || ((sweep_mask(KIND, t) >> (d - 1)) & 1)) {
+                const int tn = ASC ? t - d : t + d;
+                const bool incur = ASC ? (tn >= 0) : (tn <= 5);
+                const int tq = incur ? tn : (ASC ? tn + 6 : tn - 6);
+                // factor entry: KIND 0: L(i,i-d) = F[i][6-d]; KIND 1: U(i,i+d) = F[i][6+d];
+                //               KIND 2: U(i-d,i) = F[i-d][6+d]; KIND 3: L(i+d,i) = F[i+d][6-d]
+                if (!TR) fv[t][d] = f[ASC ? 6 - d : 6 + d];
+                else if (incur) fv[t][d] = blk[tq * UALM_FW + (ASC ? 6 + d : 6 - d)];
+                else fv[t][d] = hasnb ? (R)nb[tq * UALM_FW + (ASC ? 6 + d : 6 - d)] : 0.0;
+            }
+        }
+        if (DIV) { dgv[t] = f[6]; rdgv[t] = EXACT ? 0.0 : (R)f[13]; }
+    }
 #pragma unroll
     for (int tt = 0; tt < 6; tt++) {
         const int t = ASC ? tt : 5 - tt;            // row type processed now
-        const SPtr f = blk + t * UALM_FW;
         R v0 = rhs0[t], v1 = rhs1[t];
 #pragma unroll
         for (int d = 6; d >= 1; d--) {
@@ -667,31 +688,24 @@ __device__ __forceinline__ bool sweep_rows(SPtr blk, SPtr nb, bool hasnb, BP b0,
                 const int tn = ASC ? t - d : t + d;
                 const bool incur = ASC ? (tn >= 0) : (tn <= 5);
                 const int tq = incur ? tn : (ASC ? tn + 6 : tn - 6);
-                // factor entry: KIND 0: L(i,i-d) = F[i][6-d]; KIND 1: U(i,i+d) = F[i][6+d];
-                //               KIND 2: U(i-d,i) = F[i-d][6+d]; KIND 3: L(i+d,i) = F[i+d][6-d]
-                R fv;
-                if (!TR) fv = f[ASC ? 6 - d : 6 + d];
-                else if (incur) fv = blk[tq * UALM_FW + (ASC ? 6 + d : 6 - d)];
-                else fv = hasnb ? nb[tq * UALM_FW + (ASC ? 6 + d : 6 - d)] : 0.0;
                 // the reference skips exact-zero factors (banded_system.hpp:103,112,131,139); subtracting 0 * w instead leaves
                 // every value unchanged (at most the sign of an exact zero differs), so no test is needed here
                 const R w0 = incur ? cur0[tq] : prev0[tq];
-                v0 = v0 - fv * w0;
+                v0 = v0 - fv[t][d] * w0;
                 if (NCOL == 2) {
                     const R w1 = incur ? cur1[tq] : prev1[tq];
-                    v1 = v1 - fv * w1;
+                    v1 = v1 - fv[t][d] * w1;
                 }
             }
         }
         if (DIV) {
-            const R dg = f[6];
+            const R dg = dgv[t];
             if (EXACT) {
                 v0 = v0 / dg;
                 if (NCOL == 2) v1 = v1 / dg;
             } else {
-                const R rdg = f[13];
-                v0 = div_by_recip_flag(v0, dg, rdg, bad);
-                if (NCOL == 2) v1 = div_by_recip_flag(v1, dg, rdg, bad);
+                v0 = div_by_recip_flag(v0, dg, rdgv[t], bad);
+                if (NCOL == 2) v1 = div_by_recip_flag(v1, dg, rdgv[t], bad);
             }
         }
         at(b0, (row0 + t) * bst) = v0;
