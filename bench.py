@@ -263,11 +263,11 @@ def main():
     alg = pen_b + lb_b + mc_b
     achieved = alg / (solve_ms * 1e-3) / 1e9
     traffic = load_traffic()
-    roof = {"kernel": "ualm::solve_kernel (whole ALM/L-BFGS solve, one warp per trajectory)", "bound": "hbm", "achieved": achieved, "peak": peak,
+    roof = {"kernel": "ualm::solve_kernel (whole ALM/L-BFGS solve of the batch: a warp group per trajectory, one launch per size class on concurrent streams)", "bound": "hbm", "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "traffic": traffic.get("solve_kernel_bytes_per_launch_b1024") if args.batch == 1024 else None,
             "peak_source": peak_src, "kernel_ms": solve_ms,
             "algorithmic_bytes": {"penalty": pen_b, "lbfgs": lb_b, "minco_io": mc_b},
-            "note": "latency-bound: bit-reproducible fp64, one warp per trajectory (DESIGN.md section 4)"}
+            "note": "latency-bound: bit-reproducible fp64 dependent chains, a warp group per trajectory (DESIGN.md section 4)"}
     pms, pbytes = opt.time_penalty_kernel(5)
     roof_pen = {"kernel": "ualm::penalty_only_kernel (calConstrainCostGrad samples + accumulation, 1 evaluation per trajectory)",
                 "bound": "hbm", "achieved": pbytes / (pms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",

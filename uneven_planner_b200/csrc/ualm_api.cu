@@ -339,7 +339,7 @@ extern "C" int ualm_upload(ualm_ctx_t *c, int B, const int32_t *N, const int32_t
     CK(c->d_desc.ensure(B)); CK(c->d_order.ensure(B)); CK(c->d_wdesc.ensure(c->wdesc.size())); CK(c->d_x0.ensure(ox)); CK(c->d_x.ensure(ox)); CK(c->d_grad.ensure(ox));
     CK(c->d_lambda.ensure(os)); CK(c->d_hx.ensure(os)); CK(c->d_mu.ensure(6 * os)); CK(c->d_gx.ensure(6 * os)); CK(c->d_scale_cx.ensure(7 * os));
     CK(c->d_lm_s.ensure(oh)); CK(c->d_lm_y.ensure(oh)); CK(c->d_scr.ensure(oscr));
-    CK(c->d_ws.ensure(ows)); CK(c->d_fac.ensure(ofac)); CK(c->d_lm_aux.ensure((size_t)std::max(B, 1) * 2 * m));
+    CK(c->d_ws.ensure(ows)); CK(c->d_fac.ensure(ofac)); CK(c->d_lm_aux.ensure((size_t)std::max(B, 1) * 3 * m));
     // factor arrays: entries outside the band-in-matrix positions (and the pad rows) are never written and must read 0
     if (ofac > 0) CK(cudaMemsetAsync(c->d_fac.p, 0, sizeof(double) * ofac, c->stream));
     CK(c->d_prof.ensure((size_t)std::max(B, 1) * UALM_NPROF));

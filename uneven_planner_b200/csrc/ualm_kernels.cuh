@@ -96,7 +96,7 @@ struct BatchPtrs {
     R *x;                    // packed final decision vectors
     R *lambda, *mu, *scale_cx, *hx, *gx;
     R *lm_s, *lm_y;
-    R *lm_aux;               // per problem 2 * mem_size: lm_alpha | lm_ys
+    R *lm_aux;               // per problem 3 * mem_size: lm_alpha | lm_ys | RN(1 / lm_ys)
     R *scratch;
     R *fac;                  // LU factors
     R *ws_scaling;           // initScaling adjoint workspace
@@ -222,7 +222,7 @@ struct Traj {
     SPtrU16 yawidx;
     unsigned lutab;    // shared-memory byte address of the LU step-constant table
     // global
-    R *lambda, *mu, *scale_cx, *hx, *gx, *lm_s, *lm_y, *lm_alpha, *lm_ys, *scr;
+    R *lambda, *mu, *scale_cx, *hx, *gx, *lm_s, *lm_y, *lm_alpha, *lm_ys, *lm_rys, *scr;
     R *Fxy, *Fyaw;                  // row 0 of each factor array
     R *ws;
     // warp group of this trajectory: G warps (1, 2 or 4) of one CTA; warp 0 of the group (the leader) runs the whole algorithm,
@@ -584,7 +584,9 @@ __device__ UALM_NOINLINE void lu_dual(Traj &t, int lane)
             if (act && !isr) sts64(Wb + c.x, m);
             R val = act ? m : urow;
             // a divisor with an all-ones significand is the one case the reciprocal-based division cannot round: flag it
-            if (isr && (__double_as_longlong(piv) & 0xFFFFFFFFFFFFFll) == 0xFFFFFFFFFFFFFll) val = __longlong_as_double(0x7ff8000000000000ll);
+            // (selects, not a branch: the reciprocal lane alone would diverge from the rest of its half-warp)
+            const bool ones = (__double_as_longlong(piv) & 0xFFFFFFFFFFFFFll) == 0xFFFFFFFFFFFFFll;
+            val = (isr & ones) ? __longlong_as_double(0x7ff8000000000000ll) : val;
             if (c.w & 32u) Fk[(c.w >> 8) & 127u] = val;
             const R mr = __shfl_sync(0xffffffffu, m, (lane & 16) + (int)(c.w & 3u));
             // zero tests on the bit patterns (an fp64 compare has the latency of an fp64 add, and this one sits on the chain)
@@ -886,24 +888,29 @@ __device__ __forceinline__ bool map_in(const DevMap &m, const R pos[3]) // uneve
 
 __device__ __forceinline__ void map_get_all_with_grad_impl(const DevMap &m, const R pos[3], R values[7], R grads[7][3])
 {
+    // the map descriptor is a kernel parameter read through a generic pointer: fetch every field once (a re-read after any
+    // store costs a long-scoreboard wait, and the corner loop below used to re-read vn[2] sixteen times)
+    const int vn0 = m.vn[0], vn1 = m.vn[1], vn2 = m.vn[2];
+    const float4 *const cells = m.cells;
+    const R xy_res = m.xy_res, yaw_res = m.yaw_res, xy_inv = m.xy_inv, yaw_inv = m.yaw_inv, org0 = m.origin[0], org1 = m.origin[1], org2 = m.origin[2];
     R rs[3], rg[4][3];
     if (!map_in(m, pos)) {
         for (int r = 0; r < 4; r++) for (int k = 0; k < 3; k++) rg[r][k] = 0.0;
         rs[0] = rs[1] = rs[2] = 0.0;
     } else {
-        R pos_m[3] = {pos[0] - 0.5 * m.xy_res, pos[1] - 0.5 * m.xy_res, pos[2] - 0.5 * m.yaw_res};
+        R pos_m[3] = {pos[0] - 0.5 * xy_res, pos[1] - 0.5 * xy_res, pos[2] - 0.5 * yaw_res};
         normSO2(pos_m[2]);
         int idx[3];
-        idx[0] = (int)floor((pos_m[0] - m.origin[0]) * m.xy_inv);
-        idx[1] = (int)floor((pos_m[1] - m.origin[1]) * m.xy_inv);
-        idx[2] = (int)floor((pos_m[2] - m.origin[2]) * m.yaw_inv);
+        idx[0] = (int)floor((pos_m[0] - org0) * xy_inv);
+        idx[1] = (int)floor((pos_m[1] - org1) * xy_inv);
+        idx[2] = (int)floor((pos_m[2] - org2) * yaw_inv);
         R idx_pos[3];
-        idx_pos[0] = ((R)idx[0] + 0.5) * m.xy_res + m.origin[0];
-        idx_pos[1] = ((R)idx[1] + 0.5) * m.xy_res + m.origin[1];
-        idx_pos[2] = ((R)idx[2] + 0.5) * m.yaw_res + m.origin[2];
+        idx_pos[0] = ((R)idx[0] + 0.5) * xy_res + org0;
+        idx_pos[1] = ((R)idx[1] + 0.5) * xy_res + org1;
+        idx_pos[2] = ((R)idx[2] + 0.5) * yaw_res + org2;
         R diff[3];
-        diff[0] = (pos[0] - idx_pos[0]) * m.xy_inv;
-        diff[1] = (pos[1] - idx_pos[1]) * m.xy_inv;
+        diff[0] = (pos[0] - idx_pos[0]) * xy_inv;
+        diff[1] = (pos[1] - idx_pos[1]) * xy_inv;
         // start the eight corner cells now: the angle difference below costs two out-of-line calls the loads cannot cross
 #pragma unroll
         for (int x = 0; x < 2; x++)
@@ -912,16 +919,16 @@ __device__ __forceinline__ void map_get_all_with_grad_impl(const DevMap &m, cons
 #pragma unroll
                 for (int w = 0; w < 2; w++) {
                     int c0 = idx[0] + x, c1 = idx[1] + y, c2 = idx[2] + w;
-                    c0 = max(min(c0, m.vn[0] - 1), 0);
-                    c1 = max(min(c1, m.vn[1] - 1), 0);
-                    while (c2 > m.vn[2] - 1) c2 -= m.vn[2];
-                    while (c2 < 0) c2 += m.vn[2];
-                    prefetch_l1(&m.cells[(size_t)c0 * m.vn[1] * m.vn[2] + (size_t)c1 * m.vn[2] + c2]);
+                    c0 = max(min(c0, vn0 - 1), 0);
+                    c1 = max(min(c1, vn1 - 1), 0);
+                    while (c2 > vn2 - 1) c2 -= vn2;
+                    while (c2 < 0) c2 += vn2;
+                    prefetch_l1(&cells[(size_t)c0 * vn1 * vn2 + (size_t)c1 * vn2 + c2]);
                 }
         {
             R sd, cd;
             { const double2 scv = dev_sincos(pos[2] - idx_pos[2]); sd = scv.x; cd = scv.y; }
-            diff[2] = dev_atan2(sd, cd) * m.yaw_inv;
+            diff[2] = dev_atan2(sd, cd) * yaw_inv;
         }
         R v[2][2][2][3];
 #pragma unroll
@@ -931,11 +938,11 @@ __device__ __forceinline__ void map_get_all_with_grad_impl(const DevMap &m, cons
 #pragma unroll
                 for (int w = 0; w < 2; w++) {
                     int c0 = idx[0] + x, c1 = idx[1] + y, c2 = idx[2] + w;
-                    c0 = max(min(c0, m.vn[0] - 1), 0);
-                    c1 = max(min(c1, m.vn[1] - 1), 0);
-                    while (c2 > m.vn[2] - 1) c2 -= m.vn[2];
-                    while (c2 < 0) c2 += m.vn[2];
-                    const float4 cell = __ldg(&m.cells[(size_t)c0 * m.vn[1] * m.vn[2] + (size_t)c1 * m.vn[2] + c2]);
+                    c0 = max(min(c0, vn0 - 1), 0);
+                    c1 = max(min(c1, vn1 - 1), 0);
+                    while (c2 > vn2 - 1) c2 -= vn2;
+                    while (c2 < 0) c2 += vn2;
+                    const float4 cell = __ldg(&cells[(size_t)c0 * vn1 * vn2 + (size_t)c1 * vn2 + c2]);
                     v[x][y][w][0] = (R)cell.y; v[x][y][w][1] = (R)cell.z; v[x][y][w][2] = (R)cell.w;
                 }
 #pragma unroll
@@ -947,13 +954,13 @@ __device__ __forceinline__ void map_get_all_with_grad_impl(const DevMap &m, cons
             const R v0 = v00 * (1 - diff[1]) + v10 * diff[1];
             const R v1 = v01 * (1 - diff[1]) + v11 * diff[1];
             rs[k] = v0 * (1 - diff[2]) + v1 * diff[2];
-            rg[k][2] = (v1 - v0) * m.yaw_inv;
-            rg[k][1] = ((v10 - v00) * (1 - diff[2]) + (v11 - v01) * diff[2]) * m.xy_inv;
+            rg[k][2] = (v1 - v0) * yaw_inv;
+            rg[k][1] = ((v10 - v00) * (1 - diff[2]) + (v11 - v01) * diff[2]) * xy_inv;
             R g0 = (1 - diff[2]) * (1 - diff[1]) * (v[1][0][0][k] - v[0][0][0][k]);
             g0 += (1 - diff[2]) * diff[1] * (v[1][1][0][k] - v[0][1][0][k]);
             g0 += diff[2] * (1 - diff[1]) * (v[1][0][1][k] - v[0][0][1][k]);
             g0 += diff[2] * diff[1] * (v[1][1][1][k] - v[0][1][1][k]);
-            g0 *= m.xy_inv;
+            g0 *= xy_inv;
             rg[k][0] = g0;
         }
         const R cc = sqrt(1.0 - rs[1] * rs[1] - rs[2] * rs[2]);
@@ -1102,16 +1109,22 @@ __device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const 
     const R rrho = ((__double_as_longlong(rho) & 0xFFFFFFFFFFFFFll) == 0xFFFFFFFFFFFFFll) ? __longlong_as_double(0x7ff8000000000000ll) : 1.0 / rho;   // RN(1/rho): x / rho below is formed as div_by_recip(x, rho, rrho), bit-identical to the IEEE quotient
     const R step = t.sc[SC_TX1] / (R)K;
     R *scr = t.scr;
+    // parameters (kernel-parameter space through a generic pointer) and trajectory pointers (a struct in local memory) once
+    const R gravity = p.gravity, rho_ter = p.rho_ter, min_cxi = p.min_cxi, max_sig = p.max_sig;
+    const R max_vel2 = p.max_vel * p.max_vel, max_alon2 = p.max_acc_lon * p.max_acc_lon, max_alat2 = p.max_acc_lat * p.max_acc_lat,
+            max_kap2 = p.max_kap * p.max_kap;
+    const bool use_scaling = p.use_scaling != 0;
+    R *const lambda_p = t.lambda, *const mu_p = t.mu, *const scale_p = t.scale_cx, *const hx_p = t.hx, *const gx_p = t.gx;
     for (int s = gtid; s < S; s += GT) {
         const int i = s / (K + 1), j = s - i * (K + 1);
         // the duals and scales of this sample are needed only after the kinematics: start their cache lines now, and read them
         // in one batch before the first store below (a load placed after a store to a may-alias pointer cannot be hoisted by
         // the compiler, which would expose one memory latency per constraint)
-        prefetch_l1(t.lambda + s);
-        prefetch_l1(t.mu + 6 * (size_t)s); prefetch_l1(t.mu + 6 * (size_t)s + 5);
-        prefetch_l1(t.scale_cx + 7 * (size_t)s); prefetch_l1(t.scale_cx + 7 * (size_t)s + 6);
+        prefetch_l1(lambda_p + s);
+        prefetch_l1(mu_p + 6 * (size_t)s); prefetch_l1(mu_p + 6 * (size_t)s + 5);
+        prefetch_l1(scale_p + 7 * (size_t)s); prefetch_l1(scale_p + 7 * (size_t)s + 6);
         SampleK q;
-        sample_kin_impl<true>(t, map, p.gravity, i, t.s1tab[j], t.base[i], q);
+        sample_kin_impl<true>(t, map, gravity, i, t.s1tab[j], t.base[i], q);
         t.yawidx[s] = (unsigned short)q.yaw_idx;
         R grad_p[2] = {0, 0}, grad_v[2] = {0, 0}, grad_a[2] = {0, 0}, grad_se2[3] = {0, 0, 0};
         R grad_yaw = 0, grad_dyaw = 0, grad_vx2 = 0, grad_wz = 0, grad_ax = 0, grad_ay = 0, aug_grad = 0;
@@ -1119,15 +1132,15 @@ __device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const 
         const R vx = q.vx, wz = q.wz, ax = q.ax, ay = q.ay, curv_snorm = q.curv_snorm;
         R sc7[7], mu6[6];
 #pragma unroll
-        for (int k = 0; k < 7; k++) sc7[k] = t.scale_cx[7 * (size_t)s + k];
+        for (int k = 0; k < 7; k++) sc7[k] = scale_p[7 * (size_t)s + k];
 #pragma unroll
-        for (int k = 0; k < 6; k++) mu6[k] = t.mu[6 * (size_t)s + k];
-        const R lambda_s = t.lambda[s];
-        R *gx6 = t.gx + 6 * (size_t)s;
+        for (int k = 0; k < 6; k++) mu6[k] = mu_p[6 * (size_t)s + k];
+        const R lambda_s = lambda_p[s];
+        R *gx6 = gx_p + 6 * (size_t)s;
 
         R omega;
-        if (j == 0 || j == K) omega = 0.5 * p.rho_ter * step * scale_fx;
-        else omega = p.rho_ter * step * scale_fx;
+        if (j == 0 || j == K) omega = 0.5 * rho_ter * step * scale_fx;
+        else omega = rho_ter * step * scale_fx;
         const R user_cost = omega * sigma * sigma;
         scr[(SF_COST0 + 0) * S + s] = user_cost;
         scr[SF_USER * S + s] = user_cost;
@@ -1138,7 +1151,7 @@ __device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const 
             const R nonh_lambda = lambda_s;
             const R nhy0 = q.syaw, nhy1 = -q.cyaw;
             const R h = (q.vel[0] * nhy0 + q.vel[1] * nhy1) * sc7[0];
-            t.hx[s] = h;
+            hx_p[s] = h;
             scr[(SF_COST0 + 1) * S + s] = h * (nonh_lambda + 0.5 * rho * h);
             const R nonh_grad = (rho * h + nonh_lambda) * sc7[0];
             grad_v[0] += nonh_grad * nhy0; grad_v[1] += nonh_grad * nhy1;
@@ -1146,7 +1159,7 @@ __device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const 
         }
         { // longitude velocity
             const R m_ = mu6[0];
-            const R gv = (vx * vx - p.max_vel * p.max_vel) * sc7[1];
+            const R gv = (vx * vx - max_vel2) * sc7[1];
             gx6[0] = gv;
             if (rho * gv + m_ > 0) {
                 scr[(SF_COST0 + 2) * S + s] = gv * (m_ + 0.5 * rho * gv);
@@ -1156,7 +1169,7 @@ __device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const 
         }
         { // longitude acceleration
             const R m_ = mu6[1];
-            const R gv = (ax * ax - p.max_acc_lon * p.max_acc_lon) * sc7[2];
+            const R gv = (ax * ax - max_alon2) * sc7[2];
             gx6[1] = gv;
             if (rho * gv + m_ > 0) {
                 scr[(SF_COST0 + 3) * S + s] = gv * (m_ + 0.5 * rho * gv);
@@ -1166,7 +1179,7 @@ __device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const 
         }
         { // latitude acceleration
             const R m_ = mu6[2];
-            const R gv = (ay * ay - p.max_acc_lat * p.max_acc_lat) * sc7[3];
+            const R gv = (ay * ay - max_alat2) * sc7[3];
             gx6[2] = gv;
             if (rho * gv + m_ > 0) {
                 scr[(SF_COST0 + 4) * S + s] = gv * (m_ + 0.5 * rho * gv);
@@ -1177,13 +1190,13 @@ __device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const 
         { // curvature
             const R m_ = mu6[3];
             R gv;
-            if (p.use_scaling) gv = (curv_snorm - p.max_kap * p.max_kap) * sc7[4];
-            else gv = (curv_snorm - p.max_kap * p.max_kap) * UALM_CUR_SCALE;
+            if (use_scaling) gv = (curv_snorm - max_kap2) * sc7[4];
+            else gv = (curv_snorm - max_kap2) * UALM_CUR_SCALE;
             gx6[3] = gv;
             if (rho * gv + m_ > 0) {
                 const R denominator = 1.0 / (vx * vx + UALM_DELTA_SIGL);
                 scr[(SF_COST0 + 5) * S + s] = gv * (m_ + 0.5 * rho * gv);
-                if (p.use_scaling) aug_grad = (rho * gv + m_) * sc7[4];
+                if (use_scaling) aug_grad = (rho * gv + m_) * sc7[4];
                 else aug_grad = (rho * gv + m_) * UALM_CUR_SCALE;
                 grad_wz += aug_grad * denominator * 2.0 * wz;
                 grad_vx2 -= aug_grad * curv_snorm * denominator;
@@ -1191,7 +1204,7 @@ __device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const 
         }
         { // attitude
             const R m_ = mu6[4];
-            const R gv = (p.min_cxi - cos_xi) * sc7[5];
+            const R gv = (min_cxi - cos_xi) * sc7[5];
             gx6[4] = gv;
             if (rho * gv + m_ > 0) {
                 scr[(SF_COST0 + 6) * S + s] = gv * (m_ + 0.5 * rho * gv);
@@ -1203,13 +1216,13 @@ __device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const 
         { // surface variation
             const R m_ = mu6[5];
             R gv;
-            if (p.use_scaling) gv = (sigma - p.max_sig) * sc7[6];
-            else gv = (sigma - p.max_sig) * UALM_SIG_SCALE;
+            if (use_scaling) gv = (sigma - max_sig) * sc7[6];
+            else gv = (sigma - max_sig) * UALM_SIG_SCALE;
             gx6[5] = gv;
             if (rho * gv + m_ > 0) {
                 scr[(SF_COST0 + 7) * S + s] = gv * (m_ + 0.5 * rho * gv);
                 const R ag = rho * gv + m_;
-                if (p.use_scaling) {
+                if (use_scaling) {
 #pragma unroll
                     for (int k = 0; k < 3; k++) grad_se2[k] += ag * q.tg[6][k] * sc7[6];
                 } else {
@@ -1229,11 +1242,11 @@ __device__ UALM_NOINLINE void penalty_samples(Traj &t, const DevMap &map, const 
         grad_a[0] += grad_ax * inv_cos_vphix * q.cyaw; grad_a[1] += grad_ax * inv_cos_vphix * q.syaw;
         grad_yaw += grad_ax * inv_cos_vphix * q.lat_acc;
 #pragma unroll
-        for (int k = 0; k < 3; k++) grad_se2[k] += grad_ax * (p.gravity * q.tg[1][k] + q.tg[0][k] * q.lon_acc);
+        for (int k = 0; k < 3; k++) grad_se2[k] += grad_ax * (gravity * q.tg[1][k] + q.tg[0][k] * q.lon_acc);
         grad_a[0] += grad_ay * inv_cos_vphiy * (-q.syaw); grad_a[1] += grad_ay * inv_cos_vphiy * q.cyaw;
         grad_yaw -= grad_ay * inv_cos_vphiy * q.lon_acc;
 #pragma unroll
-        for (int k = 0; k < 3; k++) grad_se2[k] += grad_ay * (p.gravity * q.tg[3][k] + q.tg[2][k] * q.lat_acc);
+        for (int k = 0; k < 3; k++) grad_se2[k] += grad_ay * (gravity * q.tg[3][k] + q.tg[2][k] * q.lat_acc);
         grad_p[0] += grad_se2[0]; grad_p[1] += grad_se2[1];
         grad_yaw += grad_se2[2];
 
@@ -1617,7 +1630,14 @@ __device__ UALM_NOINLINE LbfgsOut lbfgs_optimize(Traj &t, const DevMap &map, con
         const R ss = lane_dot(sE, sE, n, lane);
         const R gpn = lane_dot(t.gp, t.gp, n, lane);
         const R cau = ss * sqrt(gpn) * cautious_factor;
-        if (lane == 0) t.lm_ys[end] = ys;
+        if (lane == 0) {
+            // ys divides one dot product per history step of every later two-loop: keep RN(1/ys) next to it so those quotients are
+            // a * RN(1/b) + corrections (div_by_recip) instead of a full division on the dependent chain
+            t.lm_ys[end] = ys;
+            R r = 1.0 / ys;
+            if ((__double_as_longlong(ys) & 0xFFFFFFFFFFFFFll) == 0xFFFFFFFFFFFFFll) r = __longlong_as_double(0x7ff8000000000000ll);
+            t.lm_rys[end] = r;
+        }
         UALM_SYNC();
         if (ys > cau) {
             ++bound;
@@ -1636,22 +1656,22 @@ __device__ UALM_NOINLINE LbfgsOut lbfgs_optimize(Traj &t, const DevMap &map, con
 #pragma unroll
                 for (int e = 0; e < 8; e++) { const int q = lane + 32 * e; sc_[e] = q < n ? sj[q] : 0.0; yc_[e] = q < n ? yj[q] : 0.0; }
             }
-            R ysj = t.lm_ys[j];
+            R ysj = t.lm_ys[j], rysj = t.lm_rys[j];
             for (int i = 0; i < bound; ++i) {
                 const int jn = (j + m - 1) % m;
-                R ysn = 0.0;
+                R ysn = 0.0, rysn = 0.0;
                 if (i + 1 < bound) {
                     const R *sj = t.lm_s + (size_t)jn * n, *yj = t.lm_y + (size_t)jn * n;
 #pragma unroll
                     for (int e = 0; e < 8; e++) { const int q = lane + 32 * e; if (q < n) { sn_[e] = sj[q]; yn_[e] = yj[q]; } }
-                    ysn = t.lm_ys[jn];
+                    ysn = t.lm_ys[jn]; rysn = t.lm_rys[jn];
                 }
                 R pacc = 0.0;
 #pragma unroll
                 for (int e = 0; e < 8; e++) if (lane + 32 * e < n) pacc += sc_[e] * dreg[e];
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) pacc = pacc + __shfl_xor_sync(0xffffffffu, pacc, off);
-                const R a = pacc / ysj;
+                const R a = div_by_recip(pacc, ysj, rysj);
                 if (lane == 0) t.lm_alpha[j] = a;
                 const R na = -a;
 #pragma unroll
@@ -1659,7 +1679,7 @@ __device__ UALM_NOINLINE LbfgsOut lbfgs_optimize(Traj &t, const DevMap &map, con
                 if (i + 1 < bound) {
 #pragma unroll
                     for (int e = 0; e < 8; e++) { sc_[e] = sn_[e]; yc_[e] = yn_[e]; }
-                    j = jn; ysj = ysn;
+                    j = jn; ysj = ysn; rysj = rysn;
                 }
             }
             const R scl = ys / yy;
@@ -1670,26 +1690,26 @@ __device__ UALM_NOINLINE LbfgsOut lbfgs_optimize(Traj &t, const DevMap &map, con
             R alj = t.lm_alpha[j];
             for (int i = 0; i < bound; ++i) {
                 const int jn = (j + 1) % m;
-                R ysn = 0.0, aln = 0.0;
+                R ysn = 0.0, rysn = 0.0, aln = 0.0;
                 if (i + 1 < bound) {
                     const R *sj = t.lm_s + (size_t)jn * n, *yj = t.lm_y + (size_t)jn * n;
 #pragma unroll
                     for (int e = 0; e < 8; e++) { const int q = lane + 32 * e; if (q < n) { sn_[e] = sj[q]; yn_[e] = yj[q]; } }
-                    ysn = t.lm_ys[jn]; aln = t.lm_alpha[jn];
+                    ysn = t.lm_ys[jn]; rysn = t.lm_rys[jn]; aln = t.lm_alpha[jn];
                 }
                 R pacc = 0.0;
 #pragma unroll
                 for (int e = 0; e < 8; e++) if (lane + 32 * e < n) pacc += yc_[e] * dreg[e];
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) pacc = pacc + __shfl_xor_sync(0xffffffffu, pacc, off);
-                const R beta = pacc / ysj;
+                const R beta = div_by_recip(pacc, ysj, rysj);
                 const R cf = alj - beta;
 #pragma unroll
                 for (int e = 0; e < 8; e++) dreg[e] = dreg[e] + cf * sc_[e];
                 if (i + 1 < bound) {
 #pragma unroll
                     for (int e = 0; e < 8; e++) { sc_[e] = sn_[e]; yc_[e] = yn_[e]; }
-                    j = jn; ysj = ysn; alj = aln;
+                    j = jn; ysj = ysn; rysj = rysn; alj = aln;
                 }
             }
 #pragma unroll
@@ -1965,7 +1985,7 @@ __device__ UALM_NOINLINE void traj_setup(Traj &t, const BatchPtrs &bp, const Dev
     t.mu = bp.mu + 6 * pd->off_s; t.gx = bp.gx + 6 * pd->off_s;
     t.scale_cx = bp.scale_cx + 7 * pd->off_s;
     t.lm_s = bp.lm_s + pd->off_hist; t.lm_y = bp.lm_y + pd->off_hist;
-    t.lm_alpha = bp.lm_aux + (size_t)prob * 2 * p.mem_size; t.lm_ys = t.lm_alpha + p.mem_size;
+    t.lm_alpha = bp.lm_aux + (size_t)prob * 3 * p.mem_size; t.lm_ys = t.lm_alpha + p.mem_size; t.lm_rys = t.lm_ys + p.mem_size;
     t.scr = bp.scratch + pd->off_scr;
     {
         const long long rx = 6 * pd->N + 2 * UALM_FPAD, ry = 6 * pd->M + 2 * UALM_FPAD;
