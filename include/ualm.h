@@ -129,6 +129,13 @@ int ualm_time_penalty_kernel(ualm_ctx_t *ctx, int reps, float *ms_per_launch, do
  * dual-update, other, total).  enable != 0 switches collection on for the following solves. */
 int ualm_profile(ualm_ctx_t *ctx, int enable, long long *out16);
 
+/* UnevenMap construction on the GPU (UnevenMap::init preprocessing on the host, then constructMap + filter,
+ * uneven_map.cpp:317-398, 5-43, one thread per (x, y, yaw) cell).  Same arguments and the same arithmetic as ualm_map_build
+ * below (csrc/map_cell.h is compiled for both sides): the cells are bit-identical to the host builder's.  cells: host
+ * buffer [X][Y][Yaw][4] float; kernel_ms (optional): CUDA-event time of the cell kernel. */
+int ualm_map_build_device(ualm_ctx_t *ctx, const float *pts, int64_t npts, const ualm_map_geom_t *g, double ellipsoid_x,
+                          double ellipsoid_y, double ellipsoid_z, int iter_num, float *cells, float *kernel_ms);
+
 /* =====================  host-side input pipeline (no GPU needed)  ===================== */
 
 /* UnevenMap::init cloud preprocessing + constructMap (uneven_map.cpp:127-163, 317-398, 5-43) on host

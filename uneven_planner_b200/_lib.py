@@ -80,6 +80,8 @@ def lib():
         L.ualm_init_scaling_batch.argtypes = [vp, dp, dp]
         L.ualm_time_penalty_kernel.argtypes = [vp, C.c_int, C.POINTER(C.c_float), dp]
         L.ualm_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong)]
+        L.ualm_map_build_device.argtypes = [vp, fp, C.c_int64, C.POINTER(MapGeom), C.c_double, C.c_double, C.c_double, C.c_int, fp, C.POINTER(C.c_float)]
+        L.ualm_map_build_device.restype = C.c_int
         L.ualm_profile.restype = C.c_int
         for name in ("ualm_create", "ualm_destroy", "ualm_set_params", "ualm_set_map", "ualm_solve_batch",
                      "ualm_upload", "ualm_solve_resident", "ualm_sync", "ualm_download", "ualm_last_solve_ms",

@@ -134,6 +134,19 @@ class BatchALMTrajOpt:
         _check(self.L.ualm_time_penalty_kernel(self.h, reps, C.byref(ms), C.byref(by)))
         return ms.value, by.value
 
+    def build_map(self, pts, geom=None, ellipsoid=(0.2, 0.1, 0.1), iter_num=2, name="map"):
+        """UnevenMap grid from a point cloud on the GPU (ualm_map_build_device): (UnevenMapData, kernel ms)."""
+        from . import maps
+        geom = geom or _lib.map_geometry()
+        X, Y, W = geom.voxel_num
+        cells = np.zeros((X, Y, W, 4), np.float32)
+        pts = np.ascontiguousarray(pts, dtype=np.float32)
+        ms = C.c_float()
+        fp = C.POINTER(C.c_float)
+        _check(self.L.ualm_map_build_device(self.h, pts.ctypes.data_as(fp), pts.shape[0], C.byref(geom), ellipsoid[0], ellipsoid[1], ellipsoid[2],
+                                            iter_num, cells.ctypes.data_as(fp), C.byref(ms)))
+        return maps.UnevenMapData(geom, cells, name), ms.value
+
     PHASES = ("fill", "lu", "solve", "jerk", "tables", "samples", "accumulate", "combine", "adjoint", "tail", "twoloop", "linesearch",
               "scaling", "dual", "other", "total")
 

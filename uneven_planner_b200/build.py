@@ -17,7 +17,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 CU_SOURCES = ["ualm_api.cu"]
 CXX_SOURCES = ["host_tools.cpp"]
-HEADERS = ["ualm_kernels.cuh", "../../include/ualm_detmath.h"]
+HEADERS = ["ualm_kernels.cuh", "map_cell.h", "map_prep.h", "../../include/ualm_detmath.h"]
 
 
 
@@ -25,7 +25,7 @@ def _flags():
     # -fmad=false: no FMA contraction, so every double result is bit-identical to the CPU oracle's
     # (gcc -ffp-contract=off); fp64 division and sqrt are IEEE by default (no fast-math anywhere)
     return ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-            "-Xcompiler", "-fPIC,-O3", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+            "-Xcompiler", "-fPIC,-O3,-ffp-contract=off", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
             "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
 

@@ -3,13 +3,15 @@
 //  * ualm_map_geometry / ualm_map_build / ualm_map_occupancy : the UnevenMap the optimizer queries, built from
 //    a point cloud the way UnevenMap::init + constructMap + filter do it
 //    (uneven_map/src/uneven_map.cpp:96-114, 127-163, 169-179, 317-398, 5-43), with a bin-grid neighbour search
-//    on host threads instead of PCL kd-trees and a Jacobi 3x3 eigen-solver instead of Eigen::EigenSolver.
+//    on host threads instead of PCL kd-trees and a Jacobi 3x3 eigen-solver instead of Eigen::EigenSolver; the per-cell
+//    arithmetic lives in map_cell.h and is shared with the CUDA builder (ualm_map_build_device).
 //  * ualm_dubins_path : initial (x,y,yaw) polyline standing in for KinoAstar::plan (front_end/src/kino_astar.cpp:67-236);
 //    the reference's own one-shot expansion is this Dubins family (front_end/include/front_end/kino_astar.h:242-258).
 //  * ualm_resample_path : the PlanManager input contract (plan_manager/src/plan_manager.cpp:62-122).
 //
 // Written from the behaviour of those files; shares no code with them.
 #include "ualm.h"
+#include "map_prep.h"
 
 #include <algorithm>
 #include <atomic>
@@ -44,73 +46,11 @@ extern "C" void ualm_map_geometry(double sx, double sy, double xy_res, double ya
 }
 
 namespace {
-
 struct P3 { float x, y, z; };
-
-// symmetric 3x3 eigen-decomposition, cyclic Jacobi. a is destroyed; w = eigenvalues, v columns = eigenvectors
-static void jacobi3(double a[3][3], double w[3], double v[3][3])
-{
-    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) v[i][j] = (i == j);
-    for (int sweep = 0; sweep < 32; sweep++) {
-        double off = std::fabs(a[0][1]) + std::fabs(a[0][2]) + std::fabs(a[1][2]);
-        double diag = std::fabs(a[0][0]) + std::fabs(a[1][1]) + std::fabs(a[2][2]);
-        if (off <= 1e-300 || off <= 1e-18 * diag) break;
-        for (int p = 0; p < 2; p++)
-            for (int q = p + 1; q < 3; q++) {
-                if (a[p][q] == 0.0) continue;
-                double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
-                double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
-                double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
-                for (int k = 0; k < 3; k++) { // A <- A J
-                    double akp = a[k][p], akq = a[k][q];
-                    a[k][p] = c * akp - s * akq;
-                    a[k][q] = s * akp + c * akq;
-                }
-                for (int k = 0; k < 3; k++) { // A <- J^T A
-                    double apk = a[p][k], aqk = a[q][k];
-                    a[p][k] = c * apk - s * aqk;
-                    a[q][k] = s * apk + c * aqk;
-                }
-                for (int k = 0; k < 3; k++) {
-                    double vkp = v[k][p], vkq = v[k][q];
-                    v[k][p] = c * vkp - s * vkq;
-                    v[k][q] = s * vkp + c * vkq;
-                }
-            }
-    }
-    for (int i = 0; i < 3; i++) w[i] = a[i][i];
-}
-
-struct BinGrid {
-    double x0, y0, inv;
-    int nx, ny;
-    std::vector<int> start; // nx*ny+1
-    std::vector<P3> pts;    // sorted by bin
-    void build(const std::vector<P3> &in, double bin)
-    {
-        double xmin = 1e30, ymin = 1e30, xmax = -1e30, ymax = -1e30;
-        for (auto &p : in) { xmin = std::min<double>(xmin, p.x); xmax = std::max<double>(xmax, p.x); ymin = std::min<double>(ymin, p.y); ymax = std::max<double>(ymax, p.y); }
-        if (in.empty()) { xmin = ymin = 0; xmax = ymax = 1; }
-        x0 = xmin; y0 = ymin; inv = 1.0 / bin;
-        nx = (int)((xmax - xmin) * inv) + 1; ny = (int)((ymax - ymin) * inv) + 1;
-        start.assign((size_t)nx * ny + 1, 0);
-        auto key = [&](const P3 &p) { int bx = std::min(nx - 1, std::max(0, (int)((p.x - x0) * inv))); int by = std::min(ny - 1, std::max(0, (int)((p.y - y0) * inv))); return bx * ny + by; };
-        for (auto &p : in) start[key(p) + 1]++;
-        for (size_t i = 1; i < start.size(); i++) start[i] += start[i - 1];
-        pts.resize(in.size());
-        std::vector<int> fill(start.begin(), start.end() - 1);
-        for (auto &p : in) pts[fill[key(p)]++] = p;
-    }
-    inline int bx_of(double x) const { return (int)std::floor((x - x0) * inv); }
-    inline int by_of(double y) const { return (int)std::floor((y - y0) * inv); }
-};
-
 } // namespace
 
-extern "C" int ualm_map_build(const float *pin, int64_t npts, const ualm_map_geom_t *g, double ex, double ey,
-                              double ez, int iter_num, int nthreads, float *cells)
+void ualm_map_preprocess(const float *pin, int64_t npts, double ex, double ey, double ez, UalmMapHostPrep &out)
 {
-    if (!pin || !g || !cells || npts < 0) return UALM_EINVAL;
     // ---- CropBox [-10,10]x[-10,10]x[-0.01,5]  (uneven_map.cpp:133-137)
     std::vector<P3> crop;
     crop.reserve((size_t)npts);
@@ -145,104 +85,42 @@ extern "C" int ualm_map_build(const float *pin, int64_t npts, const ualm_map_geo
             i = j;
         }
     }
-    BinGrid grid;
-    const double box_r = std::max(std::max(ex, ey), ez); // uneven_map.cpp:319
-    grid.build(cloud, box_r);
-    const double einv[3] = {1.0 / ex, 1.0 / ey, 1.0 / ez};
+    // ---- uniform XY bin grid, bin = the search radius of constructMap (uneven_map.cpp:319)
+    const double bin = std::max(std::max(ex, ey), ez);
+    double xmin = 1e30, ymin = 1e30, xmax = -1e30, ymax = -1e30;
+    for (auto &p : cloud) { xmin = std::min<double>(xmin, p.x); xmax = std::max<double>(xmax, p.x); ymin = std::min<double>(ymin, p.y); ymax = std::max<double>(ymax, p.y); }
+    if (cloud.empty()) { xmin = ymin = 0; xmax = ymax = 1; }
+    out.box_r = bin; out.x0 = xmin; out.y0 = ymin; out.inv = 1.0 / bin;
+    out.nx = (int)((xmax - xmin) * out.inv) + 1; out.ny = (int)((ymax - ymin) * out.inv) + 1;
+    out.start.assign((size_t)out.nx * out.ny + 1, 0);
+    auto key = [&](const P3 &p) {
+        int bx = std::min(out.nx - 1, std::max(0, (int)((p.x - out.x0) * out.inv)));
+        int by = std::min(out.ny - 1, std::max(0, (int)((p.y - out.y0) * out.inv)));
+        return bx * out.ny + by;
+    };
+    for (auto &p : cloud) out.start[key(p) + 1]++;
+    for (size_t i = 1; i < out.start.size(); i++) out.start[i] += out.start[i - 1];
+    out.pts.resize(3 * cloud.size());
+    std::vector<int> fill(out.start.begin(), out.start.end() - 1);
+    for (auto &p : cloud) { const int q = fill[key(p)]++; out.pts[3 * q] = p.x; out.pts[3 * q + 1] = p.y; out.pts[3 * q + 2] = p.z; }
+}
+
+extern "C" int ualm_map_build(const float *pin, int64_t npts, const ualm_map_geom_t *g, double ex, double ey,
+                              double ez, int iter_num, int nthreads, float *cells)
+{
+    if (!pin || !g || !cells || npts < 0) return UALM_EINVAL;
+    UalmMapHostPrep prep;
+    ualm_map_preprocess(pin, npts, ex, ey, ez, prep);
+    const UalmMapPrep view = prep.view(ex, ey, ez, iter_num);
     const int X = g->voxel_num[0], Y = g->voxel_num[1], W = g->voxel_num[2];
     if (nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
-
     std::atomic<int> next_x(0);
     auto worker = [&]() {
-        std::vector<const P3 *> sel;
         while (true) {
-            int x = next_x.fetch_add(1);
+            const int x = next_x.fetch_add(1);
             if (x >= X) break;
             for (int y = 0; y < Y; y++)
-                for (int w = 0; w < W; w++) {
-                    double z = 0.0, sigma = 0.0, zbx = 0.0, zby = 0.0, cc = 1.0; // RXS2(), c_buffer = 1 (uneven_map.cpp:118-119)
-                    const double px = (x + 0.5) * g->xy_resolution + g->origin[0]; // indexToPos
-                    const double py = (y + 0.5) * g->xy_resolution + g->origin[1];
-                    const double pyaw = (w + 0.5) * g->yaw_resolution + g->origin[2];
-                    for (int iter = 0; iter < iter_num; iter++) { // uneven_map.cpp:326-398
-                        const double xyaw[3] = {std::cos(pyaw), std::sin(pyaw), 0.0};
-                        const double zb[3] = {zbx, zby, cc};
-                        double yb[3] = {zb[1] * xyaw[2] - zb[2] * xyaw[1], zb[2] * xyaw[0] - zb[0] * xyaw[2], zb[0] * xyaw[1] - zb[1] * xyaw[0]};
-                        double nyb = std::sqrt(yb[0] * yb[0] + yb[1] * yb[1] + yb[2] * yb[2]);
-                        if (nyb > 0) { yb[0] /= nyb; yb[1] /= nyb; yb[2] /= nyb; }
-                        const double xb[3] = {yb[1] * zb[2] - yb[2] * zb[1], yb[2] * zb[0] - yb[0] * zb[2], yb[0] * zb[1] - yb[1] * zb[0]};
-                        double wp[3] = {px + xb[0] * 0.12, py + xb[1] * 0.12, z};
-                        if (iter == 0 && !cloud.empty()) { // nearest cloud point in the XY plane (uneven_map.cpp:346-355)
-                            const float qx = (float)wp[0], qy = (float)wp[1];
-                            int bx = std::min(grid.nx - 1, std::max(0, grid.bx_of(qx))), by = std::min(grid.ny - 1, std::max(0, grid.by_of(qy)));
-                            float best = 1e30f, bestz = 0;
-                            for (int ring = 0; ring < std::max(grid.nx, grid.ny); ring++) {
-                                for (int ix = bx - ring; ix <= bx + ring; ix++) {
-                                    if (ix < 0 || ix >= grid.nx) continue;
-                                    for (int iy = by - ring; iy <= by + ring; iy++) {
-                                        if (iy < 0 || iy >= grid.ny) continue;
-                                        if (std::max(std::abs(ix - bx), std::abs(iy - by)) != ring) continue;
-                                        for (int q = grid.start[ix * grid.ny + iy]; q < grid.start[ix * grid.ny + iy + 1]; q++) {
-                                            const P3 &p = grid.pts[q];
-                                            float d = (p.x - qx) * (p.x - qx) + (p.y - qy) * (p.y - qy);
-                                            if (d < best) { best = d; bestz = p.z; }
-                                        }
-                                    }
-                                }
-                                // every unvisited point is at least ring*bin away (query clamped into the grid)
-                                double reach = (double)ring * box_r;
-                                if (best < 1e29f && (double)best <= reach * reach) break;
-                            }
-                            if (best < 1e29f) wp[2] = bestz;
-                        }
-                        // points inside the robot-frame ellipsoid (uneven_map.cpp:357-378)
-                        sel.clear();
-                        {
-                            int bx0 = grid.bx_of(wp[0] - box_r), bx1 = grid.bx_of(wp[0] + box_r);
-                            int by0 = grid.by_of(wp[1] - box_r), by1 = grid.by_of(wp[1] + box_r);
-                            for (int ix = std::max(0, bx0); ix <= std::min(grid.nx - 1, bx1); ix++)
-                                for (int iy = std::max(0, by0); iy <= std::min(grid.ny - 1, by1); iy++)
-                                    for (int q = grid.start[ix * grid.ny + iy]; q < grid.start[ix * grid.ny + iy + 1]; q++) {
-                                        const P3 &p = grid.pts[q];
-                                        const double d[3] = {p.x - wp[0], p.y - wp[1], p.z - wp[2]};
-                                        if (d[0] * d[0] + d[1] * d[1] + d[2] * d[2] > box_r * box_r * 1.0001) continue;
-                                        const double r0 = (xb[0] * d[0] + xb[1] * d[1] + xb[2] * d[2]) * einv[0];
-                                        const double r1 = (yb[0] * d[0] + yb[1] * d[1] + yb[2] * d[2]) * einv[1];
-                                        const double r2 = (zb[0] * d[0] + zb[1] * d[1] + zb[2] * d[2]) * einv[2];
-                                        if (r0 * r0 + r1 * r1 + r2 * r2 < 1.0) sel.push_back(&p);
-                                    }
-                        }
-                        if (sel.empty()) { // uneven_map.cpp:379-386
-                            z = wp[2]; sigma = 0.0; zbx = 0.0; zby = 0.0; cc = 1.0;
-                        } else { // UnevenMap::filter (uneven_map.cpp:5-43)
-                            double m[3] = {0, 0, 0};
-                            for (auto *p : sel) { m[0] += p->x; m[1] += p->y; m[2] += p->z; }
-                            const double n = (double)sel.size();
-                            m[0] /= n; m[1] /= n; m[2] /= n;
-                            double cov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-                            for (auto *p : sel) {
-                                const double v[3] = {p->x - m[0], p->y - m[1], p->z - m[2]};
-                                for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) cov[a][b] += v[a] * v[b];
-                            }
-                            for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) cov[a][b] /= n;
-                            double wv[3], ev[3][3];
-                            jacobi3(cov, wv, ev);
-                            int k = 0;
-                            if (wv[1] < wv[k]) k = 1;
-                            if (wv[2] < wv[k]) k = 2;
-                            double nn[3] = {ev[0][k], ev[1][k], ev[2][k]};
-                            double nl = std::sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
-                            nn[0] /= nl; nn[1] /= nl; nn[2] /= nl;
-                            if (nn[2] < 0.0) { nn[0] = -nn[0]; nn[1] = -nn[1]; nn[2] = -nn[2]; }
-                            double sg = wv[k] / (wv[0] + wv[1] + wv[2]) * 3.0;
-                            if (std::isnan(sg)) { sg = 1.0; nn[0] = 1.0; nn[1] = 0.0; nn[2] = 0.0; }
-                            z = m[2]; sigma = sg; zbx = nn[0]; zby = nn[1];
-                            cc = std::sqrt(1.0 - zbx * zbx - zby * zby);
-                        }
-                    }
-                    float *o = cells + 4 * ((size_t)x * Y * W + (size_t)y * W + w);
-                    o[0] = (float)z; o[1] = (float)sigma; o[2] = (float)zbx; o[3] = (float)zby;
-                }
+                for (int w = 0; w < W; w++) ualm_map_cell(view, *g, x, y, w, cells + 4 * ((size_t)x * Y * W + (size_t)y * W + w));   // map_cell.h
         }
     };
     std::vector<std::thread> th;

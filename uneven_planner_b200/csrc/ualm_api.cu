@@ -3,6 +3,7 @@
 // per-trajectory kernels of ualm_kernels.cuh.  There is NO CPU fallback: every compute entry point needs a CUDA
 // device and returns UALM_ENOCUDA otherwise.
 #include "ualm_kernels.cuh"
+#include "map_prep.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -219,7 +220,6 @@ extern "C" int ualm_upload(ualm_ctx_t *c, int B, const int32_t *N, const int32_t
         int dev_sms = 0;
         CK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, c->device));
         const int RINGD = 2 * UALM_RINGB * 6 * UALM_FW;
-        const long long base_ctas = (B + 3) / 4;
         int occ0 = 1;   // CTAs per SM the register file allows (shared memory is checked per class below)
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, solve_kernel, UALM_THREADS * UALM_WPB, 16 * 1024));
         if (getenv("UALM_DEBUG")) {
@@ -229,7 +229,6 @@ extern "C" int ualm_upload(ualm_ctx_t *c, int B, const int32_t *N, const int32_t
                     fa.sharedSizeBytes, occ0);
         }
         const long long W = 4LL * occ0 * dev_sms;   // warp slots on the device
-        long long cap = W / 4;
         std::vector<ualm_ctx::GClass> best;
         for (int attempt = 0; attempt < 32; attempt++) {
             // Policy (measured on B200, tools/gpu_policy_dev.py): helpers shorten the latency of a trajectory without adding to the
@@ -538,5 +537,53 @@ extern "C" int ualm_profile(ualm_ctx_t *c, int enable, long long *out16)
         }
     }
     c->profile = enable != 0;
+    return UALM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// UnevenMap construction on the device.  HBM-bound gather: one thread per cell, yaw fastest so that the 64
+// threads of a CTA share (x, y) and read the same few cloud bins through L1.
+// ---------------------------------------------------------------------------------------------
+namespace ualm {
+__global__ void __launch_bounds__(64) map_build_kernel(UalmMapPrep prep, ualm_map_geom_t geom, float4 *cells)
+{
+    const int W = geom.voxel_num[2], Y = geom.voxel_num[1];
+    const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)geom.voxel_num[0] * Y * W;
+    if (cell >= total) return;
+    const int w = (int)(cell % W), y = (int)((cell / W) % Y), x = (int)(cell / ((long long)W * Y));
+    float o[4];
+    ualm_map_cell(prep, geom, x, y, w, o);
+    cells[cell] = make_float4(o[0], o[1], o[2], o[3]);
+}
+} // namespace ualm
+
+extern "C" int ualm_map_build_device(ualm_ctx_t *c, const float *pin, int64_t npts, const ualm_map_geom_t *g, double ex, double ey, double ez,
+                                     int iter_num, float *cells, float *kernel_ms)
+{
+    if (!c || !pin || !g || !cells || npts < 0) return fail(UALM_EINVAL, "null argument");
+    CK(cudaSetDevice(c->device));
+    UalmMapHostPrep prep;
+    ualm_map_preprocess(pin, npts, ex, ey, ez, prep);
+    UalmMapPrep view = prep.view(ex, ey, ez, iter_num);
+    const long long total = (long long)g->voxel_num[0] * g->voxel_num[1] * g->voxel_num[2];
+    float *d_pts = nullptr; int *d_start = nullptr; float4 *d_cells = nullptr;
+    cudaEvent_t e0, e1;
+    CK(cudaMalloc(&d_pts, sizeof(float) * std::max<size_t>(prep.pts.size(), 3)));
+    CK(cudaMalloc(&d_start, sizeof(int) * prep.start.size()));
+    CK(cudaMalloc(&d_cells, sizeof(float4) * total));
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    if (!prep.pts.empty()) CK(cudaMemcpyAsync(d_pts, prep.pts.data(), sizeof(float) * prep.pts.size(), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_start, prep.start.data(), sizeof(int) * prep.start.size(), cudaMemcpyHostToDevice, c->stream));
+    view.pts = d_pts; view.start = d_start;
+    CK(cudaEventRecord(e0, c->stream));
+    map_build_kernel<<<(unsigned)((total + 63) / 64), 64, 0, c->stream>>>(view, *g, d_cells);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e1, c->stream));
+    CK(cudaMemcpyAsync(cells, d_cells, sizeof(float4) * total, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_pts); cudaFree(d_start); cudaFree(d_cells);
     return UALM_OK;
 }

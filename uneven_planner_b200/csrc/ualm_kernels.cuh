@@ -2009,7 +2009,7 @@ __device__ UALM_NOINLINE void traj_setup(Traj &t, const BatchPtrs &bp, const Dev
 }
 
 // =============================================================================================
-// kernels (one warp = one CTA = one trajectory)
+// kernels (CTA = 4 warp slots; solve_kernel: warp groups per trajectory, the test kernels: one warp per trajectory)
 // =============================================================================================
 
 // helper warps of a group: execute the parallel phases the leader posts, nothing else
