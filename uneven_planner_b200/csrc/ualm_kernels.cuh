@@ -319,6 +319,18 @@ __device__ UALM_NOINLINE double2 dev_sincos(R x)
 }
 __device__ UALM_NOINLINE R dev_atan2(R y, R x) { return ualm_atan2(y, x); }
 
+// IEEE a / b for callers whose numerator is often exactly zero.  The inline fast path of the fp64 division hands a zero (or
+// denormal) quotient to an out-of-line slow path, and it does so for the whole warp when a single lane needs it; here a zero
+// numerator is replaced by 1 for the division and the signed zero (NaN for b = 0 or NaN) is put back afterwards.
+__device__ __forceinline__ R div_nz(R a, R b)
+{
+    const bool z = (a == 0.0);
+    const R q = (z ? 1.0 : a) / b;
+    const long long sz = (__double_as_longlong(a) ^ __double_as_longlong(b)) & (long long)0x8000000000000000ull;
+    const R zq = (b != b || b == 0.0) ? __longlong_as_double(0x7ff8000000000000ll) : __longlong_as_double(sz);
+    return z ? zq : q;
+}
+
 // a / b given rb = RN(1/b): q0 = a*rb followed by two residual corrections with FMA returns the correctly rounded quotient
 // (Markstein).  Checked bit for bit against IEEE division on 1.8e10 operand pairs on B200 (tools/microbench/fastdiv.cu).
 // Out-of-range quotients and the flagged all-ones divisor (rb = NaN) fall back to the IEEE division.
@@ -330,7 +342,8 @@ __device__ __forceinline__ R div_by_recip(R a, R b, R rb)
     e = fma(-q, b, a);
     q = fma(e, rb, q);
     const R aq = fabs(q);
-    if (!(aq < 1.0e290) || (aq < 1.0e-290 && a != 0.0)) q = a / b;
+    // (the compiler evaluates this division speculatively, so it must stay on the fast path for a zero numerator: div_nz)
+    if (!(aq < 1.0e290) || (aq < 1.0e-290 && a != 0.0)) q = div_nz(a, b);
     return q;
 }
 // the same quotient without the fallback: `bad` collects the cases that need the IEEE division, so that a chain of quotients
@@ -348,18 +361,6 @@ __device__ __forceinline__ R div_by_recip_flag(R a, R b, R rb, bool &bad)
     const R aq = fabs(q1);
     bad = bad || !(q2 == q1) || !(aq < 1.0e290) || (aq < 1.0e-290 && a != 0.0);
     return q1;
-}
-
-// IEEE a / b for callers whose numerator is often exactly zero.  The inline fast path of the fp64 division hands a zero (or
-// denormal) quotient to an out-of-line slow path, and it does so for the whole warp when a single lane needs it; here a zero
-// numerator is replaced by 1 for the division and the signed zero (NaN for b = 0 or NaN) is put back afterwards.
-__device__ __forceinline__ R div_nz(R a, R b)
-{
-    const bool z = (a == 0.0);
-    const R q = (z ? 1.0 : a) / b;
-    const long long sz = (__double_as_longlong(a) ^ __double_as_longlong(b)) & (long long)0x8000000000000000ull;
-    const R zq = (b != b || b == 0.0) ? __longlong_as_double(0x7ff8000000000000ll) : __longlong_as_double(sz);
-    return z ? zq : q;
 }
 
 // ---------------------------------------------------------------------------------------------
