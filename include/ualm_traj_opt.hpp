@@ -51,6 +51,64 @@ struct SE2Trajectory {
     }
 };
 
+// PolyTrajectory::locatePieceIdx + getValue (se2traj.hpp:343-367): piece containing time t (t is reduced to the piece-local time)
+template <int Dim>
+inline int locatePieceIdx(const std::vector<Piece<Dim>> &pieces, double &t)
+{
+    const int N = (int)pieces.size();
+    int idx;
+    double dur;
+    for (idx = 0; idx < N && t > (dur = pieces[idx].getDuration()); idx++) t -= dur;
+    if (idx == N) {
+        idx--;
+        t += pieces[idx].getDuration();
+    }
+    return idx;
+}
+template <int Dim>
+inline void getValue(const std::vector<Piece<Dim>> &pieces, double t, double *out)
+{
+    const int idx = locatePieceIdx(pieces, t);
+    pieces[idx].getValue(t, out);
+}
+template <int Dim>
+inline double getTotalDuration(const std::vector<Piece<Dim>> &pieces)   // PolyTrajectory::getTotalDuration, se2traj.hpp:291-300
+{
+    double total = 0.0;
+    for (const auto &p : pieces) total += p.getDuration();
+    return total;
+}
+
+// What PlanManager publishes to the MPC (mpc_controller/msg/SE2Traj.msg; plan_manager.cpp:151-185): the piece start points,
+// the end point and the piece durations of both splines; the boundary velocity / acceleration fields are zero in the reference.
+struct SE2TrajMsg {
+    std::vector<double> pos_pts;      // (N + 1) x 2, row-major: pos_traj[i].getValue(0), then pos_traj.getValue(total)
+    std::vector<double> posT_pts;     // N
+    std::vector<double> angle_pts;    // M + 1
+    std::vector<double> angleT_pts;   // M
+    double init_v[3] = {0, 0, 0}, init_a[3] = {0, 0, 0};
+};
+inline SE2TrajMsg toSE2TrajMsg(const SE2Trajectory &tr)
+{
+    SE2TrajMsg m;
+    double p[2], a[1];
+    for (const auto &pc : tr.pos_traj) {
+        pc.getValue(0.0, p);
+        m.pos_pts.push_back(p[0]); m.pos_pts.push_back(p[1]);
+        m.posT_pts.push_back(pc.getDuration());
+    }
+    getValue(tr.pos_traj, getTotalDuration(tr.pos_traj), p);
+    m.pos_pts.push_back(p[0]); m.pos_pts.push_back(p[1]);
+    for (const auto &pc : tr.yaw_traj) {
+        pc.getValue(0.0, a);
+        m.angle_pts.push_back(a[0]);
+        m.angleT_pts.push_back(pc.getDuration());
+    }
+    getValue(tr.yaw_traj, getTotalDuration(tr.yaw_traj), a);
+    m.angle_pts.push_back(a[0]);
+    return m;
+}
+
 // c_xy: 6N x 2 column-major, c_yaw: 6M (solver order, low -> high power), T_total = sum of piece durations
 inline SE2Trajectory make_traj(int N, int M, const double *c_xy, const double *c_yaw, double T_total)
 {

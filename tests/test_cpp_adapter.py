@@ -30,6 +30,17 @@ def _write_case(path, m, pb, i):
         f.write(pb.inner_yaw[oyaw[i]:oyaw[i + 1]].astype(np.float64).tobytes())
 
 
+def test_result_containers_and_mpc_message_export(built, tmp_path):
+    """make_traj / Piece::getValue / locatePieceIdx / toSE2TrajMsg of include/ualm_traj_opt.hpp against hand-computed values
+    (se2traj.hpp:106-118, 343-367, 682-695; plan_manager.cpp:151-185) -- host only."""
+    exe = str(tmp_path / "msg_driver")
+    lib = os.path.join(ROOT, "uneven_planner_b200")
+    subprocess.run(["g++", "-O2", "-std=c++14", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "msg_driver.cpp"),
+                    "-o", exe, "-L", lib, "-lualm", "-Wl,-rpath," + lib], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "OK", r.stdout
+
+
 def test_adapter_compiles_and_fails_loudly_without_gpu(driver, bumps_map, tmp_path):
     import torch
     from uneven_planner_b200 import problems
