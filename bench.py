@@ -222,6 +222,18 @@ def main():
     solve_ms, launches = opt.last_solve_ms()                       # CUDA events around the last solve kernel on its stream
     res, cxy, cyaw = opt.download()
     conv_local = sum(1 for r in res if r.ret_code == 0)
+    # independent quality check of the solved batch (outside the timed region): the reference's post-solve scan
+    # (getMaxVxAxAyCurAttSig + getNonHolError, 0.01 s sampling) on the GPU, rank-local
+    feas = opt.feasibility(0.01)
+    okc = np.array([r.ret_code == 0 for r in res])
+    tol = 1.05
+    within = (np.abs(feas[:, 0]) <= params.max_vel * tol) & (np.abs(feas[:, 1]) <= params.max_acc_lon * tol) & \
+             (np.abs(feas[:, 2]) <= params.max_acc_lat * tol) & (np.abs(feas[:, 3]) <= params.max_kap * tol) & \
+             (-feas[:, 4] >= params.min_cxi / tol) & (feas[:, 5] <= params.max_sig * tol)
+    quality = {"converged": int(okc.sum()), "converged_and_within_limits": int((okc & within).sum()),
+               "limits": "max |vx|, |ax|, |ay|, |curvature|, sigma <= 1.05 x limit and min cos(xi) >= limit / 1.05 over 0.01 s samples "
+                         "(ualm_feasibility_batch; rank 0's shard)",
+               "median_nonholonomic_error_per_sample": float(np.median(feas[okc, 6] / np.maximum(feas[okc, 7], 1.0))) if okc.any() else None}
     full_h = full.cpu().numpy()
     conv_total = int((full_h[:, 0] == 0).sum()) if world > 1 else conv_local
     value = conv_total * args.steps / (ms * 1e-3)
@@ -320,7 +332,7 @@ def main():
                            "l2": "per-step working set (L-BFGS history + sample scratch, %.0f MB) exceeds the 126 MB L2; the 41 MB map is reused within a step" % ((lb_b and (8.0 * 2 * params.mem_size * float(pb.nvar().sum())) / 1e6))},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
                 "gpu_launches": int((launches + 1) * args.steps),
-                "clocks": clocks, "roofline": roof, "roofline_penalty": roof_pen, "cpu_baseline": cpu, "large_batch": big,
+                "clocks": clocks, "roofline": roof, "roofline_penalty": roof_pen, "cpu_baseline": cpu, "large_batch": big, "quality": quality,
                 "work": {"evals_per_step": int(sum(r.n_evals for r in res)), "lbfgs_iters_per_step": int(sum(r.n_lbfgs_iters for r in res)), "rank0_batch": pb.B}}
         print(json.dumps(line))
     opt.close()

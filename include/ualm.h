@@ -129,6 +129,12 @@ int ualm_time_penalty_kernel(ualm_ctx_t *ctx, int reps, float *ms_per_launch, do
  * dual-update, other, total).  enable != 0 switches collection on for the following solves. */
 int ualm_profile(ualm_ctx_t *ctx, int enable, long long *out16);
 
+/* Post-solve quality scan of the solved resident batch: ALMTrajOpt::getMaxVxAxAyCurAttSig
+ * (alm_traj_opt.h:170-229) and SE2Trajectory::getNonHolError (se2traj.hpp:551-561), sampled every dt (0.01 in the
+ * reference).  out10[10 * b + ...] = {max_vx, max_ax, max_ay, max_cur, max_att (= -min cos xi), max_sig, nonhol_error,
+ * number of samples, T_xy piece duration, T_yaw piece duration}. */
+int ualm_feasibility_batch(ualm_ctx_t *ctx, double dt, double *out10);
+
 /* UnevenMap construction on the GPU (UnevenMap::init preprocessing on the host, then constructMap + filter,
  * uneven_map.cpp:317-398, 5-43, one thread per (x, y, yaw) cell).  Same arguments and the same arithmetic as ualm_map_build
  * below (csrc/map_cell.h is compiled for both sides): the cells are bit-identical to the host builder's.  cells: host

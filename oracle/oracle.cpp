@@ -1280,6 +1280,93 @@ int orc_init_scaling(const orc_params_t *p, const orc_map_t *map, const orc_prob
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Post-solve scan: PolyTrajectory::locatePieceIdx / Piece::getValue, getDotValue, getDDotValue (se2traj.hpp:343-361, 106-150;
+ * the reference stores the coefficients highest power first, so its loops i = order..0 walk this file's c[0], c[1], ...),
+ * SE2Trajectory accessors (se2traj.hpp:420-481, 551-561), ALMTrajOpt::getMaxVxAxAyCurAttSig (alm_traj_opt.h:170-229).
+ * getTerrainVariables (uneven_map.h:221-256) evaluates the same value expressions as getAllWithGrad (:318-348).
+ * ---------------------------------------------------------------------------------------- */
+namespace {
+struct PieceRef { const double *c; int stride; };   /* c[k * 1 + d * stride]: coefficient k (low -> high) of dimension d */
+inline int locate_piece(int P, double dur, double &t) /* se2traj.hpp:343-361, uniform durations */
+{
+    int idx;
+    for (idx = 0; idx < P && t > dur; idx++) t -= dur;
+    if (idx == P) { idx--; t += dur; }
+    return idx;
+}
+inline double piece_value(const double *c, double t) /* se2traj.hpp:106-118 */
+{
+    double v = 0.0, tn = 1.0;
+    for (int k = 0; k <= 5; k++) { v += tn * c[k]; tn *= t; }
+    return v;
+}
+inline double piece_dot(const double *c, double t) /* se2traj.hpp:120-134 */
+{
+    double v = 0.0, tn = 1.0;
+    int n = 1;
+    for (int k = 1; k <= 5; k++) { v += n * tn * c[k]; tn *= t; n++; }
+    return v;
+}
+inline double piece_ddot(const double *c, double t) /* se2traj.hpp:136-150 */
+{
+    double v = 0.0, tn = 1.0;
+    int m = 1, n = 2;
+    for (int k = 2; k <= 5; k++) { v += m * n * tn * c[k]; tn *= t; m++; n++; }
+    return v;
+}
+} // namespace
+
+void orc_feasibility(const orc_map_t *map, double gravity, int N, int M, const double *c_xy, const double *c_yaw, double T_xy,
+                     double T_yaw, double dt, double *out)
+{
+    MapQ<double> mq(*map);
+    const int nx = 6 * N;
+    double tot_xy = 0.0, tot_yaw = 0.0; /* PolyTrajectory::getTotalDuration, se2traj.hpp:291-300 */
+    for (int i = 0; i < N; i++) tot_xy += T_xy;
+    for (int i = 0; i < M; i++) tot_yaw += T_yaw;
+    const double total = std::min(tot_xy, tot_yaw); /* se2traj.hpp:415-418 */
+    double max_ax = 0.0, max_ay = 0.0, max_vx = 0.0, max_cur = 0.0, max_att = -1.0, max_sig = 0.0, err = 0.0;
+    long count = 0;
+    for (double t = 0.0; t < total; t += dt) {
+        double tl = t;
+        const int ip = locate_piece(N, T_xy, tl);
+        const double *cx = c_xy + 6 * ip, *cy = c_xy + nx + 6 * ip;
+        const double px = piece_value(cx, tl), py = piece_value(cy, tl);
+        const double vxw = piece_dot(cx, tl), vyw = piece_dot(cy, tl);
+        const double axw = piece_ddot(cx, tl), ayw = piece_ddot(cy, tl);
+        double ty = t;
+        const int iy = locate_piece(M, T_yaw, ty);
+        const double *cw = c_yaw + 6 * iy;
+        const double yaw = piece_value(cw, ty), dyaw = piece_dot(cw, ty);
+        double se2[3] = {px, py, yaw};
+        while (se2[2] < -M_PI) se2[2] += 2 * M_PI; /* getNormSE2Pos, se2traj.hpp:433-443 */
+        while (se2[2] > M_PI) se2[2] -= 2 * M_PI;
+        double tv[7], tg[7][3];
+        mq.getAllWithGrad(se2, tv, tg);
+        const double cy_ = Mth<double>::cos(yaw), sy_ = Mth<double>::sin(yaw);
+        const double vnorm = std::sqrt(vxw * vxw + vyw * vyw);       /* getVelNorm */
+        const double lon = axw * cy_ + ayw * sy_;                    /* getLonAcc */
+        const double lat = -axw * sy_ + ayw * cy_;                   /* getLatAcc */
+        const double vx = vnorm * tv[0];
+        const double ax = lon * tv[0] + gravity * tv[1];
+        const double ay = lat * tv[2] + gravity * tv[3];
+        const double wz = dyaw * tv[5];
+        const double cur = wz / std::sqrt(vx * vx + delta_sigl);
+        const double att = -1.0 / tv[5];
+        if (std::fabs(max_ax) < std::fabs(ax)) max_ax = ax;
+        if (std::fabs(max_ay) < std::fabs(ay)) max_ay = ay;
+        if (std::fabs(max_vx) < std::fabs(vx)) max_vx = vx;
+        if (std::fabs(max_cur) < std::fabs(cur)) max_cur = cur;
+        if (max_att < att) max_att = att;
+        if (max_sig < tv[6]) max_sig = tv[6];
+        err += std::fabs(vxw * sy_ + vyw * (-cy_));                  /* getNonHolError */
+        count++;
+    }
+    out[0] = max_vx; out[1] = max_ax; out[2] = max_ay; out[3] = max_cur; out[4] = max_att; out[5] = max_sig; out[6] = err;
+    out[7] = (double)count;
+}
+
 void orc_map_query(const orc_map_t *map, const double pos[3], double *values, double *grads)
 {
     MapQ<double> mq(*map);

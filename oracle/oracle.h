@@ -117,6 +117,13 @@ int orc_minco_grad_ct_to_qt(int Dim, int N, const double *inPs, const double *ts
 int orc_lbfgs_rosenbrock(int n, double *x, double *f, int mem_size, double g_epsilon, int past,
                          double delta, int *iters);
 
+/* Post-solve quality scan: ALMTrajOpt::getMaxVxAxAyCurAttSig (alm_traj_opt.h:170-229) and
+ * SE2Trajectory::getNonHolError (se2traj.hpp:551-561) of the trajectory {c_xy (6N x 2 col-major), c_yaw (6M), uniform piece
+ * durations T_xy, T_yaw}, sampled every dt (0.01 in the reference).
+ * out[8] = {max_vx, max_ax, max_ay, max_cur, max_att, max_sig, nonhol_error, number of samples}. */
+void orc_feasibility(const orc_map_t *map, double gravity, int N, int M, const double *c_xy, const double *c_yaw,
+                     double T_xy, double T_yaw, double dt, double *out);
+
 double orc_expC2(double tau);
 double orc_logC2(double T);
 double orc_dTdtau(double tau);

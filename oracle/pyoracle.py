@@ -183,3 +183,15 @@ def init_scaling(params, omap, pb, i, x0=None):
     sfx = np.zeros(1); scx = np.zeros(7 * S)
     lib().orc_init_scaling(C.byref(params), C.byref(omap.c), C.byref(pr), P(x0), P(sfx), P(scx))
     return float(sfx[0]), scx
+
+
+def feasibility(omap, gravity, N, M, c_xy, c_yaw, T_xy, T_yaw, dt=0.01):
+    """orc_feasibility: [max_vx, max_ax, max_ay, max_cur, max_att, max_sig, nonhol_error, samples]."""
+    out = np.zeros(8)
+    c_xy = np.ascontiguousarray(c_xy, dtype=np.float64); c_yaw = np.ascontiguousarray(c_yaw, dtype=np.float64)
+    f = lib().orc_feasibility
+    f.restype = None
+    f.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, dp, dp, C.c_double, C.c_double, C.c_double, dp]
+    f(C.addressof(omap.c), float(gravity), int(N), int(M), c_xy.ctypes.data_as(dp), c_yaw.ctypes.data_as(dp), float(T_xy), float(T_yaw), float(dt),
+      out.ctypes.data_as(dp))
+    return out

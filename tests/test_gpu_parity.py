@@ -149,6 +149,33 @@ def test_full_solve_matches_oracle_other_terrains(gpu, terrain, name):
     _assert_solve_parity(pb, res, cxy, cyaw, ores)
 
 
+def test_feasibility_scan_matches_oracle(gpu, hill_map):
+    """getMaxVxAxAyCurAttSig + getNonHolError of every solved trajectory (ualm_feasibility_batch) against
+    orc_feasibility on the same coefficients and piece durations -- bitwise, including the sample count."""
+    import pyoracle as po
+    from uneven_planner_b200 import _lib, problems
+    params = _lib.default_params()
+    pb = problems.generate(hill_map, 40, seed=2)
+    opt = gpu.BatchALMTrajOpt().init(params).set_environment(hill_map)
+    res, cxy, cyaw = opt.optimize(pb)
+    feas = opt.feasibility(0.01)
+    om = po.OracleMap(hill_map)
+    _, _, ocx, ocy = pb.offsets()
+    for i in range(pb.B):
+        N, M = int(pb.N[i]), int(pb.M[i])
+        Tx, Ty = feas[i, 8], feas[i, 9]
+        tt = 0.0
+        for _ in range(N):
+            tt += Tx
+        assert tt == res[i].total_T                                     # the piece duration of the last evaluation (Q1)
+        ref = po.feasibility(om, params.gravity, N, M, cxy[ocx[i]:ocx[i + 1]], cyaw[ocy[i]:ocy[i + 1]], Tx, Ty, 0.01)
+        assert np.array_equal(feas[i, :8], ref), (i, feas[i, :8], ref)
+    conv = np.array([r.ret_code == 0 for r in res])
+    # converged trajectories respect the limits the constraints encode (within the ALM tolerance), run_hill.yaml
+    assert np.all(np.abs(feas[conv, 0]) <= params.max_vel * 1.1) and np.all(-feas[conv, 4] >= params.min_cxi * 0.95)
+    opt.close()
+
+
 def test_full_solve_without_scaling_volcano_parameters(gpu, bumps_map):
     """run_vocano.yaml deltas: use_scaling=false (fixed cur_scale / sig_scale, Q6), rho_T=500; config 4 adds
     max_kap=0.3 and a denser sampling (int_K=32 here to keep the oracle quick)."""

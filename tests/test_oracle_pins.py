@@ -291,3 +291,32 @@ def test_oracle_matches_golden_fixture(terrain, name):
     assert np.array_equal(np.array([r[0].inner_cost for r in out]), gold["inner_cost"])
     assert np.array_equal(np.concatenate([r[1] for r in out]), gold["c_xy"])
     assert np.array_equal(np.concatenate([r[2] for r in out]), gold["c_yaw"])
+
+
+# ---------------------------------------------------------------- (9) post-solve scan
+def test_feasibility_scan_closed_forms():
+    """orc_feasibility on a flat map: a straight constant-speed run and a constant-rate turn have closed-form maxima
+    (alm_traj_opt.h:170-229, se2traj.hpp:551-561)."""
+    from uneven_planner_b200 import maps
+    flat = maps.synthetic_terrain("flat")
+    om = po.OracleMap(flat)
+    N, M, Tx, Ty = 2, 4, 1.0, 0.5
+    v, yaw0 = 0.4, 0.3
+    cxy = np.zeros(12 * N); cyaw = np.zeros(6 * M)
+    for i in range(N):           # x = v cos(yaw0) t, y = v sin(yaw0) t, piece-local coefficients low -> high
+        cxy[6 * i] = v * np.cos(yaw0) * Tx * i; cxy[6 * i + 1] = v * np.cos(yaw0)
+        cxy[6 * N + 6 * i] = v * np.sin(yaw0) * Tx * i; cxy[6 * N + 6 * i + 1] = v * np.sin(yaw0)
+    for i in range(M):
+        cyaw[6 * i] = yaw0
+    out = po.feasibility(om, 9.81, N, M, cxy, cyaw, Tx, Ty)
+    n = int(out[7])
+    assert n in (200, 201)                                    # t = 0, 0.01, ... < 2.0 by repeated addition
+    assert abs(out[0] - v) < 1e-12 and abs(out[1]) < 1e-12 and abs(out[2]) < 1e-12 and out[3] == 0.0
+    assert out[4] == -1.0 and out[5] == 0.0 and out[6] < 1e-12 * n
+    # heading off by 90 degrees: the non-holonomic error integrates |v| per sample; a yaw rate w gives curvature w / sqrt(v^2 + 0.01)
+    w = 0.2
+    for i in range(M):
+        cyaw[6 * i] = yaw0 + np.pi / 2 + w * Ty * i; cyaw[6 * i + 1] = w
+    out2 = po.feasibility(om, 9.81, N, M, cxy, cyaw, Tx, Ty)
+    assert abs(out2[3] - w / np.sqrt(v * v + 0.01)) < 1e-12
+    assert out2[6] > 0.9 * v * int(out2[7]) * np.cos(w * 2.0)

@@ -82,6 +82,8 @@ def lib():
         L.ualm_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong)]
         L.ualm_map_build_device.argtypes = [vp, fp, C.c_int64, C.POINTER(MapGeom), C.c_double, C.c_double, C.c_double, C.c_int, fp, C.POINTER(C.c_float)]
         L.ualm_map_build_device.restype = C.c_int
+        L.ualm_feasibility_batch.argtypes = [vp, C.c_double, dp]
+        L.ualm_feasibility_batch.restype = C.c_int
         L.ualm_profile.restype = C.c_int
         for name in ("ualm_create", "ualm_destroy", "ualm_set_params", "ualm_set_map", "ualm_solve_batch",
                      "ualm_upload", "ualm_solve_resident", "ualm_sync", "ualm_download", "ualm_last_solve_ms",

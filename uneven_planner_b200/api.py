@@ -134,6 +134,12 @@ class BatchALMTrajOpt:
         _check(self.L.ualm_time_penalty_kernel(self.h, reps, C.byref(ms), C.byref(by)))
         return ms.value, by.value
 
+    def feasibility(self, dt=0.01):
+        """Post-solve scan of the resident batch: array [B, 10] (see ualm_feasibility_batch)."""
+        out = np.zeros((self.pb.B, 10))
+        _check(self.L.ualm_feasibility_batch(self.h, float(dt), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
     def build_map(self, pts, geom=None, ellipsoid=(0.2, 0.1, 0.1), iter_num=2, name="map"):
         """UnevenMap grid from a point cloud on the GPU (ualm_map_build_device): (UnevenMapData, kernel ms)."""
         from . import maps

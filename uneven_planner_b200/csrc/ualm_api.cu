@@ -72,6 +72,7 @@ struct ualm_ctx {
     DevBuf<double> d_x0, d_x, d_lambda, d_mu, d_scale_cx, d_hx, d_gx, d_lm_s, d_lm_y, d_lm_aux, d_fac, d_scr, d_ws, d_cxy, d_cyaw, d_f, d_grad, d_sfx;
     DevBuf<ualm_result_t> d_res;
     DevBuf<long long> d_prof;
+    DevBuf<double> d_pieceT, d_feas;
     bool profile = false;
     float last_ms = 0.f;
     int last_launches = 0;
@@ -112,7 +113,7 @@ extern "C" int ualm_destroy(ualm_ctx_t *c)
     DevBuf<double> *bufs[] = {&c->d_x0, &c->d_x, &c->d_lambda, &c->d_mu, &c->d_scale_cx, &c->d_hx, &c->d_gx, &c->d_lm_s, &c->d_lm_y, &c->d_lm_aux, &c->d_fac,
                               &c->d_scr, &c->d_ws, &c->d_cxy, &c->d_cyaw, &c->d_f, &c->d_grad, &c->d_sfx};
     for (auto *b : bufs) b->release();
-    c->d_res.release(); c->d_prof.release();
+    c->d_res.release(); c->d_prof.release(); c->d_pieceT.release(); c->d_feas.release();
     for (int q = 0; q < ualm_ctx::NAUX; q++) cudaStreamDestroy(c->aux[q]);
     for (int q = 0; q < ualm_ctx::NAUX + 1; q++) cudaEventDestroy(c->evs[q]);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -186,7 +187,7 @@ static BatchPtrs batch_ptrs(ualm_ctx *c)
     b.desc = c->d_desc.p; b.order = c->d_order.p; b.x0 = c->d_x0.p; b.x = c->d_x.p;
     b.lambda = c->d_lambda.p; b.mu = c->d_mu.p; b.scale_cx = c->d_scale_cx.p; b.hx = c->d_hx.p; b.gx = c->d_gx.p;
     b.lm_s = c->d_lm_s.p; b.lm_y = c->d_lm_y.p; b.lm_aux = c->d_lm_aux.p; b.fac = c->d_fac.p; b.scratch = c->d_scr.p; b.ws_scaling = c->d_ws.p;
-    b.c_xy = c->d_cxy.p; b.c_yaw = c->d_cyaw.p; b.results = c->d_res.p; b.f_out = c->d_f.p; b.grad_out = c->d_grad.p;
+    b.c_xy = c->d_cxy.p; b.c_yaw = c->d_cyaw.p; b.results = c->d_res.p; b.piece_T = c->d_pieceT.p; b.f_out = c->d_f.p; b.grad_out = c->d_grad.p;
     b.scale_fx_io = c->d_sfx.p;
     b.prof = c->profile ? c->d_prof.p : nullptr;
     return b;
@@ -342,6 +343,7 @@ extern "C" int ualm_upload(ualm_ctx_t *c, int B, const int32_t *N, const int32_t
     // factor arrays: entries outside the band-in-matrix positions (and the pad rows) are never written and must read 0
     if (ofac > 0) CK(cudaMemsetAsync(c->d_fac.p, 0, sizeof(double) * ofac, c->stream));
     CK(c->d_prof.ensure((size_t)std::max(B, 1) * UALM_NPROF));
+    CK(c->d_pieceT.ensure((size_t)std::max(B, 1) * 2)); CK(c->d_feas.ensure((size_t)std::max(B, 1) * 10));
     CK(c->d_cxy.ensure(ocx)); CK(c->d_cyaw.ensure(ocy)); CK(c->d_res.ensure(B)); CK(c->d_f.ensure(B)); CK(c->d_sfx.ensure(B));
     if (B > 0) {
         CK(cudaMemcpyAsync(c->d_desc.p, c->desc.data(), sizeof(ProbDesc) * B, cudaMemcpyHostToDevice, c->stream));
@@ -537,6 +539,20 @@ extern "C" int ualm_profile(ualm_ctx_t *c, int enable, long long *out16)
         }
     }
     c->profile = enable != 0;
+    return UALM_OK;
+}
+
+extern "C" int ualm_feasibility_batch(ualm_ctx_t *c, double dt, double *out10)
+{
+    if (!c || !out10 || !(dt > 0.0)) return fail(UALM_EINVAL, "null argument or dt <= 0");
+    if (!c->have_map || !c->have_params || !c->have_batch || !c->solved) return fail(UALM_ESTATE, "ualm_feasibility_batch needs a solved resident batch");
+    CK(cudaSetDevice(c->device));
+    if (c->B == 0) return UALM_OK;
+    const BatchPtrs bp = batch_ptrs(c);
+    feasibility_kernel<<<(c->B + UALM_WPB - 1) / UALM_WPB, UALM_THREADS * UALM_WPB, 0, c->stream>>>(bp, c->dp, c->dm, dt, c->d_feas.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out10, c->d_feas.p, sizeof(double) * 10 * c->B, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return UALM_OK;
 }
 

@@ -102,6 +102,7 @@ struct BatchPtrs {
     R *ws_scaling;           // initScaling adjoint workspace
     R *c_xy, *c_yaw;
     ualm_result_t *results;
+    R *piece_T;              // per problem {T_xy piece, T_yaw piece} of the LAST evaluation (the durations getTraj() carries, Q1)
     // eval entry
     R *f_out, *grad_out, *scale_fx_io;
     long long *prof;         // optional [grid][UALM_NPROF] phase cycle counters (lane 0 of each warp)
@@ -2142,6 +2143,7 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) solve_kernel(const __
         for (int i = 0; i < N; i++) tt += t.sc[SC_TX1];
         r.total_T = tt; r.res_h = rh; r.res_g = rg; r.scale_fx = t.sc[SC_SCALE_FX]; r.rho_final = t.sc[SC_RHO];
         bp.results[prob] = r;
+        bp.piece_T[2 * prob] = t.sc[SC_TX1]; bp.piece_T[2 * prob + 1] = t.sc[SC_TY1];
         if (bp.prof) {
             t.prof[PF_TOTAL] += clock64();
             for (int q = 0; q < UALM_NPROF; q++) bp.prof[(size_t)prob * UALM_NPROF + q] = t.prof[q];
@@ -2215,6 +2217,120 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) penalty_only_kernel(c
         UALM_SYNC();
     }
     if (lane == 0) bp.f_out[prob] = t.sc[SC_CONSTR];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Post-solve quality scan: ALMTrajOpt::getMaxVxAxAyCurAttSig (alm_traj_opt.h:170-229) and
+// SE2Trajectory::getNonHolError (se2traj.hpp:551-561) of every solved trajectory, one warp per trajectory, one lane per sample
+// time.  The reference walks t = 0, dt, 2dt.. by repeated addition and keeps "the first sample with the largest |value|":
+// here every lane forms the same sequence of additions and keeps its own slice, the warp reduces by (|value|, earliest sample),
+// and the non-holonomic error is summed in sample order -- bit-identical to the sequential loops (oracle: orc_feasibility).
+// out[10 * problem + ...] = {max_vx, max_ax, max_ay, max_cur, max_att, max_sig, nonhol_error, samples, T_xy piece, T_yaw piece}
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int locate_piece(int P, R dur, R &t)   // PolyTrajectory::locatePieceIdx (se2traj.hpp:343-361), uniform durations
+{
+    int idx;
+    for (idx = 0; idx < P && t > dur; idx++) t -= dur;
+    if (idx == P) { idx--; t += dur; }
+    return idx;
+}
+__device__ __forceinline__ void piece_eval(const R *c, R t, R &v, R &dv, R &ddv)   // Piece::getValue / getDotValue / getDDotValue (se2traj.hpp:106-150)
+{
+    v = 0.0; dv = 0.0; ddv = 0.0;
+    R tn = 1.0;
+    for (int k = 0; k <= 5; k++) { v += tn * c[k]; tn *= t; }
+    tn = 1.0;
+    int n = 1;
+    for (int k = 1; k <= 5; k++) { dv += (R)n * tn * c[k]; tn *= t; n++; }
+    tn = 1.0;
+    int m = 1; n = 2;
+    for (int k = 2; k <= 5; k++) { ddv += (R)(m * n) * tn * c[k]; tn *= t; m++; n++; }
+}
+struct AbsMax {   // "if (fabs(best) < fabs(v)) best = v" over samples in time order
+    R val; int idx;
+    __device__ __forceinline__ void init() { val = 0.0; idx = 0x7fffffff; }
+    __device__ __forceinline__ void see(R v, int k) { if (fabs(val) < fabs(v)) { val = v; idx = k; } }
+    __device__ __forceinline__ void reduce()
+    {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const R ov = __shfl_xor_sync(0xffffffffu, val, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+            if (fabs(val) < fabs(ov) || (fabs(val) == fabs(ov) && oi < idx)) { val = ov; idx = oi; }
+        }
+    }
+};
+__global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) feasibility_kernel(const __grid_constant__ BatchPtrs bp, const __grid_constant__ DevParams p,
+        const __grid_constant__ DevMap map, R dt, R *out)
+{
+    const int lane = threadIdx.x & 31, prob = blockIdx.x * UALM_WPB + (threadIdx.x >> 5);
+    if (prob >= bp.B) return;   // whole warp exits
+    const ProbDesc *pd = bp.desc + prob;
+    const int N = pd->N, M = pd->M, nx = 6 * N;
+    const R *cxy = bp.c_xy + pd->off_cxy, *cyaw = bp.c_yaw + pd->off_cyaw;
+    const R Tx = bp.piece_T[2 * prob], Ty = bp.piece_T[2 * prob + 1];
+    R tot_xy = 0.0, tot_yaw = 0.0;    // PolyTrajectory::getTotalDuration (se2traj.hpp:291-300), SE2: the smaller one (:415-418)
+    for (int i = 0; i < N; i++) tot_xy += Tx;
+    for (int i = 0; i < M; i++) tot_yaw += Ty;
+    const R total = tot_xy < tot_yaw ? tot_xy : tot_yaw;
+    AbsMax mvx, max_, may, mcur;
+    mvx.init(); max_.init(); may.init(); mcur.init();
+    R matt = -1.0, msig = 0.0, err = 0.0;
+    long long count = 0;
+    R tbase = 0.0;
+    int kbase = 0;
+    while (true) {
+        R tm = 0.0, tt = tbase;
+        for (int i = 0; i < 32; i++) { if (i == lane) tm = tt; tt = tt + dt; }   // the reference's t += 0.01, same additions on every lane
+        const bool valid = tm < total;
+        R term = 0.0;
+        if (valid) {
+            R tl = tm;
+            const int ip = locate_piece(N, Tx, tl);
+            R px, py, vxw, vyw, axw, ayw, yaw, dyaw, dd;
+            piece_eval(cxy + 6 * ip, tl, px, vxw, axw);
+            piece_eval(cxy + nx + 6 * ip, tl, py, vyw, ayw);
+            R ty = tm;
+            const int iy = locate_piece(M, Ty, ty);
+            piece_eval(cyaw + 6 * iy, ty, yaw, dyaw, dd);
+            R se2[3] = {px, py, yaw};
+            normSO2(se2[2]);                                  // getNormSE2Pos (se2traj.hpp:433-443)
+            R tv[7], tg[7][3];
+            map_get_all_with_grad(map, se2, tv, tg);          // values as getTerrainVariables (uneven_map.h:221-256)
+            const double2 sc = dev_sincos(yaw);
+            const R sy_ = sc.x, cy_ = sc.y;
+            const R vnorm = sqrt(vxw * vxw + vyw * vyw);
+            const R lon = axw * cy_ + ayw * sy_;
+            const R lat = -axw * sy_ + ayw * cy_;
+            const R vx = vnorm * tv[0];
+            const R ax = lon * tv[0] + p.gravity * tv[1];
+            const R ay = lat * tv[2] + p.gravity * tv[3];
+            const R wz = dyaw * tv[5];
+            const R cur = wz / sqrt(vx * vx + UALM_DELTA_SIGL);
+            const R att = -1.0 / tv[5];
+            const int k = kbase + lane;
+            max_.see(ax, k); may.see(ay, k); mvx.see(vx, k); mcur.see(cur, k);
+            if (matt < att) matt = att;
+            if (msig < tv[6]) msig = tv[6];
+            term = fabs(vxw * sy_ + vyw * (-cy_));
+        }
+        const int cnt = __popc(__ballot_sync(0xffffffffu, valid));   // the valid lanes are a prefix: t grows with the lane
+        for (int l = 0; l < cnt; l++) err += __shfl_sync(0xffffffffu, term, l);
+        count += cnt;
+        if (cnt < 32) break;
+        tbase = tt; kbase += 32;
+    }
+    mvx.reduce(); max_.reduce(); may.reduce(); mcur.reduce();
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const R oa = __shfl_xor_sync(0xffffffffu, matt, off), os = __shfl_xor_sync(0xffffffffu, msig, off);
+        if (matt < oa) matt = oa;
+        if (msig < os) msig = os;
+    }
+    if (lane == 0) {
+        R *o = out + 10 * (size_t)prob;
+        o[0] = mvx.val; o[1] = max_.val; o[2] = may.val; o[3] = mcur.val; o[4] = matt; o[5] = msig; o[6] = err; o[7] = (R)count; o[8] = Tx; o[9] = Ty;
+    }
 }
 
 // fixed-stride result records for the multi-GPU all-gather
