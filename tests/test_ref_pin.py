@@ -1,0 +1,110 @@
+"""Pins of the oracle against the REFERENCE'S OWN SOURCE TEXT.
+
+oracle/_ref/libref.so is back_end/include/utils/{se2traj,banded_system,lbfgs}.hpp compiled unmodified from /root/reference
+against oracle/shim (a minimal Eigen stand-in; Eigen and ROS are absent from this image) by `make -C oracle ref`
+(oracle/ref_driver.cpp).  These tests feed identical seeded inputs to that build and to the oracle's restatement
+(oracle/oracle.cpp) and require BIT-IDENTICAL outputs for MinJerkOpt<1|2>::generate / getTrajJerkCost / calJerkGradCT /
+calGradCTtoQT (through BandedSystem a5) and for lbfgs_optimize + line_search_lewisoverton with the
+reference's local modifications (row a2, quirk Q8).  The shim fixes what the reference leaves to Eigen: dot()/norm() in the
+oracle's canonical 32-lane order, sum() in element order (oracle/shim/Eigen/Eigen header comment)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "libref.so")
+dp = C.POINTER(C.c_double)
+
+
+def P(a):
+    return None if a is None else a.ctypes.data_as(dp)
+
+
+@pytest.fixture(scope="module")
+def ref(built):
+    if os.path.isdir("/root/reference/src/uneven_planner/back_end/include"):
+        import subprocess
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "ref"], check=True)
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref/libref.so not built (needs /root/reference; it travels to the GPU box prebuilt)")
+    L = C.CDLL(REF)
+    L.ref_minco.restype = C.c_int
+    L.ref_minco.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp]
+    L.ref_banded.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, C.c_int]
+    L.ref_lbfgs_rosenbrock.argtypes = [C.c_int, dp, dp, C.c_int, C.c_double, C.c_int, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    return L
+
+
+@pytest.fixture(scope="module")
+def orc(built):
+    import pyoracle as po
+    L = po.lib()
+    L.orc_minco_generate.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp]
+    L.orc_minco_jerk.restype = C.c_double
+    L.orc_minco_jerk.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp]
+    L.orc_minco_grad_ct_to_qt.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, dp]
+    L.orc_lbfgs_rosenbrock.argtypes = [C.c_int, dp, dp, C.c_int, C.c_double, C.c_int, C.c_double, C.POINTER(C.c_int)]
+    return L
+
+
+@pytest.mark.parametrize("Dim", [1, 2])
+@pytest.mark.parametrize("N,uniform", [(1, True), (2, False), (5, True), (21, True), (21, False), (64, True)])
+def test_minco_headers_match_oracle_bitwise(ref, orc, Dim, N, uniform):
+    rng = np.random.default_rng(100 * N + Dim)
+    inPs = rng.normal(0, 2.0, Dim * max(N - 1, 1))[:Dim * (N - 1)].copy()
+    ts = np.full(N, rng.uniform(0.3, 1.2)) if uniform else rng.uniform(0.3, 1.2, N)
+    head = rng.normal(0, 1.0, Dim * 3); tail = rng.normal(0, 1.0, Dim * 3)
+    gdC_in = rng.normal(0, 1.0, 6 * N * Dim); gdT0 = rng.normal(0, 1.0, N)
+    # reference headers
+    c_r = np.zeros(6 * N * Dim); jerk_r = np.zeros(1); gC_r = np.zeros(6 * N * Dim); gT_r = np.zeros(N)
+    gdT_r = gdT0.copy(); gdP_r = np.zeros(max(Dim * (N - 1), 1))
+    assert ref.ref_minco(Dim, N, P(inPs) if N > 1 else P(np.zeros(1)), P(ts), P(head), P(tail), P(c_r), P(jerk_r), P(gC_r), P(gT_r),
+                         P(gdC_in), P(gdT_r), P(gdP_r)) == 0
+    # oracle restatement
+    c_o = np.zeros(6 * N * Dim)
+    orc.orc_minco_generate(Dim, N, P(inPs) if N > 1 else P(np.zeros(1)), P(ts), P(head), P(tail), P(c_o))
+    gC_o = np.zeros(6 * N * Dim); gT_o = np.zeros(N)
+    jerk_o = orc.orc_minco_jerk(Dim, N, P(c_o), P(ts), P(gC_o), P(gT_o))
+    gdT_o = gdT0.copy(); gdP_o = np.zeros(max(Dim * (N - 1), 1))
+    orc.orc_minco_grad_ct_to_qt(Dim, N, P(inPs) if N > 1 else P(np.zeros(1)), P(ts), P(head), P(tail), P(gdC_in), P(gdT_o), P(gdP_o))
+    assert np.array_equal(c_r, c_o)                        # generate: banded fill, factorizeLU, solve
+    assert jerk_r[0] == jerk_o                             # getTrajJerkCost
+    assert np.array_equal(gC_r, gC_o) and np.array_equal(gT_r, gT_o)     # calJerkGradCT
+    assert np.array_equal(gdT_r, gdT_o) and np.array_equal(gdP_r[:Dim * (N - 1)], gdP_o[:Dim * (N - 1)])   # calGradCTtoQT (solveAdj)
+    # and the solution is a solution: waypoints interpolated, boundary states met
+    cm = c_r.reshape(Dim, 6 * N)
+    assert np.allclose(cm[:, 0], head[:Dim]) and np.allclose(cm[:, 1], head[Dim:2 * Dim])
+
+
+def test_banded_system_header_solves(ref):
+    """BandedSystem (banded_system.hpp:25-145) of the reference build on a random diagonally dominant band matrix: solve and
+    adjoint solve against numpy."""
+    rng = np.random.default_rng(7)
+    n, lo, up, m = 30, 6, 6, 2
+    A = np.zeros((n, n))
+    for i in range(n):
+        for j in range(max(0, i - lo), min(n, i + up + 1)):
+            A[i, j] = rng.normal()
+        A[i, i] += 20.0
+    b = rng.normal(size=(n, m))
+    for adj in (0, 1):
+        x = np.asfortranarray(b.copy())
+        ref.ref_banded(n, lo, up, P(np.ascontiguousarray(A)), P(x), m, adj)
+        want = np.linalg.solve(A.T if adj else A, b)
+        assert np.allclose(x, want, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("n,mem,past", [(2, 8, 3), (10, 8, 3), (20, 256, 3), (6, 4, 0)])
+def test_lbfgs_header_matches_oracle_bitwise(ref, orc, n, mem, past):
+    """lbfgs_optimize + line_search_lewisoverton of lbfgs.hpp (with the reference's own modifications, lbfgs.hpp:327-330) against
+    the oracle's restatement on the Rosenbrock function: same return code, iteration count, final point and value, bit for bit."""
+    x0 = np.tile([-1.2, 1.0], n // 2).astype(np.float64)
+    xr = x0.copy(); fr = np.zeros(1); ir = C.c_int(); er = C.c_int()
+    rr = ref.ref_lbfgs_rosenbrock(n, P(xr), P(fr), mem, 1e-6, past, 1e-6, C.byref(ir), C.byref(er))
+    xo = x0.copy(); fo = np.zeros(1); io = C.c_int()
+    ro = orc.orc_lbfgs_rosenbrock(n, P(xo), P(fo), mem, 1e-6, past, 1e-6, C.byref(io))
+    assert rr == ro and ir.value == io.value
+    assert fr[0] == fo[0] and np.array_equal(xr, xo)
+    assert fr[0] < 1e-6 and np.allclose(xr, 1.0, atol=1e-2)
