@@ -17,10 +17,17 @@
  *   lbfgs_optimize + line search     back_end/include/utils/lbfgs.hpp:276-722
  *   UnevenMap::getAllWithGrad chain  uneven_map/include/uneven_map/uneven_map.h:258-377,398-454
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path
- *  and cannot be compiled in this image (Eigen/ROS/PCL absent), so the
- * oracle is pinned by analytic invariants and finite-difference checks (tests/test_oracle_*.py),
- * not by reference outputs.
+ * PARITY PINNED AGAINST THE REFERENCE'S OWN SOURCE (round 1): the reference ships no tests, golden vectors or fixtures for this
+ * path and its dependencies (Eigen, ROS, PCL, OMPL) are absent from this image, but its back-end sources
+ * compile UNMODIFIED against oracle/shim (a minimal Eigen stand-in with this oracle's reduction orders, no-op ROS/PCL headers):
+ * `make -C oracle ref` builds back_end/src/alm_traj_opt.cpp + back_end/include/{back_end/alm_traj_opt.h, utils/*.hpp} +
+ * uneven_map/include/uneven_map/uneven_map.h from /root/reference into oracle/_ref/libref.so, and tests/test_ref_pin.py requires
+ * bit-identical outputs from that build and from this restatement: MinJerkOpt / BandedSystem / lbfgs_optimize piecewise, and
+ * whole ALMTrajOpt::optimizeSE2Traj solves (return code, coefficients, durations, multipliers, scales).  What that build does
+ * NOT contain: real Eigen (its SIMD reduction order is version- and flag-dependent; the shim fixes the canonical order below),
+ * libm trig (replaced by include/ualm_detmath.h on all three sides), uneven_map.cpp (needs PCL: the grid is injected and the
+ * six-line normSO2 is restated in oracle/ref_alm_driver.cpp).  Analytic invariants and finite-difference checks
+ * (tests/test_oracle_pins.py) pin the mathematics independently.
  */
 #ifndef UALM_ORACLE_H
 #define UALM_ORACLE_H

@@ -1,0 +1,2 @@
+#pragma once
+#include <sensor_msgs/PointCloud2.h>

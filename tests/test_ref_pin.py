@@ -108,3 +108,64 @@ def test_lbfgs_header_matches_oracle_bitwise(ref, orc, n, mem, past):
     assert rr == ro and ir.value == io.value
     assert fr[0] == fo[0] and np.array_equal(xr, xo)
     assert fr[0] < 1e-6 and np.allclose(xr, 1.0, atol=1e-2)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the whole path: ALMTrajOpt::optimizeSE2Traj of back_end/src/alm_traj_opt.cpp (unmodified) vs the oracle
+# ---------------------------------------------------------------------------------------------------------------------
+class RefParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("rho_T", "rho_ter", "max_vel", "max_acc_lon", "max_acc_lat", "max_kap", "min_cxi", "max_sig")] + \
+               [("use_scaling", C.c_int)] + \
+               [(n, C.c_double) for n in ("rho", "beta", "gamma", "epsilon_con", "max_iter", "g_epsilon", "min_step", "inner_max_iter", "delta")] + \
+               [("mem_size", C.c_int), ("past", C.c_int), ("int_K", C.c_int), ("gravity", C.c_double)]
+
+
+def _ref_solve(L, params, mapdata, pb, i):
+    g = mapdata.geom
+    rp = RefParams()
+    for n, _ in RefParams._fields_:
+        setattr(rp, n, getattr(params, n))
+    cells = np.ascontiguousarray(mapdata.cells, dtype=np.float64)
+    N, M = int(pb.N[i]), int(pb.M[i])
+    S = N * (params.int_K + 1)
+    oxy, oyaw, _, _ = pb.offsets()
+    ixy = np.ascontiguousarray(pb.inner_xy[oxy[i]:oxy[i + 1]]); iyaw = np.ascontiguousarray(pb.inner_yaw[oyaw[i]:oyaw[i + 1]])
+    out = dict(c_xy=np.zeros(12 * N), c_yaw=np.zeros(6 * M), piece_T=np.zeros(2), lam=np.zeros(S), mu=np.zeros(6 * S), hx=np.zeros(S),
+               gx=np.zeros(6 * S), sfx=np.zeros(1), scx=np.zeros(7 * S), rho=np.zeros(1))
+    vn = (C.c_int * 3)(*g.voxel_num); org = (C.c_double * 3)(*g.origin); mxb = (C.c_double * 3)(*g.max_boundary)
+    L.ref_alm_solve.restype = C.c_int
+    ret = L.ref_alm_solve(C.byref(rp), P(cells), vn, org, mxb, C.c_double(g.xy_resolution), C.c_double(g.yaw_resolution), N, M,
+                          P(np.ascontiguousarray(pb.bnd[i])), C.c_double(float(pb.total_time[i])), P(ixy if ixy.size else np.zeros(1)),
+                          P(iyaw if iyaw.size else np.zeros(1)), 0, P(out["c_xy"]), P(out["c_yaw"]), P(out["piece_T"]), P(out["lam"]), P(out["mu"]),
+                          P(out["hx"]), P(out["gx"]), P(out["sfx"]), P(out["scx"]), P(out["rho"]))
+    return ret, out
+
+
+@pytest.mark.parametrize("which,use_scaling", [("bumps", 1), ("bumps", 0), ("hill", 1)])
+def test_reference_optimizeSE2Traj_matches_oracle_bitwise(ref, built, request, which, use_scaling):
+    """ALMTrajOpt::optimizeSE2Traj compiled from the reference's alm_traj_opt.cpp (innerCallback, calConstrainCostGrad, initScaling,
+    earlyExit, dual update, UnevenMap::getAllWithGrad, MINCO, L-BFGS) against oracle.cpp on the same problems: return code,
+    coefficients, piece durations, multipliers, constraint values, scales and the final rho, all bit-identical."""
+    import pyoracle as po
+    from uneven_planner_b200 import _lib, maps, problems
+    m = request.getfixturevalue("bumps_map") if which == "bumps" else maps.get_terrain("hill")
+    if m is None:
+        pytest.skip("hill.umap not present")
+    params = _lib.default_params()
+    params.use_scaling = use_scaling
+    if not use_scaling:
+        params.rho_T = 500.0
+    pb = problems.generate(m, 6, seed=11)
+    om = po.OracleMap(m)
+    op = po.params_from(params)
+    for i in range(pb.B):
+        ret, out = _ref_solve(ref, params, m, pb, i)
+        r, ocxy, ocyaw, _, olam, omu, oscx = po.solve_one(op, om, pb, i, want_duals=True)
+        assert ret == r.ret_code, i
+        assert np.array_equal(out["c_xy"], ocxy) and np.array_equal(out["c_yaw"], ocyaw), i
+        tt = 0.0
+        for _ in range(int(pb.N[i])):
+            tt += out["piece_T"][0]
+        assert tt == r.total_T and out["rho"][0] == r.rho_final and out["sfx"][0] == r.scale_fx, i
+        assert np.array_equal(out["lam"], olam) and np.array_equal(out["mu"], omu) and np.array_equal(out["scx"], oscx), i
+        assert max(np.abs(out["hx"]).max(), 0.0) == r.res_h, i      # judgeConvergence's first norm, from the reference's own hx
