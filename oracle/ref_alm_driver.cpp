@@ -53,11 +53,12 @@ struct ref_params_t {   /* same field order as orc_params_t / ualm_params_t */
 };
 
 /* cells: X*Y*W x 4 doubles {z, sigma, zbx, zby}; geometry as ualm_map_geom_t.  Outputs: ret code, c_xy (6N x 2 col-major),
- * c_yaw (6M), piece durations, lambda[S], mu[6S], hx[S], gx[6S], scale_fx, scale_cx[7S], rho at exit. */
+ * c_yaw (6M), piece durations, lambda[S], mu[6S], hx[S], gx[6S], scale_fx, scale_cx[7S], rho at exit, and feas7 = the reference's own
+ * post-solve report {getMaxVxAxAyCurAttSig(getTraj()) [6], getTraj().getNonHolError()} (alm_traj_opt.h:170-229, se2traj.hpp:551-561). */
 int ref_alm_solve(const ref_params_t *p, const double *cells, const int *voxel_num, const double *origin, const double *max_boundary,
                   double xy_res, double yaw_res, int N, int M, const double *bnd18, double total_time, const double *inner_xy,
                   const double *inner_yaw, int scaling_only, double *c_xy, double *c_yaw, double *piece_T, double *lambda, double *mu, double *hx,
-                  double *gx, double *scale_fx, double *scale_cx, double *rho_out)
+                  double *gx, double *scale_fx, double *scale_cx, double *rho_out, double *feas7)
 {
     UnevenMap::Ptr map(new UnevenMap());
     for (int k = 0; k < 3; k++) {
@@ -101,6 +102,12 @@ int ref_alm_solve(const ref_params_t *p, const double *cells, const int *voxel_n
     for (int i = 0; i < 7 * S; i++) scale_cx[i] = opt.scale_cx(i);
     *scale_fx = opt.scale_fx;
     *rho_out = opt.rho;
+    if (feas7) {
+        SE2Trajectory tr = opt.getTraj();
+        std::vector<double> mx = opt.getMaxVxAxAyCurAttSig(tr);
+        for (int k = 0; k < 6; k++) feas7[k] = mx[k];
+        feas7[6] = tr.getNonHolError();
+    }
     return ret;
 }
 

@@ -131,13 +131,13 @@ def _ref_solve(L, params, mapdata, pb, i):
     oxy, oyaw, _, _ = pb.offsets()
     ixy = np.ascontiguousarray(pb.inner_xy[oxy[i]:oxy[i + 1]]); iyaw = np.ascontiguousarray(pb.inner_yaw[oyaw[i]:oyaw[i + 1]])
     out = dict(c_xy=np.zeros(12 * N), c_yaw=np.zeros(6 * M), piece_T=np.zeros(2), lam=np.zeros(S), mu=np.zeros(6 * S), hx=np.zeros(S),
-               gx=np.zeros(6 * S), sfx=np.zeros(1), scx=np.zeros(7 * S), rho=np.zeros(1))
+               gx=np.zeros(6 * S), sfx=np.zeros(1), scx=np.zeros(7 * S), rho=np.zeros(1), feas=np.zeros(7))
     vn = (C.c_int * 3)(*g.voxel_num); org = (C.c_double * 3)(*g.origin); mxb = (C.c_double * 3)(*g.max_boundary)
     L.ref_alm_solve.restype = C.c_int
     ret = L.ref_alm_solve(C.byref(rp), P(cells), vn, org, mxb, C.c_double(g.xy_resolution), C.c_double(g.yaw_resolution), N, M,
                           P(np.ascontiguousarray(pb.bnd[i])), C.c_double(float(pb.total_time[i])), P(ixy if ixy.size else np.zeros(1)),
                           P(iyaw if iyaw.size else np.zeros(1)), 0, P(out["c_xy"]), P(out["c_yaw"]), P(out["piece_T"]), P(out["lam"]), P(out["mu"]),
-                          P(out["hx"]), P(out["gx"]), P(out["sfx"]), P(out["scx"]), P(out["rho"]))
+                          P(out["hx"]), P(out["gx"]), P(out["sfx"]), P(out["scx"]), P(out["rho"]), P(out["feas"]))
     return ret, out
 
 
@@ -169,3 +169,6 @@ def test_reference_optimizeSE2Traj_matches_oracle_bitwise(ref, built, request, w
         assert tt == r.total_T and out["rho"][0] == r.rho_final and out["sfx"][0] == r.scale_fx, i
         assert np.array_equal(out["lam"], olam) and np.array_equal(out["mu"], omu) and np.array_equal(out["scx"], oscx), i
         assert max(np.abs(out["hx"]).max(), 0.0) == r.res_h, i      # judgeConvergence's first norm, from the reference's own hx
+        # the reference's own post-solve report (getMaxVxAxAyCurAttSig + getNonHolError) against orc_feasibility on its trajectory
+        of = po.feasibility(om, params.gravity, int(pb.N[i]), int(pb.M[i]), out["c_xy"], out["c_yaw"], out["piece_T"][0], out["piece_T"][1], 0.01)
+        assert np.array_equal(out["feas"], of[:7]), (i, out["feas"], of)
