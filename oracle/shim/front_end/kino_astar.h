@@ -9,6 +9,9 @@ namespace uneven_planner {
 class KinoAstar {
 public:
     typedef std::shared_ptr<KinoAstar> Ptr;
-    std::vector<Eigen::Vector3d> plan(const Eigen::Vector3d &, const Eigen::Vector3d &) { return std::vector<Eigen::Vector3d>(); }
+    std::vector<Eigen::Vector3d> injected_path;    // the pin tests supply the front-end's polyline (x, y, yaw) here
+    void init(ros::NodeHandle &) {}
+    void setEnvironment(const UnevenMap::Ptr &) {}
+    std::vector<Eigen::Vector3d> plan(const Eigen::Vector3d &, const Eigen::Vector3d &) { return injected_path; }
 };
 }

@@ -12,7 +12,9 @@ struct Duration { Duration(double = 0.0) {} double toSec() const { return 0.0; }
 struct Time { static Time now() { return Time(); } double toSec() const { return 0.0; } Duration operator-(const Time &) const { return Duration(); } };
 struct TimerEvent {};
 struct Timer {};
-struct Publisher { template <class M> void publish(const M &) const {} };
+// publish() keeps the last message of every type so the pin tests can read what the reference would have sent
+template <class M> M &shim_last_message() { static M m; return m; }
+struct Publisher { template <class M> void publish(const M &m) const { shim_last_message<M>() = m; } };
 struct Subscriber {};
 struct Rate { Rate(double) {} void sleep() {} };
 struct TransportHints { TransportHints &tcpNoDelay() { return *this; } };

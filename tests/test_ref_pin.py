@@ -172,3 +172,75 @@ def test_reference_optimizeSE2Traj_matches_oracle_bitwise(ref, built, request, w
         # the reference's own post-solve report (getMaxVxAxAyCurAttSig + getNonHolError) against orc_feasibility on its trajectory
         of = po.feasibility(om, params.gravity, int(pb.N[i]), int(pb.M[i]), out["c_xy"], out["c_yaw"], out["piece_T"][0], out["piece_T"][1], 0.01)
         assert np.array_equal(out["feas"], of[:7]), (i, out["feas"], of)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the caller of the path: PlanManager::rcvWpsCallBack of plan_manager/src/plan_manager.cpp (unmodified)
+# ---------------------------------------------------------------------------------------------------------------------
+def _poly(c, t):
+    """Piece::getValue (se2traj.hpp:106-118) on coefficients low -> high."""
+    v, tn = 0.0, 1.0
+    for k in range(6):
+        v += tn * c[k]
+        tn *= t
+    return v
+
+
+def _end_value(c, P, dur):
+    """PolyTrajectory::getValue(getTotalDuration()) (se2traj.hpp:291-300, 343-367) of a P-piece spline with uniform durations."""
+    total = 0.0
+    for _ in range(P):
+        total += dur
+    t, idx = total, 0
+    while idx < P and t > dur:
+        t -= dur
+        idx += 1
+    if idx == P:
+        idx -= 1
+        t += dur
+    return _poly(c[6 * idx:6 * idx + 6], t)
+
+
+@pytest.mark.parametrize("seed", [3, 4])
+def test_reference_plan_manager_callback_matches_host_tools_and_oracle(ref, built, bumps_map, seed):
+    """PlanManager::rcvWpsCallBack of the reference (yaw unwrapping + arc-length resampling pm.cpp:62-122, optimizeSE2Traj, SE2Traj
+    message pm.cpp:151-185) fed with a front-end polyline, against ualm_resample_path + the oracle solve + the message layout of
+    include/ualm_traj_opt.hpp::toSE2TrajMsg: piece start points, end points and durations of both splines, bit for bit."""
+    import pyoracle as po
+    from uneven_planner_b200 import _lib, problems
+    params = _lib.default_params()
+    pb = problems.generate(bumps_map, 3, seed=seed)
+    op = po.params_from(params)
+    om = po.OracleMap(bumps_map)
+    g = bumps_map.geom
+    rp = RefParams()
+    for n, _ in RefParams._fields_:
+        setattr(rp, n, getattr(params, n))
+    cells = np.ascontiguousarray(bumps_map.cells, dtype=np.float64)
+    vn = (C.c_int * 3)(*g.voxel_num); org = (C.c_double * 3)(*g.origin); mxb = (C.c_double * 3)(*g.max_boundary)
+    mgr = np.array([0.3, 2.0, 0.5, 1.2, 0.05])                      # run_hill.yaml manager/* (problems.resample defaults)
+    for i in range(pb.B):
+        path = np.ascontiguousarray(problems.dubins(pb.starts[i], pb.goals[i]))
+        N, M = int(pb.N[i]), int(pb.M[i])
+        counts = (C.c_int * 2)()
+        pos = np.zeros(2 * (N + 8)); posT = np.zeros(N + 8); ang = np.zeros(M + 8); angT = np.zeros(M + 8)
+        rc = ref.ref_pm_plan(C.byref(rp), P(cells), vn, org, mxb, C.c_double(g.xy_resolution), C.c_double(g.yaw_resolution), P(mgr), P(path),
+                             int(path.shape[0]), counts, P(pos), P(posT), P(ang), P(angT))
+        assert rc == 0
+        assert (counts[0], counts[1]) == (N + 1, M + 1), i          # the reference's resampler produced the same piece counts
+        r, cxy, cyaw, _, _, _, _ = po.solve_one(op, om, pb, i, want_duals=True)
+        feas = np.zeros(1)
+        # durations: N * Tx == total_T with Tx the last evaluation's piece duration; recover Tx, Ty from the reference message itself and
+        # check them against the oracle's total
+        Tx, Ty = posT[0], angT[0]
+        tt = 0.0
+        for _ in range(N):
+            tt += Tx
+        assert tt == r.total_T and np.all(posT[:N] == Tx) and np.all(angT[:M] == Ty), i
+        want_pos = np.zeros(2 * (N + 1))
+        for k in range(N):
+            want_pos[2 * k] = cxy[6 * k]; want_pos[2 * k + 1] = cxy[6 * N + 6 * k]           # pos_traj[k].getValue(0)
+        want_pos[2 * N] = _end_value(cxy[:6 * N], N, Tx); want_pos[2 * N + 1] = _end_value(cxy[6 * N:], N, Tx)
+        want_ang = np.array([cyaw[6 * k] for k in range(M)] + [_end_value(cyaw, M, Ty)])
+        assert np.array_equal(pos[:2 * (N + 1)], want_pos), i
+        assert np.array_equal(ang[:M + 1], want_ang), i

@@ -257,8 +257,10 @@ extern "C" int ualm_resample_path(const double *path_in, int npts, double piece_
     }
     // boundary states (pm.cpp:80-94): 2x3 column-major [p | v | a], yaw [psi,0,0]
     const double *f = &p[0], *l = &p[3 * (size_t)(npts - 1)];
-    bnd[0] = f[0]; bnd[1] = f[1]; bnd[2] = init_sig_vel * std::cos(f[2]); bnd[3] = init_sig_vel * std::sin(f[2]); bnd[4] = 0; bnd[5] = 0;
-    bnd[6] = l[0]; bnd[7] = l[1]; bnd[8] = init_sig_vel * std::cos(l[2]); bnd[9] = init_sig_vel * std::sin(l[2]); bnd[10] = 0; bnd[11] = 0;
+    // sin / cos from ualm_detmath.h like every other trig call of the path (so the reference build of tests/test_ref_pin.py, whose
+    // trig is redirected to the same functions, produces bit-identical boundary states)
+    bnd[0] = f[0]; bnd[1] = f[1]; bnd[2] = init_sig_vel * ualm_cos(f[2]); bnd[3] = init_sig_vel * ualm_sin(f[2]); bnd[4] = 0; bnd[5] = 0;
+    bnd[6] = l[0]; bnd[7] = l[1]; bnd[8] = init_sig_vel * ualm_cos(l[2]); bnd[9] = init_sig_vel * ualm_sin(l[2]); bnd[10] = 0; bnd[11] = 0;
     bnd[12] = f[2]; bnd[13] = 0; bnd[14] = 0;
     bnd[15] = l[2]; bnd[16] = 0; bnd[17] = 0;
     // arc-length resampling (pm.cpp:96-121)
