@@ -55,25 +55,33 @@ struct ref_params_t {   /* same field order as orc_params_t / ualm_params_t */
 /* cells: X*Y*W x 4 doubles {z, sigma, zbx, zby}; geometry as ualm_map_geom_t.  Outputs: ret code, c_xy (6N x 2 col-major),
  * c_yaw (6M), piece durations, lambda[S], mu[6S], hx[S], gx[6S], scale_fx, scale_cx[7S], rho at exit, and feas7 = the reference's own
  * post-solve report {getMaxVxAxAyCurAttSig(getTraj()) [6], getTraj().getNonHolError()} (alm_traj_opt.h:170-229, se2traj.hpp:551-561). */
-int ref_alm_solve(const ref_params_t *p, const double *cells, const int *voxel_num, const double *origin, const double *max_boundary,
-                  double xy_res, double yaw_res, int N, int M, const double *bnd18, double total_time, const double *inner_xy,
-                  const double *inner_yaw, int scaling_only, double *c_xy, double *c_yaw, double *piece_T, double *lambda, double *mu, double *hx,
-                  double *gx, double *scale_fx, double *scale_cx, double *rho_out, double *feas7)
+/* the reference's UnevenMap object, filled in once and reused (building 2.5 M RXS2 cells dominates a single call otherwise) */
+void *ref_map_create(const double *cells, const int *voxel_num, const double *origin, const double *max_boundary, double xy_res, double yaw_res,
+                     double gravity)
 {
-    UnevenMap::Ptr map(new UnevenMap());
+    UnevenMap::Ptr *h = new UnevenMap::Ptr(new UnevenMap());
+    UnevenMap &map = **h;
     for (int k = 0; k < 3; k++) {
-        map->voxel_num(k) = voxel_num[k];
-        map->min_boundary(k) = origin[k]; map->map_origin(k) = origin[k]; map->max_boundary(k) = max_boundary[k];
-        map->min_idx(k) = 0; map->max_idx(k) = voxel_num[k] - 1;
+        map.voxel_num(k) = voxel_num[k];
+        map.min_boundary(k) = origin[k]; map.map_origin(k) = origin[k]; map.max_boundary(k) = max_boundary[k];
+        map.min_idx(k) = 0; map.max_idx(k) = voxel_num[k] - 1;
     }
-    map->xy_resolution = xy_res; map->yaw_resolution = yaw_res;
-    map->xy_resolution_inv = 1.0 / xy_res; map->yaw_resolution_inv = 1.0 / yaw_res;   /* uneven_map.cpp:104-105 */
-    map->gravity = p->gravity;
+    map.xy_resolution = xy_res; map.yaw_resolution = yaw_res;
+    map.xy_resolution_inv = 1.0 / xy_res; map.yaw_resolution_inv = 1.0 / yaw_res;   /* uneven_map.cpp:104-105 */
+    map.gravity = gravity;
     const size_t ncell = (size_t)voxel_num[0] * voxel_num[1] * voxel_num[2];
-    map->map_buffer.resize(ncell);
-    for (size_t i = 0; i < ncell; i++) map->map_buffer[i] = RXS2(cells[4 * i], cells[4 * i + 1], Eigen::Vector2d(cells[4 * i + 2], cells[4 * i + 3]));
-    map->map_ready = true;
+    map.map_buffer.resize(ncell);
+    for (size_t i = 0; i < ncell; i++) map.map_buffer[i] = RXS2(cells[4 * i], cells[4 * i + 1], Eigen::Vector2d(cells[4 * i + 2], cells[4 * i + 3]));
+    map.map_ready = true;
+    return h;
+}
+void ref_map_destroy(void *h) { delete (UnevenMap::Ptr *)h; }
 
+int ref_alm_solve_h(const ref_params_t *p, void *map_handle, int N, int M, const double *bnd18, double total_time, const double *inner_xy,
+                    const double *inner_yaw, double *c_xy, double *c_yaw, double *piece_T, double *lambda, double *mu, double *hx, double *gx,
+                    double *scale_fx, double *scale_cx, double *rho_out, double *feas7)
+{
+    UnevenMap::Ptr map = *(UnevenMap::Ptr *)map_handle;
     ALMTrajOpt opt;
     opt.rho_T = p->rho_T; opt.rho_ter = p->rho_ter; opt.max_vel = p->max_vel; opt.max_acc_lon = p->max_acc_lon; opt.max_acc_lat = p->max_acc_lat;
     opt.max_kap = p->max_kap; opt.min_cxi = p->min_cxi; opt.max_sig = p->max_sig; opt.use_scaling = p->use_scaling != 0; opt.rho = p->rho;
@@ -89,7 +97,6 @@ int ref_alm_solve(const ref_params_t *p, const double *cells, const int *voxel_n
     for (int j = 0; j < N - 1; j++) for (int d = 0; d < 2; d++) innerXY(d, j) = inner_xy[d + 2 * (size_t)j];
     for (int j = 0; j < M - 1; j++) innerYaw(j) = inner_yaw[j];
     int ret = opt.optimizeSE2Traj(initXY, endXY, innerXY, initYaw, endYaw, innerYaw, total_time);
-    (void)scaling_only;
 
     const Eigen::MatrixXd &cxy = opt.minco_se2.pos_minco.getCoeffs();
     const Eigen::MatrixXd &cyaw = opt.minco_se2.yaw_minco.getCoeffs();
@@ -108,6 +115,19 @@ int ref_alm_solve(const ref_params_t *p, const double *cells, const int *voxel_n
         for (int k = 0; k < 6; k++) feas7[k] = mx[k];
         feas7[6] = tr.getNonHolError();
     }
+    return ret;
+}
+
+int ref_alm_solve(const ref_params_t *p, const double *cells, const int *voxel_num, const double *origin, const double *max_boundary,
+                  double xy_res, double yaw_res, int N, int M, const double *bnd18, double total_time, const double *inner_xy,
+                  const double *inner_yaw, int scaling_only, double *c_xy, double *c_yaw, double *piece_T, double *lambda, double *mu, double *hx,
+                  double *gx, double *scale_fx, double *scale_cx, double *rho_out, double *feas7)
+{
+    (void)scaling_only;
+    void *h = ref_map_create(cells, voxel_num, origin, max_boundary, xy_res, yaw_res, p->gravity);
+    const int ret = ref_alm_solve_h(p, h, N, M, bnd18, total_time, inner_xy, inner_yaw, c_xy, c_yaw, piece_T, lambda, mu, hx, gx, scale_fx, scale_cx,
+                                    rho_out, feas7);
+    ref_map_destroy(h);
     return ret;
 }
 
