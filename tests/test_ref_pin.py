@@ -141,21 +141,26 @@ def _ref_solve(L, params, mapdata, pb, i):
     return ret, out
 
 
-@pytest.mark.parametrize("which,use_scaling", [("bumps", 1), ("bumps", 0), ("hill", 1)])
+@pytest.mark.parametrize("which,use_scaling", [("bumps", 1), ("bumps", 0), ("hill", 1), ("volcano", 0)])
 def test_reference_optimizeSE2Traj_matches_oracle_bitwise(ref, built, request, which, use_scaling):
     """ALMTrajOpt::optimizeSE2Traj compiled from the reference's alm_traj_opt.cpp (innerCallback, calConstrainCostGrad, initScaling,
     earlyExit, dual update, UnevenMap::getAllWithGrad, MINCO, L-BFGS) against oracle.cpp on the same problems: return code,
     coefficients, piece durations, multipliers, constraint values, scales and the final rho, all bit-identical."""
     import pyoracle as po
     from uneven_planner_b200 import _lib, maps, problems
-    m = request.getfixturevalue("bumps_map") if which == "bumps" else maps.get_terrain("hill")
+    from uneven_planner_b200 import configs
+    m = request.getfixturevalue("bumps_map") if which == "bumps" else maps.get_terrain(which)
     if m is None:
-        pytest.skip("hill.umap not present")
-    params = _lib.default_params()
-    params.use_scaling = use_scaling
-    if not use_scaling:
-        params.rho_T = 500.0
-    pb = problems.generate(m, 6, seed=11)
+        pytest.skip(which + ".umap not present")
+    if which == "volcano":       # BASELINE config 4: run_vocano.yaml + max_kap 0.3 + 64 samples per piece, on the volcano terrain
+        params = configs.params_for("volcano")
+        pb = problems.generate(m, 2, seed=11, **configs.gen_kwargs("volcano"))
+    else:
+        params = _lib.default_params()
+        params.use_scaling = use_scaling
+        if not use_scaling:
+            params.rho_T = 500.0
+        pb = problems.generate(m, 6, seed=11)
     om = po.OracleMap(m)
     op = po.params_from(params)
     for i in range(pb.B):
