@@ -583,23 +583,25 @@ extern "C" int ualm_map_build_device(ualm_ctx_t *c, const float *pin, int64_t np
     ualm_map_preprocess(pin, npts, ex, ey, ez, prep);
     UalmMapPrep view = prep.view(ex, ey, ez, iter_num);
     const long long total = (long long)g->voxel_num[0] * g->voxel_num[1] * g->voxel_num[2];
-    float *d_pts = nullptr; int *d_start = nullptr; float4 *d_cells = nullptr;
-    cudaEvent_t e0, e1;
-    CK(cudaMalloc(&d_pts, sizeof(float) * std::max<size_t>(prep.pts.size(), 3)));
-    CK(cudaMalloc(&d_start, sizeof(int) * prep.start.size()));
-    CK(cudaMalloc(&d_cells, sizeof(float4) * total));
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    if (!prep.pts.empty()) CK(cudaMemcpyAsync(d_pts, prep.pts.data(), sizeof(float) * prep.pts.size(), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(d_start, prep.start.data(), sizeof(int) * prep.start.size(), cudaMemcpyHostToDevice, c->stream));
-    view.pts = d_pts; view.start = d_start;
-    CK(cudaEventRecord(e0, c->stream));
-    map_build_kernel<<<(unsigned)((total + 63) / 64), 64, 0, c->stream>>>(view, *g, d_cells);
+    // scratch buffers and events are released on every exit path (CK returns on the first CUDA error)
+    struct Scratch {
+        DevBuf<float> pts; DevBuf<int> start; DevBuf<float4> cells;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        ~Scratch() { pts.release(); start.release(); cells.release(); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+    } sc;
+    CK(sc.pts.ensure(std::max<size_t>(prep.pts.size(), 3)));
+    CK(sc.start.ensure(prep.start.size()));
+    CK(sc.cells.ensure((size_t)total));
+    CK(cudaEventCreate(&sc.e0)); CK(cudaEventCreate(&sc.e1));
+    if (!prep.pts.empty()) CK(cudaMemcpyAsync(sc.pts.p, prep.pts.data(), sizeof(float) * prep.pts.size(), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(sc.start.p, prep.start.data(), sizeof(int) * prep.start.size(), cudaMemcpyHostToDevice, c->stream));
+    view.pts = sc.pts.p; view.start = sc.start.p;
+    CK(cudaEventRecord(sc.e0, c->stream));
+    map_build_kernel<<<(unsigned)((total + 63) / 64), 64, 0, c->stream>>>(view, *g, sc.cells.p);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(e1, c->stream));
-    CK(cudaMemcpyAsync(cells, d_cells, sizeof(float4) * total, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(sc.e1, c->stream));
+    CK(cudaMemcpyAsync(cells, sc.cells.p, sizeof(float4) * total, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(d_pts); cudaFree(d_start); cudaFree(d_cells);
+    if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, sc.e0, sc.e1));
     return UALM_OK;
 }
