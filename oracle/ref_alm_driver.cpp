@@ -118,6 +118,56 @@ int ref_alm_solve_h(const ref_params_t *p, void *map_handle, int N, int M, const
     return ret;
 }
 
+/* One ALMTrajOpt::calConstrainCostGrad call (alm_traj_opt.cpp:663-991) of the reference at a caller-given decision vector x =
+ * [tau | Pxy | Pyaw], multipliers, scales and rho: the object state is prepared the way optimizeSE2Traj (:179-203) and innerCallback
+ * (:284-299) prepare it, with the reference's own members and calTfromTau / MINCO_SE2::generate.  Outputs: cost, hx[S], gx[6S] and the
+ * (C, T) gradients before the adjoint. */
+int ref_alm_constrain(const ref_params_t *p, void *map_handle, int N, int M, const double *bnd18, const double *x, const double *lambda,
+                      const double *mu, const double *scale_cx, double scale_fx, double rho, double *cost, double *hx, double *gx, double *gdCxy,
+                      double *gdTxy, double *gdCyaw, double *gdTyaw)
+{
+    UnevenMap::Ptr map = *(UnevenMap::Ptr *)map_handle;
+    ALMTrajOpt opt;
+    opt.rho_T = p->rho_T; opt.rho_ter = p->rho_ter; opt.max_vel = p->max_vel; opt.max_acc_lon = p->max_acc_lon; opt.max_acc_lat = p->max_acc_lat;
+    opt.max_kap = p->max_kap; opt.min_cxi = p->min_cxi; opt.max_sig = p->max_sig; opt.use_scaling = p->use_scaling != 0; opt.rho = rho;
+    opt.beta = p->beta; opt.gamma = p->gamma; opt.epsilon_con = p->epsilon_con; opt.max_iter = p->max_iter; opt.g_epsilon = p->g_epsilon;
+    opt.min_step = p->min_step; opt.inner_max_iter = p->inner_max_iter; opt.delta = p->delta; opt.mem_size = p->mem_size; opt.past = p->past;
+    opt.int_K = p->int_K; opt.in_test = false; opt.in_debug = false;
+    opt.setEnvironment(map);
+    opt.piece_xy = N; opt.piece_yaw = M; opt.dim_T = 1;
+    opt.minco_se2.reset(N, M);
+    opt.init_xy.resize(2, 3); opt.end_xy.resize(2, 3); opt.init_yaw.resize(1, 3); opt.end_yaw.resize(1, 3);
+    for (int j = 0; j < 3; j++) for (int d = 0; d < 2; d++) { opt.init_xy(d, j) = bnd18[d + 2 * j]; opt.end_xy(d, j) = bnd18[6 + d + 2 * j]; }
+    for (int j = 0; j < 3; j++) { opt.init_yaw(0, j) = bnd18[12 + j]; opt.end_yaw(0, j) = bnd18[15 + j]; }
+    const int S = N * (p->int_K + 1);
+    opt.equal_num = S; opt.non_equal_num = 6 * S;
+    opt.hx.resize(S); opt.hx.setZero(); opt.gx.resize(6 * S); opt.gx.setZero();
+    opt.lambda.resize(S); opt.mu.resize(6 * S); opt.scale_cx.resize(7 * S);
+    for (int i = 0; i < S; i++) opt.lambda(i) = lambda[i];
+    for (int i = 0; i < 6 * S; i++) opt.mu(i) = mu[i];
+    for (int i = 0; i < 7 * S; i++) opt.scale_cx(i) = scale_cx[i];
+    opt.scale_fx = scale_fx;
+    Eigen::MatrixXd Pxy(2, N - 1), Pyaw(1, M - 1);
+    for (int j = 0; j < N - 1; j++) for (int d = 0; d < 2; d++) Pxy(d, j) = x[1 + d + 2 * (size_t)j];
+    for (int j = 0; j < M - 1; j++) Pyaw(0, j) = x[1 + 2 * (N - 1) + j];
+    Eigen::VectorXd Txy(N), Tyaw(M);
+    opt.calTfromTau(x[0], Txy);
+    opt.calTfromTau(x[0], Tyaw);
+    opt.minco_se2.generate(opt.init_xy, opt.end_xy, Pxy, Txy, opt.init_yaw, opt.end_yaw, Pyaw, Tyaw);
+    double c = 0.0;
+    Eigen::MatrixXd gCxy, gCyaw;
+    Eigen::VectorXd gTxy, gTyaw;
+    opt.calConstrainCostGrad(c, gCxy, gTxy, gCyaw, gTyaw);
+    *cost = c;
+    for (int i = 0; i < S; i++) hx[i] = opt.hx(i);
+    for (int i = 0; i < 6 * S; i++) gx[i] = opt.gx(i);
+    for (int d = 0; d < 2; d++) for (int i = 0; i < 6 * N; i++) gdCxy[i + (size_t)d * 6 * N] = gCxy(i, d);
+    for (int i = 0; i < N; i++) gdTxy[i] = gTxy(i);
+    for (int i = 0; i < 6 * M; i++) gdCyaw[i] = gCyaw(i, 0);
+    for (int i = 0; i < M; i++) gdTyaw[i] = gTyaw(i);
+    return 0;
+}
+
 int ref_alm_solve(const ref_params_t *p, const double *cells, const int *voxel_num, const double *origin, const double *max_boundary,
                   double xy_res, double yaw_res, int N, int M, const double *bnd18, double total_time, const double *inner_xy,
                   const double *inner_yaw, int scaling_only, double *c_xy, double *c_yaw, double *piece_T, double *lambda, double *mu, double *hx,

@@ -283,3 +283,48 @@ def test_mpc_side_minco_resolve_matches_oracle_bitwise(ref, orc, built, bumps_ma
             assert np.array_equal(c_mpc, c_orc)
             # the re-solved spline interpolates the same waypoints; it deviates from the back-end spline near the ends only
             assert np.allclose(c_mpc.reshape(Dim, 6 * P_)[:, 0::6], start, atol=1e-9)
+
+
+@pytest.mark.parametrize("use_scaling", [1, 0])
+def test_reference_calConstrainCostGrad_matches_oracle_bitwise(ref, built, bumps_map, use_scaling):
+    """Kernel-level pin: ONE ALMTrajOpt::calConstrainCostGrad call of the reference (alm_traj_opt.cpp:663-991) at random multipliers,
+    scales and rho -- so both branches of every inequality (active / inactive) are taken -- against orc_eval: penalty cost, hx, gx and
+    the coefficient / time gradients before the adjoint, bit for bit."""
+    import pyoracle as po
+    from uneven_planner_b200 import _lib, problems
+    params = _lib.default_params()
+    params.use_scaling = use_scaling
+    pb = problems.generate(bumps_map, 4, seed=31)
+    op, om = po.params_from(params), po.OracleMap(bumps_map)
+    g = bumps_map.geom
+    rp = RefParams()
+    for n, _ in RefParams._fields_:
+        setattr(rp, n, getattr(params, n))
+    cells = np.ascontiguousarray(bumps_map.cells, dtype=np.float64)
+    vn = (C.c_int * 3)(*g.voxel_num); org = (C.c_double * 3)(*g.origin); mxb = (C.c_double * 3)(*g.max_boundary)
+    ref.ref_map_create.restype = C.c_void_p
+    ref.ref_map_destroy.argtypes = [C.c_void_p]
+    h = C.c_void_p(ref.ref_map_create(P(cells), vn, org, mxb, C.c_double(g.xy_resolution), C.c_double(g.yaw_resolution), C.c_double(params.gravity)))
+    rng = np.random.default_rng(5)
+    try:
+        for i in range(pb.B):
+            N, M = int(pb.N[i]), int(pb.M[i])
+            S = N * (params.int_K + 1)
+            x = pb.x0(i) + rng.normal(0, 0.02, 1 + 2 * (N - 1) + (M - 1))
+            lam = rng.normal(0, 1.0, S)
+            mu = np.maximum(rng.normal(0, 20.0, 6 * S), 0.0)                    # about half of the multipliers exactly zero, the rest large enough to activate
+            scx = rng.uniform(0.05, 1.0, 7 * S)
+            sfx, rho = float(rng.uniform(1e-6, 1.0)), float(rng.choice([1.0, 8.0, 1000.0]))
+            o = po.eval_one(op, om, pb, i, x, lam, mu, scx, sfx, rho)
+            cost = np.zeros(1); hx = np.zeros(S); gx = np.zeros(6 * S); gCxy = np.zeros(12 * N); gTxy = np.zeros(N); gCyaw = np.zeros(6 * M); gTyaw = np.zeros(M)
+            rc = ref.ref_alm_constrain(C.byref(rp), h, N, M, P(np.ascontiguousarray(pb.bnd[i])), P(np.ascontiguousarray(x)), P(lam), P(mu), P(scx),
+                                       C.c_double(sfx), C.c_double(rho), P(cost), P(hx), P(gx), P(gCxy), P(gTxy), P(gCyaw), P(gTyaw))
+            assert rc == 0
+            assert cost[0] == o["parts"][1], i
+            assert np.array_equal(hx, o["hx"]) and np.array_equal(gx, o["gx"]), i
+            assert np.array_equal(gCxy, o["gdCxy"]) and np.array_equal(gTxy, o["gdTxy"]), i
+            assert np.array_equal(gCyaw, o["gdCyaw"]) and np.array_equal(gTyaw, o["gdTyaw"]), i
+            active = (rho * gx + mu > 0)
+            assert 0.01 < active.mean() < 0.99                                   # both branches exercised
+    finally:
+        ref.ref_map_destroy(h)
