@@ -118,6 +118,17 @@ int ref_alm_solve_h(const ref_params_t *p, void *map_handle, int N, int M, const
     return ret;
 }
 
+/* UnevenMap::getAllWithGrad of the reference (uneven_map.h:318-377 -> getTerrainWithGradI :258-315, posToIndex / boundIndex / isInMap):
+ * values[7], grads[21] (row-major 7 x 3) */
+void ref_map_query(void *map_handle, const double *pos, double *values, double *grads)
+{
+    UnevenMap::Ptr map = *(UnevenMap::Ptr *)map_handle;
+    std::vector<double> v;
+    std::vector<Eigen::Vector3d> g;
+    map->getAllWithGrad(Eigen::Vector3d(pos[0], pos[1], pos[2]), v, g);
+    for (int i = 0; i < 7; i++) { values[i] = v[i]; for (int k = 0; k < 3; k++) grads[3 * i + k] = g[i](k); }
+}
+
 /* One ALMTrajOpt::calConstrainCostGrad call (alm_traj_opt.cpp:663-991) of the reference at a caller-given decision vector x =
  * [tau | Pxy | Pyaw], multipliers, scales and rho: the object state is prepared the way optimizeSE2Traj (:179-203) and innerCallback
  * (:284-299) prepare it, with the reference's own members and calTfromTau / MINCO_SE2::generate.  Outputs: cost, hx[S], gx[6S] and the

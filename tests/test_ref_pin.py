@@ -328,3 +328,34 @@ def test_reference_calConstrainCostGrad_matches_oracle_bitwise(ref, built, bumps
             assert 0.01 < active.mean() < 0.99                                   # both branches exercised
     finally:
         ref.ref_map_destroy(h)
+
+
+def test_reference_map_query_matches_oracle_bitwise(ref, built, request):
+    """UnevenMap::getAllWithGrad of the reference (trilinear SE(2) interpolation with analytic gradients, yaw seam, out-of-map
+    zeros; uneven_map.h:258-377) against orc_map_query at seeded positions, including the map border and the yaw wrap."""
+    import pyoracle as po
+    from uneven_planner_b200 import maps
+    for m in (request.getfixturevalue("bumps_map"), maps.get_terrain("hill")):
+        if m is None:
+            continue
+        g = m.geom
+        om = po.OracleMap(m)
+        cells = np.ascontiguousarray(m.cells, dtype=np.float64)
+        vn = (C.c_int * 3)(*g.voxel_num); org = (C.c_double * 3)(*g.origin); mxb = (C.c_double * 3)(*g.max_boundary)
+        ref.ref_map_create.restype = C.c_void_p
+        ref.ref_map_destroy.argtypes = [C.c_void_p]
+        ref.ref_map_query.argtypes = [C.c_void_p, dp, dp, dp]
+        po.lib().orc_map_query.argtypes = [C.c_void_p, dp, dp, dp]
+        h = C.c_void_p(ref.ref_map_create(P(cells), vn, org, mxb, C.c_double(g.xy_resolution), C.c_double(g.yaw_resolution), C.c_double(9.81)))
+        rng = np.random.default_rng(17)
+        pts = np.column_stack([rng.uniform(-5.2, 5.2, 400), rng.uniform(-5.2, 5.2, 400), rng.uniform(-np.pi, np.pi, 400)])
+        pts = np.vstack([pts, [[0.0, 0.0, np.pi - 1e-6], [0.0, 0.0, -np.pi + 1e-6], [4.99, -4.99, 3.1], [-5.0, 0.0, 0.0], [2.5, 2.5, 3.14159]]])
+        try:
+            for pnt in pts:
+                pnt = np.ascontiguousarray(pnt)
+                vr = np.zeros(7); gr = np.zeros(21); vo = np.zeros(7); go = np.zeros(21)
+                ref.ref_map_query(h, P(pnt), P(vr), P(gr))
+                po.lib().orc_map_query(C.addressof(om.c), P(pnt), P(vo), P(go))
+                assert np.array_equal(vr, vo) and np.array_equal(gr, go), pnt
+        finally:
+            ref.ref_map_destroy(h)
