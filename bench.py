@@ -1,14 +1,18 @@
 #!/usr/bin/env python
 """bench.py -- converged trajectories/sec of the batched MINCO/ALM optimizer (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores (oracle)
+    python bench.py --gpus N --steps K --warmup W [--config 2|3|4|5]   # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...            # the reference algorithm on the host CPU cores (oracle)
 
-A "step" is one pass of the hot path (B independent optimizeSE2Traj solves) over one batch of synthetic problems:
-BASELINE.json configs[1], B = 1024 random SE(2) start/goal pairs per GPU on the hill UnevenMap (weak scaling: config 3's
-8192 problems on 8 GPUs is the same 1024 per GPU).  `value` is measured with the problems resident in HBM; `e2e` goes
-through the host-buffer C-ABI call (ualm_solve_batch) with pinned host inputs, H2D and D2H inside the timed region.
-One JSON line on stdout (rank 0).
+A "step" is one pass of the hot path (B independent optimizeSE2Traj solves) over one batch of synthetic problems.  The default
+workload is BASELINE.json configs[1] (the configuration the metric is quoted on): B = 1024 random SE(2) start/goal pairs per GPU
+on the hill UnevenMap (weak scaling).  --config 3: 8192 problems on the desert map, STRONG scaling (8192 / N per GPU);
+--config 4: volcano, max_kap 0.3, 64 samples per piece, B = 1024; --config 5: forest (run_forest.yaml), B = 4096.
+
+The steps are PIPELINED over `--depth` lanes of one context (include/ualm.h: several batches in flight): step s+1 is launched
+while the slowest trajectories of step s still run, and every step's results are complete inside the timed region.  `value` is
+measured with the problems resident in HBM; `e2e` goes through the host-buffer C-ABI calls (ualm_submit_batch / ualm_wait_batch)
+with pinned host inputs, H2D and D2H inside the timed region.  One JSON line on stdout (rank 0).
 """
 import argparse
 import ctypes as C
@@ -17,7 +21,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -27,6 +30,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "converged trajectories/sec (batch MINCO)"
 UNIT = "traj/s"
+ROUND = "r02"
 
 
 def load_peaks():
@@ -37,11 +41,26 @@ def load_peaks():
 
 
 def load_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this round."""
-    p = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from THIS round's committed ncu --set full capture
+    (profiles/traffic_r02.json names the command and the problem set it was taken on); absent -> null in the line."""
+    p = os.path.join(ROOT, "profiles", "traffic_%s.json" % ROUND)
     if os.path.exists(p):
         return json.load(open(p))
     return {}
+
+
+def usable_cores():
+    """host threads this process may actually use: scheduler affinity, capped by the cgroup CPU quota"""
+    n = len(os.sched_getaffinity(0))
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        pass
+    eff = n if quota is None else max(1, min(n, int(quota + 0.5)))
+    return eff, {"os_cpu_count": os.cpu_count(), "sched_affinity": n, "cgroup_cpu_quota": quota}
 
 
 def get_map(name):
@@ -51,6 +70,19 @@ def get_map(name):
         return m, name
     # no .umap travelled: clearly labelled analytic stand-in (not one of the reference's terrains)
     return maps.synthetic_terrain("bumps", seed=0), "synthetic-bumps (maps_built/%s.umap missing)" % name
+
+
+def workload(args, world):
+    """(terrain, params, generator kwargs, per-GPU batch, total batch, scaling, description) of the selected BASELINE config"""
+    from uneven_planner_b200 import configs
+    cfg = configs.BASELINE_CONFIGS[args.config]
+    terrain = args.map or cfg["terrain"]
+    total = (args.batch or cfg["batch"]) * (world if cfg["scaling"] == "weak" else 1)
+    params = configs.params_for(terrain)
+    desc = "configs[%d]: %d random SE(2) start/goal pairs%s on the %s UnevenMap, %s parameters%s" % (
+        args.config - 1, total if cfg["scaling"] == "strong" else total // world, "" if cfg["scaling"] == "strong" else " per GPU", terrain,
+        configs.YAML[terrain], "".join(", %s=%s" % kv for kv in configs.CONFIG_OVERRIDES.get(terrain, {}).items()))
+    return terrain, params, configs.gen_kwargs(terrain), total, cfg["scaling"], desc
 
 
 class ClockSampler:
@@ -111,7 +143,6 @@ def time_reference_build(m, params, pb, threads, nprob=16):
     """oracle/_ref/libref.so = the reference's own alm_traj_opt.cpp compiled against oracle/shim: timed on a few
     problems for the record.  It is bit-identical to the oracle port but several times slower (the shim evaluates every Eigen
     expression into heap temporaries), so the port stays the quoted CPU baseline."""
-    import ctypes as C
     path = os.path.join(ROOT, "oracle", "_ref", "libref.so")
     if not os.path.exists(path):
         return {"unavailable": "oracle/_ref/libref.so not built (needs the reference sources at build time)"}
@@ -167,38 +198,51 @@ def time_reference_build(m, params, pb, threads, nprob=16):
             "note": "bit-identical to the oracle port (tests/test_ref_pin.py); slower only because the Eigen stand-in is eager"}
 
 
+def cpu_parallel_run(po, params, m, pb, threads):
+    """the oracle on `threads` host threads over pb: (converged/s, seconds, converged count, mean in-thread seconds per trajectory)"""
+    t0 = time.perf_counter()
+    out = po.solve_batch(po.params_from(params), po.OracleMap(m), pb, threads=threads)
+    dt = time.perf_counter() - t0
+    conv = sum(1 for r in out if r[0].ret_code == 0)
+    return conv / dt, dt, conv, float(np.mean([r[0].t_total for r in out]))
+
+
 def run_reference(args):
-    """--impl reference: the reference algorithm (CPU oracle, oracle/oracle.cpp) on all host cores.  Rank 0 only."""
+    """--impl reference: the reference algorithm (CPU oracle port of alm_traj_opt.cpp, oracle/oracle.cpp) on all usable host cores, on the
+    SAME workload as the CUDA arm (same terrain, parameters, seed; the whole batch per step unless --ref-sample bounds it).  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle as po
-    from uneven_planner_b200 import _lib, problems
+    from uneven_planner_b200 import problems
     po.build()
-    m, mname = get_map(args.map)
-    params = _lib.default_params()
-    threads = os.cpu_count() or 1
-    sample = min(args.ref_sample, args.batch * max(args.gpus, 1))
-    pb = problems.generate(m, args.batch * max(args.gpus, 1), seed=args.seed).select(np.arange(sample))
-    op, om = po.params_from(params), po.OracleMap(m)
+    world = max(args.gpus, 1)
+    terrain, params, gen, total, scaling, desc = workload(args, world)
+    m, mname = get_map(terrain)
+    threads, core_info = usable_cores()
+    pb_all = problems.generate(m, total, seed=args.seed, **gen)
+    sample = total if args.ref_sample <= 0 else min(args.ref_sample, total)
+    pb = pb_all if sample == total else pb_all.select(np.arange(sample))
     for _ in range(min(args.warmup, 1)):
-        po.solve_batch(op, om, pb.select(np.arange(min(threads, sample))), threads=threads)
+        po.solve_batch(po.params_from(params), po.OracleMap(m), pb.select(np.arange(min(threads, sample))), threads=threads)
     t0 = time.perf_counter()
     conv = 0
     for _ in range(args.steps):
-        out = po.solve_batch(op, om, pb, threads=threads)
-        conv += sum(1 for r in out if r[0].ret_code == 0)
+        v, _, c, _ = cpu_parallel_run(po, params, m, pb, threads)
+        conv += c
     dt = time.perf_counter() - t0
     val = conv / dt
     ref_build = time_reference_build(m, params, pb, threads)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "configs[1]: random SE(2) start/goal pairs on %s UnevenMap, run_hill.yaml parameters" % mname,
-                       "batch_per_step": sample, "note": "bounded sample of the batch per step, all host threads"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": "%d of the %d problems of the workload per step, %d host threads (one optimizer per thread)" % (sample, args.batch * max(args.gpus, 1), threads)},
+            "config": {"workload": desc.replace(terrain + " UnevenMap", mname + " UnevenMap"), "global_batch": total, "batch_per_step": sample,
+                       "same_config": sample == total,
+                       "note": ("the whole batch per step" if sample == total else "a bounded sample of the batch per step: throughput is per trajectory, so the ratio stands") +
+                               ", all usable host threads; inputs generated by libualm's HOST tools (Dubins + PlanManager resampler, no GPU code), the solve is oracle/liboracle.so"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "cores_detail": core_info, "kind": "port",
+                             "sample": "%d of the %d problems of the workload per step, %d host threads (one optimizer per thread)" % (sample, total, threads)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "reference_build": ref_build}
     print(json.dumps(line))
@@ -207,22 +251,24 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--batch", type=int, default=1024, help="problems per GPU per step")
-    ap.add_argument("--map", default="hill")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json config number (1-based)")
+    ap.add_argument("--batch", type=int, default=0, help="override: problems per GPU per step (weak configs) / in total (config 3)")
+    ap.add_argument("--map", default="", help="override the config's terrain")
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--ref-sample", type=int, default=512, dest="ref_sample")
+    ap.add_argument("--depth", type=int, default=3, help="batches in flight (lanes); 1 = every step waits for its slowest trajectory")
+    ap.add_argument("--ref-sample", type=int, default=0, dest="ref_sample", help="reference arm / cpu_baseline: problems per step (0 = the whole batch, bounded at 1024 for cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--big-batch", type=int, default=4096, dest="big_batch", help="extra single-launch throughput datapoint (0 = skip)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the un-pipelined latency datapoint and the penalty-kernel timing")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     import torch
     import torch.distributed as dist
-    from uneven_planner_b200 import _lib, api, problems, distributed as D
+    from uneven_planner_b200 import api, problems, distributed as D
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -234,53 +280,69 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    m, mname = get_map(args.map)
-    params = _lib.default_params()
+    terrain, params, gen, Btot, scaling, desc = workload(args, world)
+    m, mname = get_map(terrain)
     K = params.int_K
-    Btot = args.batch * world
-    pb_all = problems.generate(m, Btot, seed=args.seed)          # identical on every rank (counter-based RNG)
+    pb_all = problems.generate(m, Btot, seed=args.seed, **gen)          # identical on every rank (counter-based RNG)
     shards = D.shard_indices(pb_all.nsamples(K), world)
     pb = pb_all.select(shards[rank])
     stride = D.record_stride(pb_all.N.max(), pb_all.M.max())
+    depth = max(1, min(args.depth, 8))
 
     opt = api.BatchALMTrajOpt(device=local_rank).init(params).set_environment(m)
-    opt.set_stream(torch.cuda.current_stream().cuda_stream)
-    records = torch.zeros((pb.B, stride), dtype=torch.float64, device=dev)
-
-    def step_resident():
-        opt.solve_resident()
-        opt.pack_records(records.data_ptr(), stride)
-        return D.all_gather_records(records, shards, rank, world) if world > 1 else records
+    records = [torch.zeros((pb.B, stride), dtype=torch.float64, device=dev) for _ in range(depth)]
+    full = [None]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- value: inputs resident in HBM ----------------
-    opt.upload(pb)
-    for _ in range(args.warmup):
-        full = step_resident()
+    def collect(lane):
+        """complete the step that ran on `lane`: its solve + record packing are done (host wait on the lane), then the NCCL all-gather"""
+        opt.select_lane(lane)
+        opt.sync()
+        full[0] = D.all_gather_records(records[lane], shards, rank, world) if world > 1 else records[lane]
+
+    def run_steps(nsteps):
+        """nsteps passes over the resident batch, `depth` of them in flight; every step is complete when this returns"""
+        for s in range(nsteps):
+            lane = s % depth
+            if s >= depth:
+                collect(lane)
+            opt.select_lane(lane)
+            if s == 0:
+                opt.mark_begin()
+            opt.solve_resident()
+            opt.pack_records(records[lane].data_ptr(), stride, wait=False)
+        for s in range(max(0, nsteps - depth), nsteps):
+            collect(s % depth)
+        opt.select_lane(0)
+
+    # ---------------- value: inputs resident in HBM (the batch uploaded once per lane), steps pipelined over the lanes ----------------
+    for lane in range(depth):
+        opt.select_lane(lane)
+        opt.upload(pb)
+    run_steps(max(args.warmup, 1))
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        full = step_resident()
-        kernel_ms.append(None)
+    run_steps(args.steps)
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
+    lanes_ms = opt.mark_end()                                            # CUDA events on the lanes' own streams: first launch -> last solve done
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms = float(tms.item())
-    solve_ms, launches = opt.last_solve_ms()                       # CUDA events around the last solve kernel on its stream
+    opt.select_lane(0)
+    _, launches = opt.last_solve_ms()
     res, cxy, cyaw = opt.download()
     conv_local = sum(1 for r in res if r.ret_code == 0)
     # independent quality check of the solved batch (outside the timed region): the reference's post-solve scan
@@ -295,69 +357,78 @@ def main():
                "limits": "max |vx|, |ax|, |ay|, |curvature|, sigma <= 1.05 x limit and min cos(xi) >= limit / 1.05 over 0.01 s samples "
                          "(ualm_feasibility_batch; rank 0's shard)",
                "median_nonholonomic_error_per_sample": float(np.median(feas[okc, 6] / np.maximum(feas[okc, 7], 1.0))) if okc.any() else None}
-    full_h = full.cpu().numpy()
+    full_h = full[0].cpu().numpy()
     conv_total = int((full_h[:, 0] == 0).sum()) if world > 1 else conv_local
     value = conv_total * args.steps / (ms * 1e-3)
 
-    # ---------------- e2e: host buffers through the C-ABI call, H2D + D2H inside the timed region ----------------
+    # ---------------- e2e: host buffers through the C-ABI calls, H2D + D2H inside the timed region, `depth` batches in flight ----------------
     def pinned(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         return t, t.numpy()
     keep = [pinned(a) for a in (pb.N.astype(np.int32), pb.M.astype(np.int32), pb.bnd, pb.total_time, pb.inner_xy, pb.inner_yaw)]
-    hN, hM, hbnd, hT, hxy, hyaw = [k[1] for k in keep]
-    out_res = (api.Result * pb.B)()
-    o_cxy_t, o_cxy = pinned(np.zeros(int(12 * pb.N.astype(np.int64).sum())))
-    o_cyaw_t, o_cyaw = pinned(np.zeros(int(6 * pb.M.astype(np.int64).sum())))
-    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    host_in = [k[1] for k in keep]
+    outs = []
+    for _ in range(depth):
+        o_cxy_t, o_cxy = pinned(np.zeros(int(12 * pb.N.astype(np.int64).sum())))
+        o_cyaw_t, o_cyaw = pinned(np.zeros(int(6 * pb.M.astype(np.int64).sum())))
+        outs.append(((api.Result * pb.B)(), o_cxy, o_cyaw, o_cxy_t, o_cyaw_t))
 
-    def step_e2e():
-        rc = opt.L.ualm_solve_batch(opt.h, pb.B, hN.ctypes.data_as(ip), hM.ctypes.data_as(ip), hbnd.ctypes.data_as(dp), hT.ctypes.data_as(dp),
-                                    hxy.ctypes.data_as(dp), hyaw.ctypes.data_as(dp), out_res, o_cxy.ctypes.data_as(dp), o_cyaw.ctypes.data_as(dp))
-        if rc != 0:
-            raise RuntimeError(opt.L.ualm_last_error())
-    e2e_steps = max(1, min(args.steps, 3))
-    step_e2e()
+    def run_e2e(nsteps):
+        tickets, conv = [], 0
+        for s in range(nsteps):
+            if s >= depth:
+                r, _, _ = opt.wait(tickets[s - depth], out=outs[s % depth][:3])
+                conv += sum(1 for q in r if q.ret_code == 0)
+            tickets.append(opt.submit(pb, depth=depth, host=host_in))
+        for s in range(max(0, nsteps - depth), nsteps):
+            r, _, _ = opt.wait(tickets[s], out=outs[s % depth][:3])
+            conv += sum(1 for q in r if q.ret_code == 0)
+        return conv
+    e2e_steps = max(depth, min(args.steps, 2 * depth))
+    run_e2e(depth)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
+    conv_e2e = run_e2e(e2e_steps)
     barrier()
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    te = torch.tensor([e2e_s, float(conv_e2e)], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = conv_total * e2e_steps / float(te.item())
-    h2d = int(sum(a.nbytes for a in (hN, hM, hbnd, hT, hxy, hyaw)))
-    d2h = int(C.sizeof(api.Result) * pb.B + o_cxy.nbytes + o_cyaw.nbytes)
+        tmax = te.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(te, op=dist.ReduceOp.SUM)
+        e2e_s, conv_e2e = float(tmax[0].item()), float(te[1].item())
+    e2e_value = conv_e2e / e2e_s
+    h2d = int(sum(a.nbytes for a in host_in))
+    d2h = int(C.sizeof(api.Result) * pb.B + outs[0][1].nbytes + outs[0][2].nbytes)
 
-    # ---------------- roofline of the dominant kernel (solve_kernel) ----------------
+    # ---------------- roofline of the dominant kernel (solve_kernel) over the timed region ----------------
     peak, peak_src = load_peaks()
     pen_b, lb_b, mc_b = algorithmic_bytes(pb, res, K)
     alg = pen_b + lb_b + mc_b
-    achieved = alg / (solve_ms * 1e-3) / 1e9
+    step_ms = lanes_ms / args.steps                                       # the kernels of consecutive steps overlap: average per step
+    achieved = alg / (step_ms * 1e-3) / 1e9
     traffic = load_traffic()
-    roof = {"kernel": "ualm::solve_kernel (whole ALM/L-BFGS solve of the batch: a warp group per trajectory, one launch per size class on concurrent streams)", "bound": "hbm", "achieved": achieved, "peak": peak,
-            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic.get("solve_kernel_bytes_per_launch_b1024") if args.batch == 1024 else None,
-            "peak_source": peak_src, "kernel_ms": solve_ms,
+    roof = {"kernel": "ualm::solve_kernel (whole ALM/L-BFGS solve of the batch: a warp group per trajectory, one launch per size class on concurrent "
+                      "streams, %d batches in flight)" % depth, "bound": "hbm", "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic.get("solve_kernel_bytes_per_launch_config%d" % args.config),
+            "traffic_source": traffic.get("source"),
+            "peak_source": peak_src, "kernel_ms": step_ms,
             "algorithmic_bytes": {"penalty": pen_b, "lbfgs": lb_b, "minco_io": mc_b},
-            "note": "latency-bound: bit-reproducible fp64 dependent chains, a warp group per trajectory (DESIGN.md section 4)"}
-    pms, pbytes = opt.time_penalty_kernel(5)
-    roof_pen = {"kernel": "ualm::penalty_only_kernel (calConstrainCostGrad samples + accumulation, 1 evaluation per trajectory)",
-                "bound": "hbm", "achieved": pbytes / (pms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": pbytes / (pms * 1e-3) / 1e9 / peak,
-                "traffic": traffic.get("penalty_only_kernel_bytes_per_launch_b1024") if args.batch == 1024 else None, "kernel_ms": pms}
-
-    # ---------------- throughput with the GPU kept full: 4x the batch in one launch (single GPU only, outside the timed region)
-    big = None
-    if world == 1 and args.big_batch > 0:
-        pbb = problems.generate(m, args.big_batch, seed=args.seed + 1)
-        opt.upload(pbb)
+            "note": "latency-bound: bit-reproducible fp64 dependent chains, a warp group per trajectory (DESIGN.md section 4); kernel_ms = CUDA-event time "
+                    "of the timed region on the lanes' own streams / steps"}
+    extras = None
+    roof_pen = None
+    if not args.no_extras:
+        # one un-pipelined solve (latency of a batch = its slowest trajectory) and the penalty phase alone, outside the timed region
+        opt.select_lane(0)
         opt.solve_resident(); opt.sync()
-        bms, _ = opt.last_solve_ms()
-        rb, _, _ = opt.download()
-        big = {"batch": args.big_batch, "kernel_ms": bms, "solved_per_s": args.big_batch / bms * 1e3,
-               "converged_per_s": sum(1 for r in rb if r.ret_code == 0) / bms * 1e3}
-        opt.upload(pb)
+        single_ms, _ = opt.last_solve_ms()
+        extras = {"single_batch_ms": single_ms, "single_batch_converged_per_s": conv_local / single_ms * 1e3,
+                  "note": "one batch alone on the device (depth 1): bounded by its slowest trajectory"}
+        pms, pbytes = opt.time_penalty_kernel(5)
+        roof_pen = {"kernel": "ualm::penalty_only_kernel (calConstrainCostGrad samples + accumulation, 1 evaluation per trajectory)",
+                    "bound": "hbm", "achieved": pbytes / (pms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": pbytes / (pms * 1e-3) / 1e9 / peak,
+                    "traffic": traffic.get("penalty_only_kernel_bytes_per_launch_config%d" % args.config), "kernel_ms": pms}
 
     # ---------------- CPU baseline on this box's host cores (rank 0, bounded sample) ----------------
     cpu = None
@@ -365,36 +436,47 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import pyoracle as po
         po.build()
-        threads = os.cpu_count() or 1
-        sample = min(args.ref_sample, pb_all.B)
+        threads, core_info = usable_cores()
+        sample = min(args.ref_sample if args.ref_sample > 0 else 1024, pb_all.B)
         sub = pb_all.select(np.arange(sample))
-        t0 = time.perf_counter()
-        out = po.solve_batch(po.params_from(params), po.OracleMap(m), sub, threads=threads)
-        dt = time.perf_counter() - t0
-        cpu_conv = sum(1 for r in out if r[0].ret_code == 0)
-        one = np.mean([r[0].t_total for r in out])
+        cpu_v, dt, cpu_conv, one = cpu_parallel_run(po, params, m, sub, threads)
         # the reference's own operating mode: one optimizer on one otherwise idle core ("1 thread, per-trajectory ms")
         n1 = min(8, sample)
         t1 = time.perf_counter()
-        po.solve_batch(po.params_from(params), po.OracleMap(m), pb_all.select(np.arange(n1)), threads=1)
+        o1 = po.solve_batch(po.params_from(params), po.OracleMap(m), pb_all.select(np.arange(n1)), threads=1)
         one_idle = (time.perf_counter() - t1) / n1
-        cpu = {"value": cpu_conv / dt, "unit": UNIT, "cores": threads, "kind": "port",
+        conv1 = sum(1 for r in o1 if r[0].ret_code == 0) / max(n1, 1)
+        solved_per_s = sample / dt
+        cpu = {"value": cpu_v, "unit": UNIT, "cores": threads, "cores_detail": core_info, "kind": "port",
                "single_thread_ms_per_trajectory": one_idle * 1e3,
-               "sample": "first %d problems of the workload, %d host threads (one optimizer instance per thread); mean %.1f ms/trajectory inside a "
-                         "thread under that load, %.1f ms/trajectory for the first %d problems on one thread of the idle host" % (sample, threads, one * 1e3, one_idle * 1e3, n1)}
+               "parallel_efficiency": solved_per_s / (threads / one_idle) if one_idle > 0 else None,
+               "sample": "first %d problems of the workload, %d host threads (one optimizer instance per thread), %.1f s; mean %.1f ms/trajectory inside a "
+                         "thread under that load, %.1f ms/trajectory for the first %d problems on one thread of the idle host (converged fraction %.2f)"
+                         % (sample, threads, dt, one * 1e3, one_idle * 1e3, n1, conv1)}
 
     if rank == 0:
+        ev = np.array([r.n_evals for r in res])
+        slow = int(np.argmax(ev))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": "configs[1]: batch=%d random SE(2) start/goal pairs per GPU on %s UnevenMap, run_hill.yaml parameters" % (args.batch, mname),
+                "config": {"workload": desc.replace(terrain + " UnevenMap", mname + " UnevenMap"),
                            "global_batch": Btot, "parallelism": "dp%d (independent shards, final NCCL all-gather of result records)" % world,
-                           "converged_per_step": conv_total, "solved_per_step": Btot,
-                           "l2": "per-step working set (L-BFGS history + sample scratch, %.0f MB) exceeds the 126 MB L2; the 41 MB map is reused within a step" % ((lb_b and (8.0 * 2 * params.mem_size * float(pb.nvar().sum())) / 1e6))},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+                           "converged_per_step": conv_total, "solved_per_step": Btot, "batches_in_flight": depth,
+                           "pipelining": "steps are launched on %d lanes round robin; a lane is re-used only after its previous step is complete; all %d steps "
+                                         "are complete (results packed%s) inside the timed region" % (depth, args.steps, ", all-gathered" if world > 1 else ""),
+                           "l2": "no flush needed: per-step working set (L-BFGS history + sample scratch, %.0f MB per lane) exceeds the 126 MB L2; the 41 MB map is "
+                                 "reused within a step" % ((8.0 * 2 * params.mem_size * float(pb.nvar().sum())) / 1e6)},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                        "api": "ualm_submit_batch / ualm_wait_batch, pinned host buffers, %d batches in flight" % depth},
                 "gpu_launches": int((launches + 1) * args.steps),
-                "clocks": clocks, "roofline": roof, "roofline_penalty": roof_pen, "cpu_baseline": cpu, "large_batch": big, "quality": quality,
-                "work": {"evals_per_step": int(sum(r.n_evals for r in res)), "lbfgs_iters_per_step": int(sum(r.n_lbfgs_iters for r in res)), "rank0_batch": pb.B}}
+                "clocks": clocks, "roofline": roof, "roofline_penalty": roof_pen, "cpu_baseline": cpu, "latency": extras, "quality": quality,
+                "work": {"evals_per_step": int(ev.sum()), "lbfgs_iters_per_step": int(sum(r.n_lbfgs_iters for r in res)), "rank0_batch": pb.B,
+                         "evals_per_trajectory": {"mean": float(ev.mean()), "p50": float(np.percentile(ev, 50)), "p99": float(np.percentile(ev, 99)),
+                                                  "second_max": int(np.sort(ev)[-2]) if len(ev) > 1 else int(ev.max()), "max": int(ev.max())},
+                         "slowest_trajectory": {"n_evals": int(ev[slow]), "N": int(pb.N[slow]), "ret_code": int(res[slow].ret_code),
+                                                "outer_iters": int(res[slow].outer_iters)},
+                         "lanes_event_ms_per_step": step_ms}}
         print(json.dumps(line))
     opt.close()
     if world > 1:

@@ -60,7 +60,9 @@ void ualm_map_geometry(double map_size_x, double map_size_y, double xy_resolutio
 /* ---- per-problem result record (what the reference prints / returns: alm_traj_opt.cpp:176,252,267,272-273;
  *      alm_traj_opt.h:142) ---- */
 typedef struct {
-    int32_t ret_code;        /* 0 converged / 1 L-BFGS hard error / 2 ALM max_iter */
+    int32_t ret_code;        /* 0 converged / 1 L-BFGS hard error / 2 ALM max_iter (the reference's codes); UALM_ELIMIT (-4): this
+                                problem exceeds the compiled limits (N <= 64, M <= 128) and was not solved -- the rest of its
+                                batch is unaffected */
     int32_t outer_iters;
     int32_t n_evals;         /* cost+gradient evaluations */
     int32_t n_lbfgs_iters;   /* accepted line searches */
@@ -69,21 +71,35 @@ typedef struct {
     int32_t sum_bound;       /* sum over L-BFGS iterations of the history depth used (bytes accounting) */
     int32_t reserved;
     double  inner_cost, jerk_cost, total_T, res_h, res_g, scale_fx, rho_final;
+    double  piece_T_xy, piece_T_yaw;   /* the uniform piece durations getTraj() carries: T1(i) of the LAST evaluation
+                                          (alm_traj_opt.h:257-261, se2traj.hpp:682-695); total_T is their N-fold sum */
 } ualm_result_t;
 
 typedef struct ualm_ctx ualm_ctx_t;
 
-/* precision: 64 = parity path (double), 32 = throughput path (float).  device = CUDA ordinal. */
+/* precision: 64 = parity path (IEEE double, bit-identical to the CPU oracle / the reference sources); 65 = "fast64", the
+ * throughput path in double (re-associated reductions, FMA, prefactored MINCO system: not bit-reproducible); 32 = the
+ * throughput path in float.  device = CUDA ordinal. */
 int ualm_create(ualm_ctx_t **ctx, int device, int precision);
 int ualm_destroy(ualm_ctx_t *ctx);
 const char *ualm_last_error(void);
-/* run all work of this context on a caller-owned CUDA stream (e.g. torch's current stream); NULL restores the
- * context's own stream */
+/* Run the work of the selected lane on a caller-owned CUDA stream.  The handle is taken literally: NULL is the legacy
+ * default stream (torch.cuda.current_stream().cuda_stream == 0 when torch runs on its default stream).  ualm_reset_stream
+ * goes back to the lane's own non-blocking stream.  ualm_solve_resident is asynchronous on that stream: follow it with
+ * ualm_sync (or a stream-ordered consumer on the SAME stream) before touching its outputs. */
 int ualm_set_stream(ualm_ctx_t *ctx, void *cuda_stream);
-int ualm_set_params(ualm_ctx_t *ctx, const ualm_params_t *p);                    /* ALMTrajOpt::init */
+int ualm_reset_stream(ualm_ctx_t *ctx);
+/* ALMTrajOpt::init.  int_K, mem_size and past are baked into uploaded batches: a parameter change invalidates every resident
+ * batch (upload again before the next solve / eval); it is refused while a submitted batch is in flight. */
+int ualm_set_params(ualm_ctx_t *ctx, const ualm_params_t *p);
 /* cells: host, [X][Y][Yaw][4] float {z, sigma, zbx, zby}, address x*Y*Yaw + y*Yaw + yaw (uneven_map.h:427-435).
  * One-time upload (replaces setEnvironment; the reference's map_buffer is private, uneven_map.h:91). */
 int ualm_set_map(ualm_ctx_t *ctx, const ualm_map_geom_t *g, const float *cells);
+/* The reference's own grid: UnevenMap::map_buffer is RXS2 {double z, sigma; Vector2d zb} (uneven_map.h:36-64), i.e. 4 doubles
+ * per cell in the same address order.  repack_to_float = 0 keeps the doubles on the device (82 MB for 200x200x64: bit parity
+ * for maps built in-process by the reference); != 0 rounds them to the float4 grid of ualm_set_map (41 MB, what a map read
+ * back from this repo's .umap file or from the reference's 6-digit CSV cache holds anyway). */
+int ualm_set_map_f64(ualm_ctx_t *ctx, const ualm_map_geom_t *g, const double *cells, int repack_to_float);
 
 /* ---- batch solve = B independent optimizeSE2Traj calls ----
  * Ragged inputs are packed back to back in problem order: inner_xy has sum 2(N_b-1) doubles,
@@ -104,10 +120,38 @@ int ualm_download(ualm_ctx_t *ctx, ualm_result_t *results, double *c_xy, double 
  * number of kernel launches it made */
 int ualm_last_solve_ms(ualm_ctx_t *ctx, float *ms, int *launches);
 
+/* ---- several batches in flight on one context ("lanes") ----
+ * A lane is one resident batch with its own buffers, launch plan and streams; kernels of different lanes run concurrently, so
+ * the slow tail of batch k (a few long-running trajectories) overlaps the bulk of batch k+1.
+ *   ualm_select_lane(ctx, i): upload / solve_resident / sync / download / pack_records / last_solve_ms / eval / feasibility act
+ *                             on lane i (0 <= i < ualm_max_lanes(); lane 0 is selected at creation).
+ *   ualm_submit_batch:  upload + launch on the next lane of a `depth`-deep ring, returns a ticket without waiting for the solve
+ *                       (host inputs are consumed before it returns).  UALM_ESTATE when that lane is still in flight.
+ *   ualm_wait_batch:    blocks until the ticket's batch is complete, D2H of its results (same outputs as ualm_solve_batch).
+ *   ualm_mark_begin / ualm_mark_end: CUDA-event time (ms) from the selected lane's stream at mark_begin to the completion of the
+ *                       last solve of every lane at mark_end. */
+int ualm_max_lanes(void);
+int ualm_select_lane(ualm_ctx_t *ctx, int lane);
+int ualm_submit_batch(ualm_ctx_t *ctx, int B, const int32_t *N, const int32_t *M, const double *bnd, const double *total_time,
+                      const double *inner_xy, const double *inner_yaw, int depth, int *ticket);
+int ualm_wait_batch(ualm_ctx_t *ctx, int ticket, ualm_result_t *results, double *c_xy, double *c_yaw);
+int ualm_mark_begin(ualm_ctx_t *ctx);
+int ualm_mark_end(ualm_ctx_t *ctx, float *ms);
+
+/* ---- several GPUs from one host process ----
+ * ctxs[r] lives on its own device with the same parameters and map bound.  The batch is dealt over the contexts (cost-sorted
+ * snake), every device solves its shard concurrently, and the results come back in problem order.  There is no collective: the
+ * problems never interact and one host gathers by D2H copies.  (One process per GPU: ualm_pack_records_device + an NCCL
+ * all-gather of the records on the caller's communicator, uneven_planner_b200/distributed.py.) */
+int ualm_solve_batch_multi(ualm_ctx_t **ctxs, int nctx, int B, const int32_t *N, const int32_t *M, const double *bnd,
+                           const double *total_time, const double *inner_xy, const double *inner_yaw, ualm_result_t *results,
+                           double *c_xy, double *c_yaw);
+
 /* Fixed-stride result records for the multi-GPU all-gather: writes B records of `stride` doubles into
  * a DEVICE buffer (e.g. a torch tensor): [ret, outer, evals, iters, cost, jerk, T, res_h, res_g, N, M, pad,
- * c_xy(12N) , c_yaw(6M), zero pad].  stride >= 12 + 12 Nmax + 6 Mmax. */
+ * c_xy(12N) , c_yaw(6M), zero pad].  stride >= 12 + 12 Nmax + 6 Mmax.  The _async form does not wait for the kernel. */
 int ualm_pack_records_device(ualm_ctx_t *ctx, double *d_records, int stride);
+int ualm_pack_records_device_async(ualm_ctx_t *ctx, double *d_records, int stride);
 
 /* ---- phase entry points (kernel-level parity) ----
  * One innerCallback evaluation (alm_traj_opt.cpp:280-347) per problem of the uploaded batch at the given

@@ -109,22 +109,28 @@ inline SE2TrajMsg toSE2TrajMsg(const SE2Trajectory &tr)
     return m;
 }
 
-// c_xy: 6N x 2 column-major, c_yaw: 6M (solver order, low -> high power), T_total = sum of piece durations
-inline SE2Trajectory make_traj(int N, int M, const double *c_xy, const double *c_yaw, double T_total)
+// c_xy: 6N x 2 column-major, c_yaw: 6M (solver order, low -> high power); T_xy / T_yaw: the uniform piece durations T1(i) the
+// reference's getTraj() carries (MinJerkOpt::getTraj, se2traj.hpp:682-695; calTfromTau, alm_traj_opt.h:257-261) --
+// ualm_result_t::piece_T_xy / piece_T_yaw, NOT total_T / N (the N-fold sum divided back differs by a few ulps)
+inline SE2Trajectory make_traj(int N, int M, const double *c_xy, const double *c_yaw, double T_xy, double T_yaw)
 {
     SE2Trajectory tr;
     tr.pos_traj.resize(N);
     tr.yaw_traj.resize(M);
     for (int i = 0; i < N; i++) {
-        tr.pos_traj[i].duration = T_total / N;  // uniform durations, alm_traj_opt.h:257-261
+        tr.pos_traj[i].duration = T_xy;
         for (int d = 0; d < 2; d++)
             for (int k = 0; k < 6; k++) tr.pos_traj[i].coeff[d][5 - k] = c_xy[6 * i + k + d * 6 * N];
     }
     for (int i = 0; i < M; i++) {
-        tr.yaw_traj[i].duration = T_total / M;
+        tr.yaw_traj[i].duration = T_yaw;
         for (int k = 0; k < 6; k++) tr.yaw_traj[i].coeff[0][5 - k] = c_yaw[6 * i + k];
     }
     return tr;
+}
+inline SE2Trajectory make_traj(int N, int M, const double *c_xy, const double *c_yaw, const ualm_result_t &r)
+{
+    return make_traj(N, M, c_xy, c_yaw, r.piece_T_xy, r.piece_T_yaw);
 }
 
 class ALMTrajOpt {
@@ -147,6 +153,11 @@ public:
     // ALMTrajOpt::setEnvironment(UnevenMap::Ptr): the map grid (UnevenMap::map_buffer is private in the reference,
     // uneven_map.h:91, so the maintainer-side binding passes geometry + a float4 view of the cells)
     void setEnvironment(const ualm_map_geom_t &geom, const float *cells_xyzw) { check(ualm_set_map(ctx_, &geom, cells_xyzw), "ualm_set_map"); }
+    // the same from the reference's own double grid (UnevenMap::map_buffer, RXS2 = 4 doubles per cell, uneven_map.h:36-64)
+    void setEnvironment(const ualm_map_geom_t &geom, const double *rxs2_cells, bool repack_to_float = false)
+    {
+        check(ualm_set_map_f64(ctx_, &geom, rxs2_cells, repack_to_float ? 1 : 0), "ualm_set_map_f64");
+    }
 
     // ---- single problem, the reference's call (alm_traj_opt.h:92-98), plain pointers ----
     // initStateXY/endStateXY: 2x3 column-major; innerPtsXY: 2 x (N-1) column-major; initYaw/endYaw: 3; innerPtsYaw: M-1
@@ -163,7 +174,7 @@ public:
         check(ualm_solve_batch(ctx_, 1, &N, &M, bnd, &totalTime, innerPtsXY, innerPtsYaw, &last_, c_xy_.data(), c_yaw_.data()), "ualm_solve_batch");
         return last_.ret_code;
     }
-    SE2Trajectory getTraj() const { return make_traj(last_N_, last_M_, c_xy_.data(), c_yaw_.data(), last_.total_T); }
+    SE2Trajectory getTraj() const { return make_traj(last_N_, last_M_, c_xy_.data(), c_yaw_.data(), last_); }
     const ualm_result_t &lastResult() const { return last_; }
 
 #ifdef UALM_WITH_EIGEN
@@ -183,6 +194,16 @@ public:
     {
         check(ualm_solve_batch(ctx_, B, N, M, bnd, total_time, inner_xy, inner_yaw, results, c_xy, c_yaw), "ualm_solve_batch");
     }
+
+    // pipelined form: submit returns once the batch is uploaded and queued (up to `depth` batches in flight), wait collects it
+    int submitBatch(int B, const int32_t *N, const int32_t *M, const double *bnd, const double *total_time, const double *inner_xy,
+                    const double *inner_yaw, int depth = 2)
+    {
+        int ticket = -1;
+        check(ualm_submit_batch(ctx_, B, N, M, bnd, total_time, inner_xy, inner_yaw, depth, &ticket), "ualm_submit_batch");
+        return ticket;
+    }
+    void waitBatch(int ticket, ualm_result_t *results, double *c_xy, double *c_yaw) { check(ualm_wait_batch(ctx_, ticket, results, c_xy, c_yaw), "ualm_wait_batch"); }
 
     ualm_ctx_t *handle() { return ctx_; }
 

@@ -88,10 +88,11 @@ def params_from(p):
 
 
 class OracleMap:
-    """Holds the double copy of the float32 cells the oracle reads."""
+    """Holds the double grid the oracle reads: the map's own double cells (cells64) when it has them, else the float32 cells widened."""
 
     def __init__(self, mapdata):
-        self.cells = np.ascontiguousarray(mapdata.cells, dtype=np.float64)
+        c64 = getattr(mapdata, "cells64", None)
+        self.cells = np.ascontiguousarray(mapdata.cells if c64 is None else c64, dtype=np.float64)
         g = mapdata.geom
         self.c = OMap()
         self.c.cells = self.cells.ctypes.data_as(dp)

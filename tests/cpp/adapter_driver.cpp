@@ -32,6 +32,7 @@ int main(int argc, char **argv)
         double p[2];
         tr.pos_traj[0].getValue(0.0, p);
         printf("start %.17g %.17g\n", p[0], p[1]);
+        printf("durations %.17g %.17g\n", tr.pos_traj[0].getDuration(), tr.yaw_traj[0].getDuration());
         for (size_t i = 0; i < tr.pos_traj.size(); i++)
             for (int d = 0; d < 2; d++)
                 for (int k = 0; k < 6; k++) printf("%.17g\n", tr.pos_traj[i].coeff[d][k]);

@@ -22,7 +22,7 @@ int main()
     cxy[12 + 2] = 1.0;                             // piece 0: y = s^2
     cxy[12 + 6] = 2.25; cxy[12 + 7] = 3.0; cxy[12 + 8] = 1.0;   // piece 1: y = (1.5 + s)^2
     for (int i = 0; i < M; i++) { cyaw[6 * i] = 0.5 * i; cyaw[6 * i + 1] = 0.5; }   // yaw = 0.5 t, piece duration 1
-    SE2Trajectory tr = make_traj(N, M, cxy.data(), cyaw.data(), T);
+    SE2Trajectory tr = make_traj(N, M, cxy.data(), cyaw.data(), T / N, T / M);   // piece durations 1.5 and 1 (exact)
     CHECK(tr.pos_traj.size() == 2 && tr.yaw_traj.size() == 3);
     CHECK(tr.pos_traj[0].getDuration() == 1.5 && tr.yaw_traj[0].getDuration() == 1.0);
     CHECK(tr.pos_traj[0].coeff[0][5] == 1.0 && tr.pos_traj[0].coeff[0][4] == 2.0);      // highest power first

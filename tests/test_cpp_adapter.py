@@ -72,6 +72,17 @@ def test_adapter_matches_batch_api(driver, bumps_map, tmp_path):
     assert int(head[1]) == res[1].ret_code and int(head[3]) == res[1].n_evals and float(head[5]) == res[1].inner_cost
     N = int(pb.N[1])
     c = cxy[ocx[1]:ocx[2]]
+    # getTraj() carries the piece durations of the last evaluation (T1(i), se2traj.hpp:682-695): bit-identical to the oracle's and
+    # (tests/test_ref_pin.py) to the reference build's
+    import pyoracle as po
+    r_o = po.solve_one(po.params_from(_lib.default_params()), po.OracleMap(bumps_map), pb, 1)[0]
+    dur = [float(x) for x in lines[2].split()[1:]]
+    assert dur[0] == res[1].piece_T_xy and dur[1] == res[1].piece_T_yaw
+    tt = 0.0
+    for _ in range(int(pb.N[1])):
+        tt += dur[0]
+    assert tt == res[1].total_T == r_o.total_T
+    lines = lines[:2] + lines[3:]
     coeffs = np.array([float(x) for x in lines[2:2 + 12 * N]]).reshape(N, 2, 6)
     for i in range(N):
         for d in range(2):

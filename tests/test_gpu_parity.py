@@ -121,8 +121,8 @@ def test_full_solve_matches_oracle_hill(gpu, hill_map):
 @pytest.mark.parametrize("name", ["hill", "desert", "volcano", "forest"])
 def test_full_solve_matches_golden_fixture(gpu, terrain, name):
     """committed oracle outputs per terrain with the parameter sets of BASELINE configs 1-5 (tests/golden/make_golden.py,
-    uneven_planner_b200/configs.py): hill; desert (max_sig 0.08); volcano (no scaling, rho_T 500, max_kap 0.3, 64 samples per
-    piece); forest"""
+    uneven_planner_b200/configs.py): hill; desert (== hill); volcano (max_sig 0.08 + config 4's max_kap 0.3, 64 samples per
+    piece); forest (no scaling, rho_T 500, max_sig 0.001)"""
     from uneven_planner_b200 import configs, problems
     m = terrain(name)
     gold = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{name}_oracle_golden.npz"))

@@ -139,3 +139,33 @@ def test_problem_generator_is_deterministic_and_valid(bumps_map):
     assert np.all(np.hypot(*(a.starts[:, :2] - a.goals[:, :2]).T) >= 1.5)
     sub = a.select([3, 5])
     assert np.array_equal(sub.x0(1), a.x0(5))
+
+
+REF_PARAMS = "/root/reference/src/uneven_planner/plan_manager/params"
+
+
+def test_config_table_matches_reference_yaml(built):
+    """uneven_planner_b200/configs.py is the one table of per-terrain parameter deltas: re-derive it from the reference's own yaml
+    files where they exist (this container; the GPU box has no /root/reference)."""
+    if not os.path.isdir(REF_PARAMS):
+        pytest.skip("reference yaml files not present")
+    import yaml
+    from uneven_planner_b200 import configs
+    keys = [n for n, _ in _lib.Params._fields_ if n != "gravity"]
+    for name, fname in configs.YAML.items():
+        y = yaml.safe_load(open(os.path.join(REF_PARAMS, fname)))
+        node = y["manager_node"]
+        alm, um = node["alm_traj_opt"], node["uneven_map"]
+        p = configs.params_for(name, overrides=False)
+        for k in keys:
+            want = alm[k]
+            want = (1 if want else 0) if isinstance(want, bool) else float(want)
+            assert float(getattr(p, k)) == float(want), (name, k, getattr(p, k), want)
+        assert p.gravity == float(um["gravity"])
+        g = configs.gen_kwargs(name)
+        assert g["max_rho"] == float(um["max_rho"]) and g["min_cnormal"] == float(um["min_cnormal"]), name
+    # BASELINE config 4's overrides stay explicit, on top of run_vocano.yaml
+    p4 = configs.params_for("volcano")
+    assert p4.max_kap == 0.3 and p4.int_K == 64 and p4.max_sig == 0.08 and p4.use_scaling == 1
+    pf = configs.params_for("forest")
+    assert pf.use_scaling == 0 and pf.rho_T == 500.0 and pf.max_sig == 0.001

@@ -141,7 +141,7 @@ def _ref_solve(L, params, mapdata, pb, i):
     return ret, out
 
 
-@pytest.mark.parametrize("which,use_scaling", [("bumps", 1), ("bumps", 0), ("hill", 1), ("volcano", 0)])
+@pytest.mark.parametrize("which,use_scaling", [("bumps", 1), ("bumps", 0), ("hill", 1), ("volcano", 1), ("forest", 0)])
 def test_reference_optimizeSE2Traj_matches_oracle_bitwise(ref, built, request, which, use_scaling):
     """ALMTrajOpt::optimizeSE2Traj compiled from the reference's alm_traj_opt.cpp (innerCallback, calConstrainCostGrad, initScaling,
     earlyExit, dual update, UnevenMap::getAllWithGrad, MINCO, L-BFGS) against oracle.cpp on the same problems: return code,
@@ -152,9 +152,12 @@ def test_reference_optimizeSE2Traj_matches_oracle_bitwise(ref, built, request, w
     m = request.getfixturevalue("bumps_map") if which == "bumps" else maps.get_terrain(which)
     if m is None:
         pytest.skip(which + ".umap not present")
-    if which == "volcano":       # BASELINE config 4: run_vocano.yaml + max_kap 0.3 + 64 samples per piece, on the volcano terrain
-        params = configs.params_for("volcano")
-        pb = problems.generate(m, 2, seed=11, **configs.gen_kwargs("volcano"))
+    if which in ("volcano", "forest"):
+        # BASELINE config 4: run_vocano.yaml (max_sig 0.08) + max_kap 0.3 + 64 samples per piece on the volcano terrain;
+        # config 5: run_forest.yaml (no scaling, rho_T 500, max_sig 0.001) on the forest terrain
+        params = configs.params_for(which)
+        assert params.use_scaling == use_scaling
+        pb = problems.generate(m, 2 if which == "volcano" else 3, seed=11, **configs.gen_kwargs(which))
     else:
         params = _lib.default_params()
         params.use_scaling = use_scaling

@@ -31,7 +31,8 @@ class Result(C.Structure):
     _fields_ = [("ret_code", C.c_int32), ("outer_iters", C.c_int32), ("n_evals", C.c_int32),
                 ("n_lbfgs_iters", C.c_int32), ("last_lbfgs_ret", C.c_int32), ("max_bound", C.c_int32), ("sum_bound", C.c_int32), ("reserved", C.c_int32),
                 ("inner_cost", C.c_double), ("jerk_cost", C.c_double), ("total_T", C.c_double),
-                ("res_h", C.c_double), ("res_g", C.c_double), ("scale_fx", C.c_double), ("rho_final", C.c_double)]
+                ("res_h", C.c_double), ("res_g", C.c_double), ("scale_fx", C.c_double), ("rho_final", C.c_double),
+                ("piece_T_xy", C.c_double), ("piece_T_yaw", C.c_double)]
 
 
 _lib = None
@@ -85,6 +86,19 @@ def lib():
         L.ualm_feasibility_batch.argtypes = [vp, C.c_double, dp]
         L.ualm_feasibility_batch.restype = C.c_int
         L.ualm_profile.restype = C.c_int
+        L.ualm_reset_stream.argtypes = [vp]
+        L.ualm_set_map_f64.argtypes = [vp, C.POINTER(MapGeom), dp, C.c_int]
+        L.ualm_max_lanes.argtypes = []
+        L.ualm_select_lane.argtypes = [vp, C.c_int]
+        L.ualm_submit_batch.argtypes = [vp, C.c_int, ip, ip, dp, dp, dp, dp, C.c_int, C.POINTER(C.c_int)]
+        L.ualm_wait_batch.argtypes = [vp, C.c_int, C.POINTER(Result), dp, dp]
+        L.ualm_mark_begin.argtypes = [vp]
+        L.ualm_mark_end.argtypes = [vp, C.POINTER(C.c_float)]
+        L.ualm_solve_batch_multi.argtypes = [C.POINTER(vp), C.c_int, C.c_int, ip, ip, dp, dp, dp, dp, C.POINTER(Result), dp, dp]
+        L.ualm_pack_records_device_async.argtypes = [vp, vp, C.c_int]
+        for name in ("ualm_reset_stream", "ualm_set_map_f64", "ualm_max_lanes", "ualm_select_lane", "ualm_submit_batch", "ualm_wait_batch",
+                     "ualm_mark_begin", "ualm_mark_end", "ualm_solve_batch_multi", "ualm_pack_records_device_async"):
+            getattr(L, name).restype = C.c_int
         for name in ("ualm_create", "ualm_destroy", "ualm_set_params", "ualm_set_map", "ualm_solve_batch",
                      "ualm_upload", "ualm_solve_resident", "ualm_sync", "ualm_download", "ualm_last_solve_ms",
                      "ualm_pack_records_device", "ualm_eval_batch", "ualm_init_scaling_batch",

@@ -62,14 +62,65 @@ class BatchALMTrajOpt:
         _check(self.L.ualm_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
         return self
 
-    def set_environment(self, mapdata):
+    def set_environment(self, mapdata, repack_to_float=False):
+        """Binds the map grid.  A map that carries the reference's own double grid (`cells64`, RXS2 = 4 doubles per cell) goes
+        through ualm_set_map_f64; repack_to_float rounds it to the float4 grid on the way."""
         self.map = mapdata
-        _check(self.L.ualm_set_map(self.h, C.byref(mapdata.geom), mapdata.cells.ctypes.data_as(C.POINTER(C.c_float))))
+        c64 = getattr(mapdata, "cells64", None)
+        if c64 is not None:
+            _check(self.L.ualm_set_map_f64(self.h, C.byref(mapdata.geom), c64.ctypes.data_as(dp), 1 if repack_to_float else 0))
+        else:
+            _check(self.L.ualm_set_map(self.h, C.byref(mapdata.geom), mapdata.cells.ctypes.data_as(C.POINTER(C.c_float))))
         return self
+
+    def reset_stream(self):
+        _check(self.L.ualm_reset_stream(self.h))
+        return self
+
+    # ---- lanes: several resident batches in flight on this context ----------------------
+    def select_lane(self, lane):
+        _check(self.L.ualm_select_lane(self.h, int(lane)))
+        self.pb = self._lane_pb.get(int(lane), self.pb) if hasattr(self, "_lane_pb") else self.pb
+        self._lane = int(lane)
+        return self
+
+    def mark_begin(self):
+        _check(self.L.ualm_mark_begin(self.h))
+
+    def mark_end(self):
+        ms = C.c_float()
+        _check(self.L.ualm_mark_end(self.h, C.byref(ms)))
+        return ms.value
+
+    def submit(self, pb, depth=2, host=None):
+        """ualm_submit_batch: returns a ticket; `host` = optional pre-made (N, M, bnd, T, ixy, iyaw) host arrays (e.g. pinned)."""
+        if host is None:
+            host = [np.ascontiguousarray(a) for a in (pb.N.astype(np.int32), pb.M.astype(np.int32), pb.bnd.astype(np.float64),
+                                                        pb.total_time.astype(np.float64), pb.inner_xy.astype(np.float64),
+                                                        pb.inner_yaw.astype(np.float64))]
+        N, M, bnd, T, ixy, iyaw = host
+        t = C.c_int(-1)
+        _check(self.L.ualm_submit_batch(self.h, pb.B, _p(N, ip), _p(M, ip), _p(bnd), _p(T), _p(ixy), _p(iyaw), int(depth), C.byref(t)))
+        if not hasattr(self, "_tickets"):
+            self._tickets = {}
+        self._tickets[t.value] = (pb, host)
+        return t.value
+
+    def wait(self, ticket, out=None):
+        """ualm_wait_batch: (results, c_xy, c_yaw) of the ticket's batch; `out` = optional preallocated (res, cxy, cyaw)."""
+        pb, _ = self._tickets.pop(ticket)
+        if out is None:
+            out = ((Result * pb.B)(), np.zeros(int(12 * pb.N.astype(np.int64).sum())), np.zeros(int(6 * pb.M.astype(np.int64).sum())))
+        res, cxy, cyaw = out
+        _check(self.L.ualm_wait_batch(self.h, int(ticket), res, _p(cxy), _p(cyaw)))
+        return res, cxy, cyaw
 
     # ---- three-step path -------------------------------------------------------------
     def upload(self, pb):
         self.pb = pb
+        if not hasattr(self, "_lane_pb"):
+            self._lane_pb = {}
+        self._lane_pb[getattr(self, "_lane", 0)] = pb
         self._keep = [np.ascontiguousarray(a) for a in (pb.N.astype(np.int32), pb.M.astype(np.int32), pb.bnd.astype(np.float64),
                                                         pb.total_time.astype(np.float64), pb.inner_xy.astype(np.float64),
                                                         pb.inner_yaw.astype(np.float64))]
@@ -107,8 +158,9 @@ class BatchALMTrajOpt:
         _check(self.L.ualm_solve_batch(self.h, pb.B, _p(N, ip), _p(M, ip), _p(bnd), _p(T), _p(ixy), _p(iyaw), res, _p(cxy), _p(cyaw)))
         return res, cxy, cyaw
 
-    def pack_records(self, dev_ptr, stride):
-        _check(self.L.ualm_pack_records_device(self.h, C.c_void_p(dev_ptr), stride))
+    def pack_records(self, dev_ptr, stride, wait=True):
+        f = self.L.ualm_pack_records_device if wait else self.L.ualm_pack_records_device_async
+        _check(f(self.h, C.c_void_p(dev_ptr), stride))
 
     # ---- phase entry points ----------------------------------------------------------
     def eval_batch(self, x=None, lam=None, mu=None, scale_cx=None, scale_fx=None, rho=None):
@@ -160,3 +212,16 @@ class BatchALMTrajOpt:
         out = (C.c_longlong * 16)()
         _check(self.L.ualm_profile(self.h, 1 if enable else 0, out if read else None))
         return dict(zip(self.PHASES, list(out))) if read else None
+
+
+def solve_batch_multi(opts, pb):
+    """ualm_solve_batch_multi: one host process, one BatchALMTrajOpt per device (same params and map bound on each)."""
+    L = opts[0].L
+    hs = (C.c_void_p * len(opts))(*[o.h for o in opts])
+    N = np.ascontiguousarray(pb.N, np.int32); M = np.ascontiguousarray(pb.M, np.int32)
+    bnd = np.ascontiguousarray(pb.bnd, np.float64); T = np.ascontiguousarray(pb.total_time, np.float64)
+    ixy = np.ascontiguousarray(pb.inner_xy, np.float64); iyaw = np.ascontiguousarray(pb.inner_yaw, np.float64)
+    res = (Result * pb.B)()
+    cxy = np.zeros(int(12 * N.astype(np.int64).sum())); cyaw = np.zeros(int(6 * M.astype(np.int64).sum()))
+    _check(L.ualm_solve_batch_multi(hs, len(opts), pb.B, _p(N, ip), _p(M, ip), _p(bnd), _p(T), _p(ixy), _p(iyaw), res, _p(cxy), _p(cyaw)))
+    return res, cxy, cyaw

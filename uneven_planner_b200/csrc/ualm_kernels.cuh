@@ -32,6 +32,10 @@
 #define UALM_FPAD 8             // zero pad rows before and after each factor array (chunked prefetch may overrun)
 #define UALM_SYNC() __syncwarp()
 #define UALM_RINGB 4            // factor-ring depth in 6-row blocks per system (prefetch distance UALM_RINGB - 2)
+#define UALM_NMAX 64            // compiled limits on the piece counts of one problem (a problem over them is skipped with
+#define UALM_MMAX 128           //   ret_code = UALM_ELIMIT; the rest of its batch is solved)
+#define UALM_NREG 8             // L-BFGS two-loop register tile: each lane owns elements lane, lane + 32, ... (n <= 32 * UALM_NREG)
+static_assert(1 + 2 * (UALM_NMAX - 1) + (UALM_MMAX - 1) <= 32 * UALM_NREG, "decision vector must fit the two-loop register tile");
 
 namespace ualm {
 
@@ -65,7 +69,8 @@ struct DevParams {
 };
 
 struct DevMap {
-    const float4 *cells;   // {z, sigma, zbx, zby}
+    const float4 *cells;   // {z, sigma, zbx, zby} as float32, or null when
+    const double *cells64; //   the reference's own RXS2 grid (4 doubles per cell, uneven_map.h:36-64) is bound instead
     int vn[3];
     R origin[3], maxb[3], xy_res, yaw_res, xy_inv, yaw_inv;
 };
@@ -87,6 +92,7 @@ struct ProbDesc {
 
 struct BatchPtrs {
     int B;
+    int n_active;            // problems within the compiled limits = entries of `order`
     const int4 *wdesc;       // solve_kernel: per warp slot {problem (-1 = idle), leader slot in CTA, group size, warp in group | helper ring << 8}
     int n_leader_slots;      // solve_kernel: full per-trajectory slots per CTA (4 / G); helper rings follow them
     int adopt;               // solve_kernel: warps of a finished trajectory join the other trajectory of a two-slot CTA
@@ -894,6 +900,7 @@ __device__ __forceinline__ void map_get_all_with_grad_impl(const DevMap &m, cons
     // store costs a long-scoreboard wait, and the corner loop below used to re-read vn[2] sixteen times)
     const int vn0 = m.vn[0], vn1 = m.vn[1], vn2 = m.vn[2];
     const float4 *const cells = m.cells;
+    const double *const cells64 = m.cells64;
     const R xy_res = m.xy_res, yaw_res = m.yaw_res, xy_inv = m.xy_inv, yaw_inv = m.yaw_inv, org0 = m.origin[0], org1 = m.origin[1], org2 = m.origin[2];
     R rs[3], rg[4][3];
     if (!map_in(m, pos)) {
@@ -925,7 +932,8 @@ __device__ __forceinline__ void map_get_all_with_grad_impl(const DevMap &m, cons
                     c1 = max(min(c1, vn1 - 1), 0);
                     while (c2 > vn2 - 1) c2 -= vn2;
                     while (c2 < 0) c2 += vn2;
-                    prefetch_l1(&cells[(size_t)c0 * vn1 * vn2 + (size_t)c1 * vn2 + c2]);
+                    const size_t adr = (size_t)c0 * vn1 * vn2 + (size_t)c1 * vn2 + c2;
+                    prefetch_l1(cells64 ? (const void *)(cells64 + 4 * adr) : (const void *)&cells[adr]);
                 }
         {
             R sd, cd;
@@ -944,8 +952,14 @@ __device__ __forceinline__ void map_get_all_with_grad_impl(const DevMap &m, cons
                     c1 = max(min(c1, vn1 - 1), 0);
                     while (c2 > vn2 - 1) c2 -= vn2;
                     while (c2 < 0) c2 += vn2;
-                    const float4 cell = __ldg(&cells[(size_t)c0 * vn1 * vn2 + (size_t)c1 * vn2 + c2]);
-                    v[x][y][w][0] = (R)cell.y; v[x][y][w][1] = (R)cell.z; v[x][y][w][2] = (R)cell.w;
+                    const size_t adr = (size_t)c0 * vn1 * vn2 + (size_t)c1 * vn2 + c2;
+                    if (cells64) {
+                        const double2 lo = __ldg((const double2 *)(cells64 + 4 * adr)), hi = __ldg((const double2 *)(cells64 + 4 * adr) + 1);
+                        v[x][y][w][0] = lo.y; v[x][y][w][1] = hi.x; v[x][y][w][2] = hi.y;
+                    } else {
+                        const float4 cell = __ldg(&cells[adr]);
+                        v[x][y][w][0] = (R)cell.y; v[x][y][w][1] = (R)cell.z; v[x][y][w][2] = (R)cell.w;
+                    }
                 }
 #pragma unroll
         for (int k = 0; k < 3; k++) {
@@ -1649,14 +1663,14 @@ __device__ UALM_NOINLINE LbfgsOut lbfgs_optimize(Traj &t, const DevMap &map, con
             end = (end + 1) % m;
             // two-loop recursion (lbfgs.hpp:691-710).  Each lane owns elements lane, lane+32, ... (<= 8 of them) of d in
             // registers; the history vectors of the NEXT step are loaded while the current step's dot product runs.
-            R dreg[8], sc_[8], yc_[8], sn_[8], yn_[8];
+            R dreg[UALM_NREG], sc_[UALM_NREG], yc_[UALM_NREG], sn_[UALM_NREG], yn_[UALM_NREG];
 #pragma unroll
-            for (int e = 0; e < 8; e++) { const int q = lane + 32 * e; dreg[e] = q < n ? t.d[q] : 0.0; sn_[e] = 0.0; yn_[e] = 0.0; }
+            for (int e = 0; e < UALM_NREG; e++) { const int q = lane + 32 * e; dreg[e] = q < n ? t.d[q] : 0.0; sn_[e] = 0.0; yn_[e] = 0.0; }
             int j = (end + m - 1) % m;
             {
                 const R *sj = t.lm_s + (size_t)j * n, *yj = t.lm_y + (size_t)j * n;
 #pragma unroll
-                for (int e = 0; e < 8; e++) { const int q = lane + 32 * e; sc_[e] = q < n ? sj[q] : 0.0; yc_[e] = q < n ? yj[q] : 0.0; }
+                for (int e = 0; e < UALM_NREG; e++) { const int q = lane + 32 * e; sc_[e] = q < n ? sj[q] : 0.0; yc_[e] = q < n ? yj[q] : 0.0; }
             }
             R ysj = t.lm_ys[j], rysj = t.lm_rys[j];
             for (int i = 0; i < bound; ++i) {
@@ -1665,28 +1679,28 @@ __device__ UALM_NOINLINE LbfgsOut lbfgs_optimize(Traj &t, const DevMap &map, con
                 if (i + 1 < bound) {
                     const R *sj = t.lm_s + (size_t)jn * n, *yj = t.lm_y + (size_t)jn * n;
 #pragma unroll
-                    for (int e = 0; e < 8; e++) { const int q = lane + 32 * e; if (q < n) { sn_[e] = sj[q]; yn_[e] = yj[q]; } }
+                    for (int e = 0; e < UALM_NREG; e++) { const int q = lane + 32 * e; if (q < n) { sn_[e] = sj[q]; yn_[e] = yj[q]; } }
                     ysn = t.lm_ys[jn]; rysn = t.lm_rys[jn];
                 }
                 R pacc = 0.0;
 #pragma unroll
-                for (int e = 0; e < 8; e++) if (lane + 32 * e < n) pacc += sc_[e] * dreg[e];
+                for (int e = 0; e < UALM_NREG; e++) if (lane + 32 * e < n) pacc += sc_[e] * dreg[e];
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) pacc = pacc + __shfl_xor_sync(0xffffffffu, pacc, off);
                 const R a = div_by_recip(pacc, ysj, rysj);
                 if (lane == 0) t.lm_alpha[j] = a;
                 const R na = -a;
 #pragma unroll
-                for (int e = 0; e < 8; e++) dreg[e] = dreg[e] + na * yc_[e];
+                for (int e = 0; e < UALM_NREG; e++) dreg[e] = dreg[e] + na * yc_[e];
                 if (i + 1 < bound) {
 #pragma unroll
-                    for (int e = 0; e < 8; e++) { sc_[e] = sn_[e]; yc_[e] = yn_[e]; }
+                    for (int e = 0; e < UALM_NREG; e++) { sc_[e] = sn_[e]; yc_[e] = yn_[e]; }
                     j = jn; ysj = ysn; rysj = rysn;
                 }
             }
             const R scl = ys / yy;
 #pragma unroll
-            for (int e = 0; e < 8; e++) dreg[e] = dreg[e] * scl;
+            for (int e = 0; e < UALM_NREG; e++) dreg[e] = dreg[e] * scl;
             UALM_SYNC();
             // second loop walks oldest -> newest starting at the j where the first loop stopped (vectors still in sc_/yc_)
             R alj = t.lm_alpha[j];
@@ -1696,26 +1710,26 @@ __device__ UALM_NOINLINE LbfgsOut lbfgs_optimize(Traj &t, const DevMap &map, con
                 if (i + 1 < bound) {
                     const R *sj = t.lm_s + (size_t)jn * n, *yj = t.lm_y + (size_t)jn * n;
 #pragma unroll
-                    for (int e = 0; e < 8; e++) { const int q = lane + 32 * e; if (q < n) { sn_[e] = sj[q]; yn_[e] = yj[q]; } }
+                    for (int e = 0; e < UALM_NREG; e++) { const int q = lane + 32 * e; if (q < n) { sn_[e] = sj[q]; yn_[e] = yj[q]; } }
                     ysn = t.lm_ys[jn]; rysn = t.lm_rys[jn]; aln = t.lm_alpha[jn];
                 }
                 R pacc = 0.0;
 #pragma unroll
-                for (int e = 0; e < 8; e++) if (lane + 32 * e < n) pacc += yc_[e] * dreg[e];
+                for (int e = 0; e < UALM_NREG; e++) if (lane + 32 * e < n) pacc += yc_[e] * dreg[e];
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) pacc = pacc + __shfl_xor_sync(0xffffffffu, pacc, off);
                 const R beta = div_by_recip(pacc, ysj, rysj);
                 const R cf = alj - beta;
 #pragma unroll
-                for (int e = 0; e < 8; e++) dreg[e] = dreg[e] + cf * sc_[e];
+                for (int e = 0; e < UALM_NREG; e++) dreg[e] = dreg[e] + cf * sc_[e];
                 if (i + 1 < bound) {
 #pragma unroll
-                    for (int e = 0; e < 8; e++) { sc_[e] = sn_[e]; yc_[e] = yn_[e]; }
+                    for (int e = 0; e < UALM_NREG; e++) { sc_[e] = sn_[e]; yc_[e] = yn_[e]; }
                     j = jn; ysj = ysn; rysj = rysn; alj = aln;
                 }
             }
 #pragma unroll
-            for (int e = 0; e < 8; e++) { const int q = lane + 32 * e; if (q < n) t.d[q] = dreg[e]; }
+            for (int e = 0; e < UALM_NREG; e++) { const int q = lane + 32 * e; if (q < n) t.d[q] = dreg[e]; }
         }
         UALM_SYNC();
         prof_mark(t, lane, PF_TWOLOOP);
@@ -2142,6 +2156,7 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) solve_kernel(const __
         R tt = 0.0;
         for (int i = 0; i < N; i++) tt += t.sc[SC_TX1];
         r.total_T = tt; r.res_h = rh; r.res_g = rg; r.scale_fx = t.sc[SC_SCALE_FX]; r.rho_final = t.sc[SC_RHO];
+        r.piece_T_xy = t.sc[SC_TX1]; r.piece_T_yaw = t.sc[SC_TY1];
         bp.results[prob] = r;
         bp.piece_T[2 * prob] = t.sc[SC_TX1]; bp.piece_T[2 * prob + 1] = t.sc[SC_TY1];
         if (bp.prof) {
@@ -2160,7 +2175,7 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) eval_kernel(const __g
         const __grid_constant__ SmemLayout L, R rho)
 {
     const int lane = threadIdx.x & 31, wslot = blockIdx.x * UALM_WPB + (threadIdx.x >> 5);
-    if (wslot >= bp.B) return;   // whole warp exits; warps never synchronise with each other
+    if (wslot >= bp.n_active) return;   // whole warp exits; warps never synchronise with each other
     const unsigned sm = (unsigned)__cvta_generic_to_shared(ualm_smem) + 8u * (unsigned)((threadIdx.x >> 5) * L.total_doubles);
     const int prob = bp.order[wslot];
     Traj t;
@@ -2181,7 +2196,7 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) scaling_kernel(const 
         const __grid_constant__ SmemLayout L)
 {
     const int lane = threadIdx.x & 31, wslot = blockIdx.x * UALM_WPB + (threadIdx.x >> 5);
-    if (wslot >= bp.B) return;   // whole warp exits; warps never synchronise with each other
+    if (wslot >= bp.n_active) return;   // whole warp exits; warps never synchronise with each other
     const unsigned sm = (unsigned)__cvta_generic_to_shared(ualm_smem) + 8u * (unsigned)((threadIdx.x >> 5) * L.total_doubles);
     const int prob = bp.order[wslot];
     Traj t;
@@ -2199,7 +2214,7 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) penalty_only_kernel(c
         const __grid_constant__ SmemLayout L, int reps)
 {
     const int lane = threadIdx.x & 31, wslot = blockIdx.x * UALM_WPB + (threadIdx.x >> 5);
-    if (wslot >= bp.B) return;   // whole warp exits; warps never synchronise with each other
+    if (wslot >= bp.n_active) return;   // whole warp exits; warps never synchronise with each other
     const unsigned sm = (unsigned)__cvta_generic_to_shared(ualm_smem) + 8u * (unsigned)((threadIdx.x >> 5) * L.total_doubles);
     const int prob = bp.order[wslot];
     Traj t;
@@ -2266,6 +2281,10 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) feasibility_kernel(co
     const int lane = threadIdx.x & 31, prob = blockIdx.x * UALM_WPB + (threadIdx.x >> 5);
     if (prob >= bp.B) return;   // whole warp exits
     const ProbDesc *pd = bp.desc + prob;
+    if (pd->S == 0) {            // over the compiled limits: not solved (ret_code = UALM_ELIMIT)
+        if (lane < 10) out[10 * (size_t)prob + lane] = 0.0;
+        return;
+    }
     const int N = pd->N, M = pd->M, nx = 6 * N;
     const R *cxy = bp.c_xy + pd->off_cxy, *cyaw = bp.c_yaw + pd->off_cyaw;
     const R Tx = bp.piece_T[2 * prob], Ty = bp.piece_T[2 * prob + 1];

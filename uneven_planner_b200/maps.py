@@ -21,22 +21,19 @@ BUILT_DIR = os.path.join(ROOT, "maps_built")          # git-ignored, travels wit
 REF_MAPS = "/root/reference/src/uneven_planner/uneven_map/maps"   # only present in the build container
 MAGIC = b"UMAP0001"
 
-# per-terrain parameter deltas (plan_manager/params/run_*.yaml)
-TERRAINS = {
-    "hill": dict(pcd="hill.pcd", max_rho=0.05),
-    "desert": dict(pcd="desert.pcd", max_rho=0.08),
-    "volcano": dict(pcd="vocano.pcd", max_rho=0.001),
-    "forest": dict(pcd="forest.pcd", max_rho=0.05),
-    "mountain": dict(pcd="mountain.pcd", max_rho=0.05),
-}
+# per-terrain cloud files and occupancy thresholds live in configs.TERRAINS (one table, derived from the reference's yaml files)
+from .configs import TERRAINS  # noqa: E402
 
 
 class UnevenMapData:
     """Geometry + float32 cells [X,Y,Yaw,4] = (z, sigma, zbx, zby)."""
 
-    def __init__(self, geom, cells, name="map"):
+    def __init__(self, geom, cells, name="map", cells64=None):
         self.geom = geom
         self.cells = np.ascontiguousarray(cells, dtype=np.float32)
+        # optional: the reference's own grid (RXS2 = 4 doubles per cell, uneven_map.h:36-64) for maps built in-process by the
+        # reference; consumers that can (ualm_set_map_f64, the oracle) read it instead of the float32 copy
+        self.cells64 = None if cells64 is None else np.ascontiguousarray(cells64, dtype=np.float64)
         self.name = name
         X, Y, W = geom.voxel_num
         assert self.cells.shape == (X, Y, W, 4), self.cells.shape
