@@ -4,6 +4,7 @@
 // device and returns UALM_ENOCUDA otherwise.
 #include "ualm_kernels.cuh"
 #include "map_prep.h"
+#include "ualm_tp_host.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -95,6 +96,7 @@ struct Lane {
 
 struct ualm_ctx {
     int device = 0, precision = 64;
+    ualm_tp::TpEngine *tp = nullptr;     // precision 32 / 65: the throughput engine (ualm_tp.cu) behind the same entry points
     bool have_params = false, have_map = false;
     ualm_params_t hp;
     DevParams dp;
@@ -127,10 +129,22 @@ static int lane_make(ualm_ctx *c, Lane &l)
 
 extern "C" const char *ualm_last_error(void) { return g_err.c_str(); }
 
+// throughput contexts forward to the engine; its error text lands in the same thread-local message
+#define TP_CALL(expr)                                  \
+    do {                                               \
+        std::string em_;                               \
+        std::string *err = &em_;                       \
+        const int rc_ = (expr);                        \
+        if (rc_ != UALM_OK) g_err = em_;               \
+        return rc_;                                    \
+    } while (0)
+#define TP_UNSUPPORTED(name) return fail(UALM_EINVAL, name " is an entry point of the parity path (precision 64) only")
+
 extern "C" int ualm_create(ualm_ctx_t **out, int device, int precision)
 {
     if (!out) return fail(UALM_EINVAL, "ctx out pointer is NULL");
-    if (precision != 64) return fail(UALM_EINVAL, "precision must be 64 here (the throughput paths 65 / 32 are created through ualm_tp_create)");
+    if (precision != 64 && precision != 65 && precision != 32)
+        return fail(UALM_EINVAL, "precision must be 64 (bit-reproducible double), 65 (throughput path in double) or 32 (throughput path in float)");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev <= 0) return fail(UALM_ENOCUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
@@ -140,6 +154,13 @@ extern "C" int ualm_create(ualm_ctx_t **out, int device, int precision)
     c->device = device; c->precision = precision;
     if (const char *e = getenv("UALM_GROUPS")) c->group_mode = atoi(e);   // 0 = one warp per trajectory everywhere (developer switch)
     c->b = &c->lanes[0];
+    if (precision != 64) {
+        std::string em;
+        const int rc = ualm_tp::tp_create(&c->tp, device, precision, &em);
+        if (rc != UALM_OK) { delete c; return fail(rc, em); }
+        *out = c;
+        return UALM_OK;
+    }
     int rc = lane_make(c, c->lanes[0]);
     if (rc == UALM_OK) {
         cudaError_t e1 = cudaStreamCreateWithFlags(&c->join, cudaStreamNonBlocking);
@@ -157,6 +178,7 @@ extern "C" int ualm_destroy(ualm_ctx_t *c)
     if (!c) return UALM_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    if (c->tp) { ualm_tp::tp_destroy(c->tp); c->tp = nullptr; }
     c->cells.release(); c->cells64.release();
     for (auto &l : c->lanes) l.release();
     if (c->join) cudaStreamDestroy(c->join);
@@ -171,8 +193,10 @@ extern "C" int ualm_select_lane(ualm_ctx_t *c, int lane)
     if (!c) return fail(UALM_EINVAL, "null ctx");
     if (lane < 0 || lane >= UALM_MAX_LANES) return fail(UALM_EINVAL, "lane out of range [0, UALM_MAX_LANES)");
     CK(cudaSetDevice(c->device));
-    int rc = lane_make(c, c->lanes[lane]);
-    if (rc) return rc;
+    if (!c->tp) {
+        int rc = lane_make(c, c->lanes[lane]);
+        if (rc) return rc;
+    }
     c->cur = lane; c->b = &c->lanes[lane];
     return UALM_OK;
 }
@@ -185,6 +209,7 @@ extern "C" int ualm_max_lanes(void) { return UALM_MAX_LANES; }
 extern "C" int ualm_set_stream(ualm_ctx_t *c, void *s)
 {
     if (!c) return fail(UALM_EINVAL, "null ctx");
+    if (c->tp) TP_UNSUPPORTED("ualm_set_stream");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->b->stream));
     c->b->stream = (cudaStream_t)s;
@@ -193,6 +218,7 @@ extern "C" int ualm_set_stream(ualm_ctx_t *c, void *s)
 extern "C" int ualm_reset_stream(ualm_ctx_t *c)
 {
     if (!c) return fail(UALM_EINVAL, "null ctx");
+    if (c->tp) return UALM_OK;
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->b->stream));
     c->b->stream = c->b->own_stream;
@@ -218,6 +244,7 @@ extern "C" int ualm_set_params(ualm_ctx_t *c, const ualm_params_t *p)
     d.min_step = p->min_step; d.delta = p->delta; d.inner_max_iter = (int)p->inner_max_iter; d.mem_size = p->mem_size; d.past = p->past;
     d.int_K = p->int_K; d.gravity = p->gravity;
     c->have_params = true;
+    if (c->tp) TP_CALL(ualm_tp::tp_set_params(c->tp, p, err));
     return UALM_OK;
 }
 
@@ -248,7 +275,9 @@ extern "C" int ualm_set_map(ualm_ctx_t *c, const ualm_map_geom_t *g, const float
     CK(cudaMemcpy(c->cells.p, cells, ncell * sizeof(float4), cudaMemcpyHostToDevice));
     c->cells64.release();
     c->dm.cells = c->cells.p; c->dm.cells64 = nullptr;
-    return map_geometry_set(c, g);
+    map_geometry_set(c, g);
+    if (c->tp) TP_CALL(ualm_tp::tp_set_map(c->tp, g, cells, err));      // (the context's own copy serves the post-solve scan)
+    return UALM_OK;
 }
 
 // the reference's own grid: UnevenMap::map_buffer is RXS2 {double z, sigma; Vector2d zb} = 4 doubles per cell (uneven_map.h:36-64)
@@ -259,7 +288,7 @@ extern "C" int ualm_set_map_f64(ualm_ctx_t *c, const ualm_map_geom_t *g, const d
     CK(cudaSetDevice(c->device));
     CK(cudaDeviceSynchronize());
     const size_t ncell = (size_t)g->voxel_num[0] * g->voxel_num[1] * g->voxel_num[2];
-    if (repack_to_float) {
+    if (repack_to_float || c->tp) {      // the throughput path always reads the float4 grid
         std::vector<float> f(4 * ncell);
         for (size_t q = 0; q < 4 * ncell; q++) f[q] = (float)cells[q];
         return ualm_set_map(c, g, f.data());
@@ -311,6 +340,7 @@ extern "C" int ualm_upload(ualm_ctx_t *c, int B, const int32_t *N, const int32_t
                            const double *inner_xy, const double *inner_yaw)
 {
     if (!c || B < 0 || (B > 0 && (!N || !M || !bnd || !total_time))) return fail(UALM_EINVAL, "bad argument");
+    if (c->tp) TP_CALL(ualm_tp::tp_upload(c->tp, c->cur, B, N, M, bnd, total_time, inner_xy, inner_yaw, err));
     if (!c->have_params) return fail(UALM_ESTATE, "ualm_set_params must be called before ualm_upload");
     Lane *l = c->b;
     if (l->in_flight) return fail(UALM_ESTATE, "ualm_upload into a lane whose submitted batch is still in flight");
@@ -500,6 +530,7 @@ extern "C" int ualm_upload(ualm_ctx_t *c, int B, const int32_t *N, const int32_t
 extern "C" int ualm_solve_resident(ualm_ctx_t *c)
 {
     if (!c) return fail(UALM_EINVAL, "null ctx");
+    if (c->tp) TP_CALL(ualm_tp::tp_admit(c->tp, c->cur, err));      // joins the pool of running trajectories; ualm_sync / download drive the rounds
     Lane *l = c->b;
     if (!c->have_map || !c->have_params || !l->have_batch) return fail(UALM_ESTATE, "set_params, set_map and upload must precede solve");
     CK(cudaSetDevice(c->device));
@@ -532,6 +563,10 @@ extern "C" int ualm_solve_resident(ualm_ctx_t *c)
 extern "C" int ualm_sync(ualm_ctx_t *c)
 {
     if (!c) return fail(UALM_EINVAL, "null ctx");
+    if (c->tp) {
+        if (!ualm_tp::tp_lane_in_flight(c->tp, c->cur)) return UALM_OK;
+        TP_CALL(ualm_tp::tp_collect(c->tp, c->cur, err));
+    }
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->b->stream));
     return UALM_OK;
@@ -539,6 +574,7 @@ extern "C" int ualm_sync(ualm_ctx_t *c)
 
 extern "C" int ualm_last_solve_ms(ualm_ctx_t *c, float *ms, int *launches)
 {
+    if (c && c->tp) return ualm_tp::tp_last_solve(c->tp, c->cur, ms, launches) == UALM_OK ? UALM_OK : fail(UALM_ESTATE, "no collected solve to time");
     if (!c || !c->b->solved) return fail(UALM_ESTATE, "no solve to time");
     Lane *l = c->b;
     CK(cudaEventSynchronize(l->ev1));
@@ -553,6 +589,7 @@ extern "C" int ualm_last_solve_ms(ualm_ctx_t *c, float *ms, int *launches)
 extern "C" int ualm_mark_begin(ualm_ctx_t *c)
 {
     if (!c) return fail(UALM_EINVAL, "null ctx");
+    if (c->tp) TP_CALL(ualm_tp::tp_mark_begin(c->tp, err));
     CK(cudaSetDevice(c->device));
     CK(cudaEventRecord(c->evA, c->b->stream));
     return UALM_OK;
@@ -560,6 +597,7 @@ extern "C" int ualm_mark_begin(ualm_ctx_t *c)
 extern "C" int ualm_mark_end(ualm_ctx_t *c, float *ms)
 {
     if (!c || !ms) return fail(UALM_EINVAL, "null argument");
+    if (c->tp) TP_CALL(ualm_tp::tp_mark_end(c->tp, ms, err));
     CK(cudaSetDevice(c->device));
     for (auto &l : c->lanes)
         if (l.made && l.solved) CK(cudaStreamWaitEvent(c->join, l.ev1, 0));
@@ -571,6 +609,10 @@ extern "C" int ualm_mark_end(ualm_ctx_t *c, float *ms)
 
 extern "C" int ualm_download(ualm_ctx_t *c, ualm_result_t *results, double *c_xy, double *c_yaw)
 {
+    if (c && c->tp) {
+        if (!ualm_tp::tp_lane_in_flight(c->tp, c->cur) && !ualm_tp::tp_lane_collected(c->tp, c->cur)) return fail(UALM_ESTATE, "nothing solved");
+        TP_CALL(ualm_tp::tp_download(c->tp, c->cur, results, c_xy, c_yaw, err));
+    }
     if (!c || !c->b->solved) return fail(UALM_ESTATE, "nothing solved");
     Lane *l = c->b;
     CK(cudaSetDevice(c->device));
@@ -601,6 +643,15 @@ extern "C" int ualm_submit_batch(ualm_ctx_t *c, int B, const int32_t *N, const i
     if (!c || !ticket) return fail(UALM_EINVAL, "null argument");
     if (depth < 1 || depth > UALM_MAX_LANES) return fail(UALM_EINVAL, "depth out of range [1, UALM_MAX_LANES]");
     const int lane = c->next_submit % depth;
+    if (c->tp) {
+        if (ualm_tp::tp_lane_in_flight(c->tp, lane)) return fail(UALM_ESTATE, "all lanes of this depth are in flight: ualm_wait_batch the oldest ticket first");
+        std::string em;
+        int rc = ualm_tp::tp_upload(c->tp, lane, B, N, M, bnd, total_time, inner_xy, inner_yaw, &em);
+        if (!rc) rc = ualm_tp::tp_admit(c->tp, lane, &em);
+        if (rc) return fail(rc, em);
+        *ticket = lane; c->next_submit = (lane + 1) % depth;
+        return UALM_OK;
+    }
     if (c->lanes[lane].in_flight) return fail(UALM_ESTATE, "all lanes of this depth are in flight: ualm_wait_batch the oldest ticket first");
     const int keep = c->cur;
     int rc = ualm_select_lane(c, lane);
@@ -613,6 +664,10 @@ extern "C" int ualm_submit_batch(ualm_ctx_t *c, int B, const int32_t *N, const i
 extern "C" int ualm_wait_batch(ualm_ctx_t *c, int ticket, ualm_result_t *results, double *c_xy, double *c_yaw)
 {
     if (!c || ticket < 0 || ticket >= UALM_MAX_LANES) return fail(UALM_EINVAL, "bad ticket");
+    if (c->tp) {
+        if (!ualm_tp::tp_lane_in_flight(c->tp, ticket)) return fail(UALM_ESTATE, "ticket is not in flight");
+        TP_CALL(ualm_tp::tp_download(c->tp, ticket, results, c_xy, c_yaw, err));
+    }
     if (!c->lanes[ticket].in_flight) return fail(UALM_ESTATE, "ticket is not in flight");
     const int keep = c->cur;
     c->cur = ticket; c->b = &c->lanes[ticket];
@@ -690,6 +745,10 @@ extern "C" int ualm_solve_batch_multi(ualm_ctx_t **ctxs, int nctx, int B, const 
 
 extern "C" int ualm_pack_records_device(ualm_ctx_t *c, double *d_records, int stride)
 {
+    if (c && c->tp) {
+        if (!d_records) return fail(UALM_EINVAL, "null buffer");
+        TP_CALL(ualm_tp::tp_pack_records(c->tp, c->cur, d_records, stride, err));
+    }
     if (!c || !c->b->solved || !d_records) return fail(UALM_ESTATE, "nothing solved / null buffer");
     Lane *l = c->b;
     if (stride < 12 + 12 * l->Nmax + 6 * l->Mmax) return fail(UALM_EINVAL, "record stride too small");
@@ -704,6 +763,7 @@ extern "C" int ualm_pack_records_device(ualm_ctx_t *c, double *d_records, int st
 // the same without the host-side wait (pipelined callers synchronise the lane themselves before reading the records)
 extern "C" int ualm_pack_records_device_async(ualm_ctx_t *c, double *d_records, int stride)
 {
+    if (c && c->tp) return ualm_pack_records_device(c, d_records, stride);     // the engine gathers a batch only once it is complete
     if (!c || !c->b->solved || !d_records) return fail(UALM_ESTATE, "nothing solved / null buffer");
     Lane *l = c->b;
     if (stride < 12 + 12 * l->Nmax + 6 * l->Mmax) return fail(UALM_EINVAL, "record stride too small");
@@ -732,6 +792,7 @@ extern "C" int ualm_eval_batch(ualm_ctx_t *c, const double *x, const double *lam
                                const double *scale_fx, double rho, double *f, double *grad, double *hx, double *gx, double *c_xy,
                                double *c_yaw)
 {
+    if (c && c->tp) TP_CALL(ualm_tp::tp_eval(c->tp, c->cur, x, lambda, mu, scale_cx, scale_fx, rho, f, grad, hx, gx, c_xy, c_yaw, err));
     if (!c || !c->b->have_batch || !c->have_map) return fail(UALM_ESTATE, "upload and set_map first");
     Lane *l = c->b;
     if (l->n_active != l->B) return fail(UALM_ELIMIT, "ualm_eval_batch: the uploaded batch holds problems over the compiled limits");
@@ -758,6 +819,7 @@ extern "C" int ualm_eval_batch(ualm_ctx_t *c, const double *x, const double *lam
 
 extern "C" int ualm_init_scaling_batch(ualm_ctx_t *c, double *scale_fx, double *scale_cx)
 {
+    if (c && c->tp) TP_CALL(ualm_tp::tp_init_scaling(c->tp, c->cur, scale_fx, scale_cx, err));
     if (!c || !c->b->have_batch || !c->have_map) return fail(UALM_ESTATE, "upload and set_map first");
     Lane *l = c->b;
     if (l->n_active != l->B) return fail(UALM_ELIMIT, "ualm_init_scaling_batch: the uploaded batch holds problems over the compiled limits");
@@ -774,8 +836,9 @@ extern "C" int ualm_init_scaling_batch(ualm_ctx_t *c, double *scale_fx, double *
 
 extern "C" int ualm_time_penalty_kernel(ualm_ctx_t *c, int reps, float *ms_per_launch, double *algorithmic_bytes)
 {
-    if (!c || !c->b->have_batch || !c->have_map) return fail(UALM_ESTATE, "upload and set_map first");
     if (reps < 1) return fail(UALM_EINVAL, "reps < 1");
+    if (c && c->tp) TP_CALL(ualm_tp::tp_time_penalty(c->tp, c->cur, reps, getenv("UALM_TP_NOTMA") ? 0 : 1, ms_per_launch, algorithmic_bytes, err));
+    if (!c || !c->b->have_batch || !c->have_map) return fail(UALM_ESTATE, "upload and set_map first");
     Lane *l = c->b;
     if (l->n_active != l->B) return fail(UALM_ELIMIT, "ualm_time_penalty_kernel: the uploaded batch holds problems over the compiled limits");
     if (ms_per_launch) *ms_per_launch = 0.f;
@@ -809,6 +872,7 @@ extern "C" int ualm_time_penalty_kernel(ualm_ctx_t *c, int reps, float *ms_per_l
 extern "C" int ualm_profile(ualm_ctx_t *c, int enable, long long *out16)
 {
     if (!c) return fail(UALM_EINVAL, "null ctx");
+    if (c->tp) TP_UNSUPPORTED("ualm_profile");
     Lane *l = c->b;
     CK(cudaSetDevice(c->device));
     if (out16 && c->profile && l->solved && l->B > 0) {
@@ -826,9 +890,51 @@ extern "C" int ualm_profile(ualm_ctx_t *c, int enable, long long *out16)
     return UALM_OK;
 }
 
+namespace ualm {
+__global__ void piece_T_from_results(const ualm_result_t *res, int B, double *piece_T)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) { piece_T[2 * b] = res[b].piece_T_xy; piece_T[2 * b + 1] = res[b].piece_T_yaw; }
+}
+} // namespace ualm
+
+// the scan over coefficients that already sit on the device (B problems, ragged offsets from N / M, piece durations from the records)
+static int feasibility_from_device(ualm_ctx *c, int B, const int32_t *N, const int32_t *M, const ualm_result_t *d_res, const double *d_cxy, const double *d_cyaw,
+                                   double dt, double *out10)
+{
+    struct Tmp { DevBuf<ProbDesc> desc; DevBuf<double> pt, feas; ~Tmp() { desc.release(); pt.release(); feas.release(); } } t;
+    std::vector<ProbDesc> desc(B);
+    long long ocx = 0, ocy = 0;
+    for (int b = 0; b < B; b++) {
+        memset(&desc[b], 0, sizeof(ProbDesc));
+        desc[b].N = N[b]; desc[b].M = M[b]; desc[b].off_cxy = ocx; desc[b].off_cyaw = ocy;
+        desc[b].S = (N[b] > UALM_NMAX || M[b] > UALM_MMAX) ? 0 : 1;      // S == 0 marks a problem that was not solved
+        ocx += 12LL * N[b]; ocy += 6LL * M[b];
+    }
+    CK(t.desc.ensure(B)); CK(t.pt.ensure(2 * (size_t)B)); CK(t.feas.ensure(10 * (size_t)B));
+    CK(cudaMemcpy(t.desc.p, desc.data(), sizeof(ProbDesc) * B, cudaMemcpyHostToDevice));
+    piece_T_from_results<<<(B + 127) / 128, 128>>>(d_res, B, t.pt.p);
+    BatchPtrs bp;
+    memset(&bp, 0, sizeof(bp));
+    bp.B = B; bp.desc = t.desc.p; bp.c_xy = const_cast<double *>(d_cxy); bp.c_yaw = const_cast<double *>(d_cyaw); bp.piece_T = t.pt.p;
+    feasibility_kernel<<<(B + UALM_WPB - 1) / UALM_WPB, UALM_THREADS * UALM_WPB>>>(bp, c->dp, c->dm, dt, t.feas.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out10, t.feas.p, sizeof(double) * 10 * B, cudaMemcpyDeviceToHost));
+    return UALM_OK;
+}
+
 extern "C" int ualm_feasibility_batch(ualm_ctx_t *c, double dt, double *out10)
 {
     if (!c || !out10 || !(dt > 0.0)) return fail(UALM_EINVAL, "null argument or dt <= 0");
+    if (c->tp) {
+        const ualm_result_t *d_res; const double *d_cxy, *d_cyaw;
+        int B = 0; const int32_t *N = nullptr, *M = nullptr;
+        if (ualm_tp::tp_lane_outputs(c->tp, c->cur, &d_res, &d_cxy, &d_cyaw, &B, &N, &M) != UALM_OK)
+            return fail(UALM_ESTATE, "ualm_feasibility_batch needs a solved, collected batch (ualm_sync / ualm_download first)");
+        CK(cudaSetDevice(c->device));
+        if (B == 0) return UALM_OK;
+        return feasibility_from_device(c, B, N, M, d_res, d_cxy, d_cyaw, dt, out10);
+    }
     Lane *l = c->b;
     if (!c->have_map || !c->have_params || !l->have_batch || !l->solved) return fail(UALM_ESTATE, "ualm_feasibility_batch needs a solved resident batch");
     CK(cudaSetDevice(c->device));
