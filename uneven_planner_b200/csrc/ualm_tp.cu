@@ -74,8 +74,16 @@ struct TpEngine {
     int capacity = 0;
     std::vector<int> free_slots;
     int live = 0;                 // slots admitted and not yet freed
-    bool need_compact = false;
-    int scale_rounds = 0;         // rounds that still have to run ks_kernel
+    // groups: every batch in flight is split into TP_SUBGROUPS groups (group = lane * TP_SUBGROUPS + k); each group has its own
+    // stream, active list and round sequence, so ka of one group overlaps kb of another and a slow trajectory only holds up
+    // the rounds of its own group
+    cudaStream_t gstream[TP_NGROUPS] = {};
+    cudaEvent_t gev[TP_NGROUPS] = {};
+    int glive[TP_NGROUPS] = {};           // slots admitted and not yet freed, per group
+    int gscale[TP_NGROUPS] = {};          // rounds that still have to run ks_kernel
+    bool gcompact[TP_NGROUPS] = {};
+    long long grounds[TP_NGROUPS] = {};
+    int sg = 2;                           // subgroups per batch in use (UALM_TP_SUBGROUPS, <= TP_SUBGROUPS)
     int Nmax_live = 1, Mmax_live = 1;
     Buf<TpState> st;
     Buf<int> active, n_active, remaining;
@@ -87,12 +95,7 @@ struct TpEngine {
     TpLane lanes[TP_LANES];
     long long rounds_total = 0;
     int chunk = 8;
-    // developer profile (UALM_TP_PROFILE=1): CUDA events around the kernels of every round, drained at each chunk's host sync
-    bool prof = false;
-    std::vector<cudaEvent_t> pev;     // 3 per round of the current chunk: before ka | after ka (+ks) | after kb
-    int pev_used = 0;
-    double ka_ms = 0, kb_ms = 0;
-    long long prof_rounds = 0;
+    bool prof = false;            // developer profile (UALM_TP_PROFILE=1): in-kernel phase cycle counters, printed at destroy
 };
 
 static int build_tables(TpEngine *e, std::string *err)
@@ -140,6 +143,7 @@ int tp_create(TpEngine **out, int device, int precision, std::string *err)
     if (const char *s = getenv("UALM_TP_NOTMA")) e->use_tma = atoi(s) ? 0 : 1;
     if (const char *s = getenv("UALM_TP_CHUNK")) e->chunk = std::max(1, atoi(s));
     if (const char *s = getenv("UALM_TP_PROFILE")) e->prof = atoi(s) != 0;
+    if (const char *s = getenv("UALM_TP_SUBGROUPS")) e->sg = std::min(TP_SUBGROUPS, std::max(1, atoi(s)));
     memset(&e->E, 0, sizeof(e->E));
     auto failed = [&](int rc) { tp_destroy(e); return rc; };
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&e->evA) != cudaSuccess ||
@@ -149,9 +153,14 @@ int tp_create(TpEngine **out, int device, int precision, std::string *err)
     }
     for (auto &l : e->lanes)
         if (cudaEventCreate(&l.ev0) != cudaSuccess || cudaEventCreate(&l.ev1) != cudaSuccess) { if (err) *err = "event creation failed"; return failed(UALM_ENOCUDA); }
-    if (e->remaining.ensure(TP_MAX_TICKETS) != cudaSuccess || e->n_active.ensure(1) != cudaSuccess) { if (err) *err = "allocation failed"; return failed(UALM_ENOCUDA); }
+    for (int g = 0; g < TP_NGROUPS; g++)
+        if (cudaStreamCreateWithFlags(&e->gstream[g], cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&e->gev[g], cudaEventDisableTiming) != cudaSuccess) {
+            if (err) *err = "group stream creation failed";
+            return failed(UALM_ENOCUDA);
+        }
+    if (e->remaining.ensure(TP_MAX_TICKETS) != cudaSuccess || e->n_active.ensure(TP_NGROUPS) != cudaSuccess) { if (err) *err = "allocation failed"; return failed(UALM_ENOCUDA); }
     cudaMemsetAsync(e->remaining.p, 0, sizeof(int) * TP_MAX_TICKETS, e->stream);
-    cudaMemsetAsync(e->n_active.p, 0, sizeof(int), e->stream);
+    cudaMemsetAsync(e->n_active.p, 0, sizeof(int) * TP_NGROUPS, e->stream);
     int rc = build_tables(e, err);
     if (rc) return failed(rc);
     *out = e;
@@ -163,9 +172,6 @@ void tp_destroy(TpEngine *e)
     if (!e) return;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    if (e->prof && e->prof_rounds > 0)
-        fprintf(stderr, "[ualm-tp] profile: %lld rounds, ka(+ks) %.1f us/round, kb %.1f us/round (CUDA events; total %.1f ms)\n", e->prof_rounds,
-                1e3 * e->ka_ms / e->prof_rounds, 1e3 * e->kb_ms / e->prof_rounds, e->ka_ms + e->kb_ms);
     if (e->prof && e->kprof.p) {
         long long h[32];
         cudaMemcpy(h, e->kprof.p, sizeof(h), cudaMemcpyDeviceToHost);
@@ -184,7 +190,7 @@ void tp_destroy(TpEngine *e)
         fprintf(stderr, " total %.0f\n", (double)tb / std::max(1ll, h[16 + 7]));
         e->kprof.release();
     }
-    for (auto ev : e->pev) cudaEventDestroy(ev);
+    for (int g = 0; g < TP_NGROUPS; g++) { if (e->gstream[g]) cudaStreamDestroy(e->gstream[g]); if (e->gev[g]) cudaEventDestroy(e->gev[g]); }
     for (auto &l : e->lanes) {
         l.d_ad.release(); l.d_gd.release(); l.d_x0.release(); l.d_cxy.release(); l.d_cyaw.release(); l.d_xout.release(); l.d_f.release(); l.d_grad.release();
         l.d_hx.release(); l.d_gx.release(); l.d_sfx.release(); l.d_scx.release(); l.d_lam.release(); l.d_mu.release(); l.d_scin.release(); l.d_sfin.release();
@@ -224,6 +230,7 @@ int tp_set_params(TpEngine *e, const ualm_params_t *p, std::string *err)
     // the pool strides depend on int_K and mem_size: it is rebuilt at the next admission; uploaded batches stay valid (they hold
     // problem data only), but nothing may be resident in the pool
     e->capacity = 0; e->free_slots.clear(); e->live = 0;
+    for (int g = 0; g < TP_NGROUPS; g++) { e->glive[g] = 0; e->gscale[g] = 0; e->gcompact[g] = false; }
     for (auto &l : e->lanes) { l.collected = false; }
     return UALM_OK;
 }
@@ -266,7 +273,7 @@ static int pool_alloc(TpEngine *e, int cap, std::string *err)
 {
     const int K = e->p.int_K, m = e->p.mem_size;
     const size_t Smax = (size_t)TP_NMAX * (K + 1), es = e->esz();
-    TCK(e->st.ensure(cap)); TCK(e->active.ensure(cap));
+    TCK(e->st.ensure(cap)); TCK(e->active.ensure((size_t)cap * TP_NGROUPS));
     TCK(e->vec.ensure((size_t)cap * 5 * TP_NVAR)); TCK(e->cd.ensure((size_t)cap * TP_CSTRIDE)); TCK(e->gw.ensure((size_t)cap * TP_CSTRIDE));
     TCK(e->kb_cost.ensure(cap)); TCK(e->lm_ys.ensure((size_t)cap * m)); TCK(e->lm_alpha.ensure((size_t)cap * m));
     if (e->f32()) TCK(e->cr.ensure((size_t)cap * TP_CSTRIDE * es));
@@ -274,7 +281,8 @@ static int pool_alloc(TpEngine *e, int cap, std::string *err)
     TCK(e->dual.ensure((size_t)cap * TP_NDUAL * Smax * es));
     TCK(e->hs.ensure((size_t)cap * m * TP_NVAR * es)); TCK(e->hy.ensure((size_t)cap * m * TP_NVAR * es));
     TCK(cudaMemsetAsync(e->st.p, 0, sizeof(TpState) * cap, e->stream));     // every slot PH_FREE
-    TCK(cudaMemsetAsync(e->n_active.p, 0, sizeof(int), e->stream));
+    TCK(cudaMemsetAsync(e->n_active.p, 0, sizeof(int) * TP_NGROUPS, e->stream));
+    TCK(cudaStreamSynchronize(e->stream));
     TpPool &E = e->E;
     E.capacity = cap; E.m = m; E.K = K; E.Smax = (int)Smax; E.use_tma = e->use_tma;
     E.st = e->st.p; E.active = e->active.p; E.n_active = e->n_active.p; E.remaining = e->remaining.p;
@@ -287,6 +295,7 @@ static int pool_alloc(TpEngine *e, int cap, std::string *err)
     e->free_slots.clear();
     for (int s = cap - 1; s >= 0; s--) e->free_slots.push_back(s);
     e->live = 0;
+    for (int g = 0; g < TP_NGROUPS; g++) e->glive[g] = 0;
     if (getenv("UALM_DEBUG")) fprintf(stderr, "[ualm-tp] pool of %d slots allocated (%.2f MB per slot)\n", cap,
                                       (double)((size_t)5 * TP_NVAR * 8 + 3 * TP_CSTRIDE * 8 + TP_NDUAL * Smax * es + 2 * (size_t)m * TP_NVAR * es) / 1e6);
     return UALM_OK;
@@ -347,7 +356,7 @@ int tp_upload(TpEngine *e, int lane, int B, const int32_t *N, const int32_t *M, 
     return UALM_OK;
 }
 
-static int admit_impl(TpEngine *e, int lane, int mode, std::string *err)
+static int admit_impl(TpEngine *e, int lane, int mode, bool single_group, std::string *err)
 {
     TpLane &l = e->lanes[lane];
     if (!e->have_params || !e->have_map || !l.have_batch) { if (err) *err = "set_params, set_map and upload must precede the solve"; return UALM_ESTATE; }
@@ -355,10 +364,16 @@ static int admit_impl(TpEngine *e, int lane, int mode, std::string *err)
     TCK(cudaSetDevice(e->device));
     int need = 0;
     for (int b = 0; b < l.B; b++) if (!(l.N[b] > TP_NMAX || l.M[b] > TP_MMAX)) need++;
-    // the pool grows only while nothing is resident; it is sized for four batches of this size in flight
-    if (e->live == 0 && e->capacity < 4 * need) {
+    // the pool grows only while nothing is resident; it is sized for TP_LANES batches of this size in flight (fewer when that
+    // would take more than ~64 GB of HBM)
+    int mult = TP_LANES;
+    {
+        const double per_slot = 5.0 * TP_NVAR * 8 + 3.0 * TP_CSTRIDE * 8 + (double)TP_NDUAL * TP_NMAX * (e->p.int_K + 1) * e->esz() + 2.0 * e->p.mem_size * TP_NVAR * e->esz();
+        while (mult > 1 && per_slot * mult * need > 64e9) mult /= 2;
+    }
+    if (e->live == 0 && e->capacity < mult * need) {
         int cap = std::max(1024, e->capacity);
-        while (cap < 4 * need) cap *= 2;
+        while (cap < mult * need) cap *= 2;
         if (const char *s = getenv("UALM_TP_CAPACITY")) cap = std::max(cap, atoi(s));
         int rc = pool_alloc(e, cap, err);
         if (rc) return rc;
@@ -366,6 +381,7 @@ static int admit_impl(TpEngine *e, int lane, int mode, std::string *err)
     if ((int)e->free_slots.size() < need) { if (err) *err = "throughput pool exhausted: collect a batch in flight first (the pool grows only when idle)"; return UALM_ELIMIT; }
     l.slots.clear();
     std::vector<ualm_result_t> res0(l.B);
+    int k = 0;
     for (int b = 0; b < l.B; b++) {
         memset(&res0[b], 0, sizeof(ualm_result_t));
         const bool skip = l.N[b] > TP_NMAX || l.M[b] > TP_MMAX;
@@ -373,7 +389,10 @@ static int admit_impl(TpEngine *e, int lane, int mode, std::string *err)
         const int s = e->free_slots.back();
         e->free_slots.pop_back();
         l.slots.push_back(s);
-        l.ad[b].slot = s; l.ad[b].mode = mode; l.gd[b].slot = s;
+        const int g = lane * TP_SUBGROUPS + (single_group ? 0 : k % e->sg);
+        l.ad[b].slot = s; l.ad[b].mode = mode; l.ad[b].group = g; l.gd[b].slot = s;
+        e->glive[g]++;
+        k++;
     }
     e->live += (int)l.slots.size();
     e->Nmax_live = std::max(e->Nmax_live, l.Nmax); e->Mmax_live = std::max(e->Mmax_live, l.Mmax);
@@ -403,10 +422,13 @@ static int admit_impl(TpEngine *e, int lane, int mode, std::string *err)
         if (e->f32()) admit_kernel<float><<<BA, 128, 0, e->stream>>>(e->E, l.d_ad.p, l.d_x0.p, BA, e->p.use_scaling, e->p.int_K, lam, mu, scx, sfx, l.rho_eval, l.d_offs.p);
         else admit_kernel<double><<<BA, 128, 0, e->stream>>>(e->E, l.d_ad.p, l.d_x0.p, BA, e->p.use_scaling, e->p.int_K, lam, mu, scx, sfx, l.rho_eval, l.d_offs.p);
         TCK(cudaGetLastError());
-        TCK(cudaStreamSynchronize(e->stream));     // ad / offs / res0 are stack-local staging vectors
+        // host-synchronised: ad / offs / res0 are stack-local staging vectors, and the lane's group streams start after the admission
+        TCK(cudaStreamSynchronize(e->stream));
         l.launches++;
-        e->need_compact = true;
-        if ((mode == 0 && e->p.use_scaling) || mode == 2) e->scale_rounds = std::max(e->scale_rounds, 1);
+        for (int q = 0; q < TP_SUBGROUPS; q++) {
+            const int g = lane * TP_SUBGROUPS + q;
+            if (e->glive[g] > 0) { e->gcompact[g] = true; if ((mode == 0 && e->p.use_scaling) || mode == 2) e->gscale[g] = std::max(e->gscale[g], 1); }
+        }
     } else {
         e->h_remaining[lane] = 0;
         TCK(cudaStreamSynchronize(e->stream));
@@ -418,7 +440,7 @@ static int admit_impl(TpEngine *e, int lane, int mode, std::string *err)
 int tp_admit(TpEngine *e, int lane, std::string *err)
 {
     if (lane < 0 || lane >= TP_LANES) { if (err) *err = "lane out of range"; return UALM_EINVAL; }
-    return admit_impl(e, lane, 0, err);
+    return admit_impl(e, lane, 0, false, err);
 }
 
 static size_t kb_smem_bytes(TpEngine *e, bool tma)
@@ -435,23 +457,6 @@ static size_t ks_smem_bytes(TpEngine *e)
     const size_t coef = ((size_t)12 * e->Nmax_live * 3 + (size_t)6 * e->Mmax_live * 3 + e->Nmax_live + e->Mmax_live) * es;
     return ((arrays + 15) & ~(size_t)15) + coef + 64;
 }
-
-static cudaEvent_t prof_event(TpEngine *e)
-{
-    if (e->pev_used == (int)e->pev.size()) { cudaEvent_t ev; cudaEventCreate(&ev); e->pev.push_back(ev); }
-    return e->pev[e->pev_used++];
-}
-static void prof_drain(TpEngine *e)      // after a stream synchronisation
-{
-    for (int q = 0; q + 2 < e->pev_used; q += 3) {
-        float a = 0.f, b = 0.f;
-        cudaEventElapsedTime(&a, e->pev[q], e->pev[q + 1]);
-        cudaEventElapsedTime(&b, e->pev[q + 1], e->pev[q + 2]);
-        e->ka_ms += a; e->kb_ms += b; e->prof_rounds++;
-    }
-    e->pev_used = 0;
-}
-
 // ka_kernel's shared memory per warp: column buffer (12 N + 6 M doubles of the largest live problem), aliased by the two-loop's
 // history ring (4 slots x {s, y} x n elements), followed by the factor ring
 static void ka_layout(TpEngine *e)
@@ -464,16 +469,16 @@ static void ka_layout(TpEngine *e)
 }
 static size_t ka_smem_bytes(TpEngine *e) { return (size_t)TP_KA_WARPS * (e->E.ka_col_bytes + 2 * TP_RING * TP_BLK * 8); }
 
+// one round of group g on its stream: ka -> [ks] -> kb
 template <class R>
-static int launch_round(TpEngine *e, int upper, bool with_ks, bool tma, std::string *err)
+static int launch_round(TpEngine *e, int g, bool with_ks, bool tma, std::string *err)
 {
-    if (e->prof) cudaEventRecord(prof_event(e), e->stream);
-    ka_kernel<R><<<(upper + TP_KA_WARPS - 1) / TP_KA_WARPS, 32 * TP_KA_WARPS, ka_smem_bytes(e), e->stream>>>(e->E, e->p);
-    if (with_ks) ks_kernel<R><<<upper, TP_KB_THREADS, ks_smem_bytes(e), e->stream>>>(e->E, e->p, e->map);
-    if (e->prof) cudaEventRecord(prof_event(e), e->stream);
-    if (tma) kb_kernel<R, true><<<upper, TP_KB_THREADS, kb_smem_bytes(e, true), e->stream>>>(e->E, e->p, e->map, e->tmap);
-    else kb_kernel<R, false><<<upper, TP_KB_THREADS, kb_smem_bytes(e, false), e->stream>>>(e->E, e->p, e->map, e->tmap);
-    if (e->prof) cudaEventRecord(prof_event(e), e->stream);
+    const int upper = e->glive[g];
+    cudaStream_t st = e->gstream[g];
+    ka_kernel<R><<<(upper + TP_KA_WARPS - 1) / TP_KA_WARPS, 32 * TP_KA_WARPS, ka_smem_bytes(e), st>>>(e->E, e->p, g);
+    if (with_ks) ks_kernel<R><<<upper, TP_KB_THREADS, ks_smem_bytes(e), st>>>(e->E, e->p, e->map, g);
+    if (tma) kb_kernel<R, true><<<upper, TP_KB_THREADS, kb_smem_bytes(e, true), st>>>(e->E, e->p, e->map, e->tmap, g);
+    else kb_kernel<R, false><<<upper, TP_KB_THREADS, kb_smem_bytes(e, false), st>>>(e->E, e->p, e->map, e->tmap, g);
     TCK(cudaGetLastError());
     return UALM_OK;
 }
@@ -485,15 +490,15 @@ static int set_attrs(TpEngine *e, std::string *err)
     const int pi = sizeof(R) == 4 ? 0 : 1;
     ka_layout(e);
     const size_t a = kb_smem_bytes(e, true), b = kb_smem_bytes(e, false), c = ks_smem_bytes(e), d = ka_smem_bytes(e);
+    if (a > 227 * 1024 || c > 227 * 1024 || d > 227 * 1024) { if (err) *err = "problem too large for shared memory"; return UALM_ELIMIT; }
     if (d > done_ka[pi]) { TCK(cudaFuncSetAttribute(ka_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d)); done_ka[pi] = d; }
-    if (a > 227 * 1024 || c > 227 * 1024) { if (err) *err = "problem too large for shared memory"; return UALM_ELIMIT; }
     if (a > done_kb[pi][1]) { TCK(cudaFuncSetAttribute(kb_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a)); done_kb[pi][1] = a; }
     if (b > done_kb[pi][0]) { TCK(cudaFuncSetAttribute(kb_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b)); done_kb[pi][0] = b; }
     if (c > done_ks[pi]) { TCK(cudaFuncSetAttribute(ks_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c)); done_ks[pi] = c; }
     return UALM_OK;
 }
 
-// run `nr` rounds over everything that is live
+// `nr` rounds of every live group, interleaved over the groups' streams
 static int run_rounds(TpEngine *e, int nr, std::string *err)
 {
     if (e->live <= 0) return UALM_OK;
@@ -501,16 +506,19 @@ static int run_rounds(TpEngine *e, int nr, std::string *err)
     if (rc) return rc;
     const bool tma = e->have_tmap && e->use_tma;
     for (int r = 0; r < nr; r++) {
-        if (e->need_compact || (e->rounds_total % e->chunk) == 0) {
-            compact_kernel<<<1, 1024, 0, e->stream>>>(e->E, e->capacity);
-            e->need_compact = false;
+        for (int g = 0; g < TP_NGROUPS; g++) {
+            if (e->glive[g] <= 0) continue;
+            if (e->gcompact[g] || (e->grounds[g] % e->chunk) == 0) {
+                compact_kernel<<<1, 1024, 0, e->gstream[g]>>>(e->E, e->capacity, g);
+                e->gcompact[g] = false;
+            }
+            const bool with_ks = e->gscale[g] > 0;
+            rc = e->f32() ? launch_round<float>(e, g, with_ks, tma, err) : launch_round<double>(e, g, with_ks, tma, err);
+            if (rc) return rc;
+            if (e->gscale[g] > 0) e->gscale[g]--;
+            e->grounds[g]++;
+            e->lanes[g / TP_SUBGROUPS].launches += 2 + (with_ks ? 1 : 0);
         }
-        const bool with_ks = e->scale_rounds > 0;
-        rc = e->f32() ? launch_round<float>(e, e->live, with_ks, tma, err) : launch_round<double>(e, e->live, with_ks, tma, err);
-        if (rc) return rc;
-        if (e->scale_rounds > 0) e->scale_rounds--;
-        e->rounds_total++;
-        for (auto &l : e->lanes) if (l.in_flight) l.launches += 2 + (with_ks ? 1 : 0);
     }
     return UALM_OK;
 }
@@ -524,11 +532,12 @@ int tp_collect(TpEngine *e, int lane, std::string *err)
     TCK(cudaSetDevice(e->device));
     long long guard = 0;
     while (true) {
+        // the lane's own groups are the pace setters: wait for what was queued for them, then look at the lane's counter
+        for (int q = 0; q < TP_SUBGROUPS; q++) TCK(cudaStreamSynchronize(e->gstream[lane * TP_SUBGROUPS + q]));
         TCK(cudaMemcpyAsync(e->h_remaining, e->remaining.p, sizeof(int) * TP_LANES, cudaMemcpyDeviceToHost, e->stream));
         TCK(cudaStreamSynchronize(e->stream));
-        if (e->prof) prof_drain(e);
         if (e->h_remaining[lane] <= 0) break;
-        int rc = run_rounds(e, e->chunk, err);
+        int rc = run_rounds(e, e->chunk, err);        // every live group advances, not only this lane's
         if (rc) return rc;
         if ((guard += e->chunk) > 400000) { if (err) *err = "throughput engine: a trajectory did not terminate"; return UALM_ENOCUDA; }
     }
@@ -544,7 +553,6 @@ int tp_collect(TpEngine *e, int lane, std::string *err)
         gather_kernel<R><<<l.B, 128, 0, e->stream>>>(e->E, l.d_gd.p, l.B, l.d_res.p, l.d_cxy.p, l.d_cyaw.p, l.d_xout.p, ev ? l.d_f.p : nullptr,            \
                                                      ev ? l.d_grad.p : nullptr, ev ? l.d_hx.p : nullptr, ev ? l.d_gx.p : nullptr, ev ? l.d_sfx.p : nullptr,    \
                                                      ev ? l.d_scx.p : nullptr)
-        // skipped problems have slot -1: the gather kernel must not touch them
         if (e->f32()) GATHER(float); else GATHER(double);
 #undef GATHER
         TCK(cudaGetLastError());
@@ -557,7 +565,7 @@ int tp_collect(TpEngine *e, int lane, std::string *err)
     for (int s : l.slots) e->free_slots.push_back(s);
     e->live -= (int)l.slots.size();
     l.slots.clear();
-    e->need_compact = true;
+    for (int q = 0; q < TP_SUBGROUPS; q++) { const int g = lane * TP_SUBGROUPS + q; e->glive[g] = 0; e->gscale[g] = 0; e->gcompact[g] = false; }
     l.in_flight = false; l.collected = true;
     return UALM_OK;
 }
@@ -633,6 +641,7 @@ int tp_mark_begin(TpEngine *e, std::string *err)
 int tp_mark_end(TpEngine *e, float *ms, std::string *err)
 {
     TCK(cudaSetDevice(e->device));
+    for (int g = 0; g < TP_NGROUPS; g++) { TCK(cudaEventRecord(e->gev[g], e->gstream[g])); TCK(cudaStreamWaitEvent(e->stream, e->gev[g], 0)); }
     TCK(cudaEventRecord(e->evB, e->stream));
     TCK(cudaEventSynchronize(e->evB));
     TCK(cudaEventElapsedTime(ms, e->evA, e->evB));
@@ -662,7 +671,7 @@ int tp_eval(TpEngine *e, int lane, const double *x, const double *lambda, const 
     if ((rc = put(e, l.d_scin, scale_cx, 7 * l.tot_s, l.has_scx, err))) return rc;
     if ((rc = put(e, l.d_sfin, scale_fx, l.B, l.has_sfx, err))) return rc;
     l.rho_eval = rho;
-    rc = admit_impl(e, lane, 1, err);
+    rc = admit_impl(e, lane, 1, false, err);
     l.has_lam = l.has_mu = l.has_scx = l.has_sfx = false;
     if (rc) return rc;
     if ((rc = tp_collect(e, lane, err))) return rc;
@@ -685,7 +694,7 @@ int tp_init_scaling(TpEngine *e, int lane, double *scale_fx, double *scale_cx, s
     if (!l.have_batch || !e->have_map) { if (err) *err = "upload and set_map first"; return UALM_ESTATE; }
     for (int b = 0; b < l.B; b++) if (l.N[b] > TP_NMAX || l.M[b] > TP_MMAX) { if (err) *err = "batch holds problems over the compiled limits"; return UALM_ELIMIT; }
     TCK(cudaSetDevice(e->device));
-    int rc = admit_impl(e, lane, 2, err);
+    int rc = admit_impl(e, lane, 2, false, err);
     if (rc) return rc;
     if ((rc = tp_collect(e, lane, err))) return rc;
     if (l.B > 0) {
@@ -708,29 +717,31 @@ int tp_time_penalty(TpEngine *e, int lane, int reps, int use_tma, float *ms_per_
     TCK(cudaSetDevice(e->device));
     // admit as single evaluations (initial guess, zero duals, unit scales), run the forward half of a round, then time kb alone
     l.has_lam = l.has_mu = l.has_scx = l.has_sfx = false; l.rho_eval = e->p.rho;
-    int rc = admit_impl(e, lane, 1, err);
+    int rc = admit_impl(e, lane, 1, true, err);
     if (rc) return rc;
     rc = e->f32() ? set_attrs<float>(e, err) : set_attrs<double>(e, err);
     if (rc) return rc;
-    compact_kernel<<<1, 1024, 0, e->stream>>>(e->E, e->capacity);
-    e->need_compact = false;
-    const int upper = e->live;
+    const int g = lane * TP_SUBGROUPS;
+    cudaStream_t st = e->gstream[g];
+    compact_kernel<<<1, 1024, 0, st>>>(e->E, e->capacity, g);
+    e->gcompact[g] = false;
+    const int upper = e->glive[g];
     const bool tma = e->have_tmap && use_tma;
-    if (e->f32()) ka_kernel<float><<<(upper + TP_KA_WARPS - 1) / TP_KA_WARPS, 32 * TP_KA_WARPS, ka_smem_bytes(e), e->stream>>>(e->E, e->p);
-    else ka_kernel<double><<<(upper + TP_KA_WARPS - 1) / TP_KA_WARPS, 32 * TP_KA_WARPS, ka_smem_bytes(e), e->stream>>>(e->E, e->p);
+    if (e->f32()) ka_kernel<float><<<(upper + TP_KA_WARPS - 1) / TP_KA_WARPS, 32 * TP_KA_WARPS, ka_smem_bytes(e), st>>>(e->E, e->p, g);
+    else ka_kernel<double><<<(upper + TP_KA_WARPS - 1) / TP_KA_WARPS, 32 * TP_KA_WARPS, ka_smem_bytes(e), st>>>(e->E, e->p, g);
     auto kb = [&]() {
         if (e->f32()) {
-            if (tma) kb_kernel<float, true><<<upper, TP_KB_THREADS, kb_smem_bytes(e, true), e->stream>>>(e->E, e->p, e->map, e->tmap);
-            else kb_kernel<float, false><<<upper, TP_KB_THREADS, kb_smem_bytes(e, false), e->stream>>>(e->E, e->p, e->map, e->tmap);
+            if (tma) kb_kernel<float, true><<<upper, TP_KB_THREADS, kb_smem_bytes(e, true), st>>>(e->E, e->p, e->map, e->tmap, g);
+            else kb_kernel<float, false><<<upper, TP_KB_THREADS, kb_smem_bytes(e, false), st>>>(e->E, e->p, e->map, e->tmap, g);
         } else {
-            if (tma) kb_kernel<double, true><<<upper, TP_KB_THREADS, kb_smem_bytes(e, true), e->stream>>>(e->E, e->p, e->map, e->tmap);
-            else kb_kernel<double, false><<<upper, TP_KB_THREADS, kb_smem_bytes(e, false), e->stream>>>(e->E, e->p, e->map, e->tmap);
+            if (tma) kb_kernel<double, true><<<upper, TP_KB_THREADS, kb_smem_bytes(e, true), st>>>(e->E, e->p, e->map, e->tmap, g);
+            else kb_kernel<double, false><<<upper, TP_KB_THREADS, kb_smem_bytes(e, false), st>>>(e->E, e->p, e->map, e->tmap, g);
         }
     };
     kb();    // warm-up
-    TCK(cudaEventRecord(e->evA, e->stream));
+    TCK(cudaEventRecord(e->evA, st));
     for (int r = 0; r < reps; r++) kb();
-    TCK(cudaEventRecord(e->evB, e->stream));
+    TCK(cudaEventRecord(e->evB, st));
     TCK(cudaGetLastError());
     TCK(cudaEventSynchronize(e->evB));
     float ms = 0.f;

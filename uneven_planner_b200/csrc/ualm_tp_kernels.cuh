@@ -48,6 +48,8 @@ namespace ualm_tp {
 #define TP_TILE_BYTES (TP_TILE * TP_TILE * TP_TILE * 16)
 #define TP_MAXPPC 7                     // pieces per sample chunk (<= TP_KB_THREADS / (K + 1))
 #define TP_MAX_TICKETS 64
+#define TP_SUBGROUPS 4                  // every batch in flight is split into up to this many independently advancing groups
+#define TP_NGROUPS (8 * TP_SUBGROUPS)   // lanes x subgroups: each group has its own stream, active list and round sequence
 
 #define TP_DELTA_SIGL 0.01
 #define TP_CUR_SCALE 10.0
@@ -81,7 +83,7 @@ struct TpMap {
 
 struct TpState {
     int phase, N, M, n, S, ticket, index, need_scale;
-    int mode, padm0, padm1, padm2;   // 0 = solve, 1 = one evaluation at the given duals (kernel-level parity), 2 = initScaling only
+    int mode, group, padm1, padm2;   // 0 = solve, 1 = one evaluation at the given duals (kernel-level parity), 2 = initScaling only
     int n_evals, iters_total, outer_iter, last_ret, ret_code, max_bound, sum_bound, pad0;
     int k, end, bound, ls_count, brackt, touched, pad1, pad2;
     double fx, step, stp, ls_mu, ls_nu, dginit, finit, dgtest, dstest;
@@ -95,8 +97,8 @@ struct TpState {
 struct TpPool {
     int capacity, m, K, Smax, use_tma, ka_col_bytes, ka_hist_stride, pad;
     TpState *st;
-    int *active;            // active slot list
-    int *n_active;          // [1]
+    int *active;            // [TP_NGROUPS][capacity] active slot list per group
+    int *n_active;          // [TP_NGROUPS]
     int *remaining;         // per ticket: trajectories not yet done
     double *vec;            // [cap][5][TP_NVAR]  x | g | xp | gp | d
     double *cd;             // [cap][TP_CSTRIDE]  coefficients of the last forward solve (double)
@@ -874,13 +876,13 @@ __device__ int advance(const TpPool &E, const TpParams &p, const SlotView &v, in
 }
 
 template <class R>
-__global__ void __launch_bounds__(32 * TP_KA_WARPS) ka_kernel(const __grid_constant__ TpPool E, const __grid_constant__ TpParams p)
+__global__ void __launch_bounds__(32 * TP_KA_WARPS) ka_kernel(const __grid_constant__ TpPool E, const __grid_constant__ TpParams p, int group)
 {
     const int lane = threadIdx.x & 31, widx = blockIdx.x * TP_KA_WARPS + (threadIdx.x >> 5);
-    if (widx >= *E.n_active) return;
+    if (widx >= E.n_active[group]) return;
     extern __shared__ __align__(16) unsigned char ka_smem[];     // per warp: column buffer (ka_col_bytes) | factor ring
     unsigned char *wbase = ka_smem + (size_t)(threadIdx.x >> 5) * (E.ka_col_bytes + 2 * TP_RING * TP_BLK * 8);
-    const int slot = E.active[widx];
+    const int slot = E.active[(size_t)group * E.capacity + widx];
     SlotView v = slot_view(E, slot, (double *)wbase, (double *)(wbase + E.ka_col_bytes));
     TpState *st = v.st;
     const int ph = st->phase;
@@ -914,29 +916,31 @@ __global__ void __launch_bounds__(32 * TP_KA_WARPS) ka_kernel(const __grid_const
     if (lane == 0) st->phase = next;
 }
 
-// rebuild the active list from the slot phases (one CTA); slots in PH_NEW join here
-__global__ void compact_kernel(const __grid_constant__ TpPool E, int hi)
+// rebuild the active list of one group from the slot phases (one CTA); slots in PH_NEW join here
+__global__ void compact_kernel(const __grid_constant__ TpPool E, int hi, int group)
 {
     __shared__ int s_count;
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
+    int *list = E.active + (size_t)group * E.capacity;
     for (int s0 = 0; s0 < hi; s0 += blockDim.x) {
         const int s = s0 + threadIdx.x;
-        const bool live = s < hi && E.st[s].phase != PH_FREE && E.st[s].phase != PH_DONE;
+        bool live = false;
+        if (s < hi) { const int ph = E.st[s].phase; live = ph != PH_FREE && ph != PH_DONE && E.st[s].group == group; }
         const unsigned bal = __ballot_sync(0xffffffffu, live);
         int base = 0;
         if ((threadIdx.x & 31) == 0 && bal) base = atomicAdd(&s_count, __popc(bal));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (live) E.active[base + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u))] = s;
+        if (live) list[base + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u))] = s;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *E.n_active = s_count;
+    if (threadIdx.x == 0) E.n_active[group] = s_count;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // admission: problem b of a submitted batch -> slot
 // ---------------------------------------------------------------------------------------------------------------------
-struct AdmitDesc { int slot, N, M, ticket, index, mode, pad0, pad1; long long off_x; double total_time; double bnd[18]; };
+struct AdmitDesc { int slot, N, M, ticket, index, mode, group, pad1; long long off_x; double total_time; double bnd[18]; };
 
 template <class R>
 __global__ void admit_kernel(const __grid_constant__ TpPool E, const AdmitDesc *ad, const double *x0, int B, int use_scaling, int K,
@@ -964,7 +968,7 @@ __global__ void admit_kernel(const __grid_constant__ TpPool E, const AdmitDesc *
     if (threadIdx.x == 0) {
         st->N = a.N; st->M = a.M; st->n = n; st->S = S; st->ticket = a.ticket; st->index = a.index;
         for (int k = 0; k < 18; k++) st->bnd[k] = a.bnd[k];
-        st->mode = a.mode;
+        st->mode = a.mode; st->group = a.group;
         st->need_scale = ((a.mode == 0 && use_scaling) || a.mode == 2) ? 1 : 0;
         st->phase = PH_NEW;
         if (a.mode == 1) { st->rho = rho_eval; st->scale_fx = sfx ? sfx[b] : 1.0; }

@@ -290,10 +290,10 @@ struct KbShared {     // fixed part of kb_kernel's shared memory; the dynamic pa
 // ---------------------------------------------------------------------------------------------------------------------
 template <class R, bool TMA>
 __global__ void __launch_bounds__(TP_KB_THREADS) kb_kernel(const __grid_constant__ TpPool E, const __grid_constant__ TpParams p, const __grid_constant__ TpMap map,
-                                                           const __grid_constant__ CUtensorMap tmap)
+                                                           const __grid_constant__ CUtensorMap tmap, int group)
 {
-    if ((int)blockIdx.x >= *E.n_active) return;
-    const int slot = E.active[blockIdx.x];
+    if ((int)blockIdx.x >= E.n_active[group]) return;
+    const int slot = E.active[(size_t)group * E.capacity + blockIdx.x];
     const TpState *st = E.st + slot;
     const int ph = st->phase;
     if (ph != PH_REQ_FIRST && ph != PH_REQ_LS && ph != PH_REQ_EVALONLY) return;
@@ -504,10 +504,10 @@ __global__ void __launch_bounds__(TP_KB_THREADS) kb_kernel(const __grid_constant
 // of f = jerk + rho_ter int sigma^2 + rho_T T.
 // ---------------------------------------------------------------------------------------------------------------------
 template <class R>
-__global__ void __launch_bounds__(TP_KB_THREADS) ks_kernel(const __grid_constant__ TpPool E, const __grid_constant__ TpParams p, const __grid_constant__ TpMap map)
+__global__ void __launch_bounds__(TP_KB_THREADS) ks_kernel(const __grid_constant__ TpPool E, const __grid_constant__ TpParams p, const __grid_constant__ TpMap map, int group)
 {
-    if ((int)blockIdx.x >= *E.n_active) return;
-    const int slot = E.active[blockIdx.x];
+    if ((int)blockIdx.x >= E.n_active[group]) return;
+    const int slot = E.active[(size_t)group * E.capacity + blockIdx.x];
     TpState *st = E.st + slot;
     if (!st->need_scale || st->phase == PH_NEW || st->phase == PH_DONE || st->phase == PH_FREE) return;
     const int N = st->N, M = st->M, S = st->S, K = p.int_K, K1 = K + 1, nx = 6 * N, ny = 6 * M, tid = threadIdx.x;
