@@ -193,6 +193,10 @@ int ualm_map_build_device(ualm_ctx_t *ctx, const float *pts, int64_t npts, const
  * ellipsoid = {0.2,0.1,0.1}, iter_num = 2 in every reference yaml. */
 int ualm_map_build(const float *pts, int64_t npts, const ualm_map_geom_t *g, double ellipsoid_x,
                    double ellipsoid_y, double ellipsoid_z, int iter_num, int nthreads, float *cells);
+/* the cloud ualm_map_build / ualm_map_build_device work on: UnevenMap::init's CropBox + 1 cm VoxelGrid (uneven_map.cpp:133-143), as xyz
+ * floats.  Returns the number of points (pts_out may be NULL to query it; UALM_ELIMIT when max_pts is too small). */
+int64_t ualm_map_preprocess_cloud(const float *pts, int64_t npts, double ellipsoid_x, double ellipsoid_y, double ellipsoid_z, float *pts_out,
+                                  int64_t max_pts);
 /* occupancy (uneven_map.cpp:169-179): occ3[X*Y*Yaw], occ2[X*Y] (1 = occupied) */
 int ualm_map_occupancy(const float *cells, const ualm_map_geom_t *g, double min_cnormal, double max_rho,
                        uint8_t *occ3, uint8_t *occ2);

@@ -55,3 +55,16 @@ def test_device_map_edge_cases(opt):
         host = maps.build_from_cloud(pts, geom)
         dev, _ = opt.build_map(pts, geom)
         assert np.array_equal(host.cells.view(np.uint32), dev.cells.view(np.uint32))
+
+
+def test_device_map_matches_the_reference_build(opt):
+    """ualm_map_build_device against the reference's OWN constructMap + filter (oracle/_ref/librefmap.so = uneven_map.cpp compiled
+    unmodified, tests/test_ref_pin.py) on the same preprocessed cloud: float32 cells = the reference's doubles rounded, up to 2 ulps,
+    except the <= 0.02 % of cells at the rim of the empty patch (degenerate footprints)."""
+    from test_ref_pin import analytic_cloud, preprocessed, reference_construct_map
+    pts = analytic_cloud(1.1, 100, seed=1, hole=(0.35, -0.3, 0.14))
+    geom, ref = reference_construct_map(preprocessed(pts), 1.6)
+    dev, _ = opt.build_map(pts, geom)
+    d = np.abs(dev.cells.astype(np.float64) - ref)
+    rel = (d / np.maximum(np.abs(ref), 1e-3)).max(axis=-1)
+    assert (rel > 3e-7).mean() <= 2e-4

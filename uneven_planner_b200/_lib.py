@@ -58,6 +58,8 @@ def lib():
     L.ualm_dubins_path.argtypes = [dp, dp, C.c_double, C.c_double, dp, C.c_int]
     L.ualm_resample_path.argtypes = [dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp,
                                      C.c_int, dp, C.c_int, ip, ip, dp]
+    L.ualm_map_preprocess_cloud.argtypes = [fp, C.c_int64, C.c_double, C.c_double, C.c_double, fp, C.c_int64]
+    L.ualm_map_preprocess_cloud.restype = C.c_int64
     for name in ("ualm_map_build", "ualm_map_occupancy", "ualm_dubins_path", "ualm_resample_path"):
         getattr(L, name).restype = C.c_int
     # GPU entry points (present once the CUDA translation unit is linked in)

@@ -105,6 +105,19 @@ void ualm_map_preprocess(const float *pin, int64_t npts, double ex, double ey, d
     for (auto &p : cloud) { const int q = fill[key(p)]++; out.pts[3 * q] = p.x; out.pts[3 * q + 1] = p.y; out.pts[3 * q + 2] = p.z; }
 }
 
+extern "C" int64_t ualm_map_preprocess_cloud(const float *pin, int64_t npts, double ex, double ey, double ez, float *pts_out, int64_t max_pts)
+{
+    if (!pin || npts < 0) return UALM_EINVAL;
+    UalmMapHostPrep prep;
+    ualm_map_preprocess(pin, npts, ex, ey, ez, prep);
+    const int64_t n = (int64_t)(prep.pts.size() / 3);
+    if (pts_out) {
+        if (n > max_pts) return UALM_ELIMIT;
+        std::copy(prep.pts.begin(), prep.pts.end(), pts_out);
+    }
+    return n;
+}
+
 extern "C" int ualm_map_build(const float *pin, int64_t npts, const ualm_map_geom_t *g, double ex, double ey,
                               double ez, int iter_num, int nthreads, float *cells)
 {

@@ -48,7 +48,7 @@ struct DevBuf {
 // One in-flight batch ("lane"): its own device buffers, launch plan, streams and events.  A context owns up to UALM_MAX_LANES of
 // them so that several batches can be resident and running at once (the stragglers of batch k drain while batch k+1 fills the
 // SMs they left: ualm_submit_batch / ualm_wait_batch, or ualm_select_lane + the three-step calls).
-#define UALM_MAX_LANES 8
+#define UALM_MAX_LANES 16
 struct Lane {
     bool made = false;
     cudaStream_t stream = nullptr, own_stream = nullptr;

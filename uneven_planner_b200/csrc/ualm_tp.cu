@@ -13,7 +13,7 @@
 
 namespace ualm_tp {
 
-#define TP_LANES 8
+#define TP_LANES TP_MAXLANES
 
 #define TCK(call)                                                                                       \
     do {                                                                                                \
@@ -216,7 +216,7 @@ static bool any_in_flight(TpEngine *e)
 
 int tp_set_params(TpEngine *e, const ualm_params_t *p, std::string *err)
 {
-    if (p->int_K < 1 || p->int_K > 128) { if (err) *err = "int_K out of range [1,128]"; return UALM_ELIMIT; }
+    if (p->int_K < 1 || p->int_K > TP_KB_THREADS - 1) { if (err) *err = "int_K out of range [1,127] on the throughput path"; return UALM_ELIMIT; }
     if (p->mem_size < 1 || p->mem_size > 1024) { if (err) *err = "mem_size out of range [1,1024]"; return UALM_ELIMIT; }
     if (p->past < 0 || p->past > 16) { if (err) *err = "past out of range [0,16]"; return UALM_ELIMIT; }
     if (any_in_flight(e)) { if (err) *err = "ualm_set_params while a batch is in flight"; return UALM_ESTATE; }
@@ -446,14 +446,14 @@ int tp_admit(TpEngine *e, int lane, std::string *err)
 static size_t kb_smem_bytes(TpEngine *e, bool tma)
 {
     const size_t es = e->esz();
-    const size_t arrays = 12 * (size_t)TP_NS * es + 3 * (size_t)TP_NS * 4;
+    const size_t arrays = (size_t)(TP_KB_THREADS / 32) * (TP_MAXPPC * 13 + TP_YCAP * 7) * es;      // ChunkPart<R>
     const size_t coef = ((size_t)12 * e->Nmax_live + (size_t)6 * e->Mmax_live * 2 + e->Mmax_live) * es;
     return (tma ? (size_t)TP_MAXPPC * TP_TILE_BYTES : 0) + ((arrays + 15) & ~(size_t)15) + coef + 64;
 }
 static size_t ks_smem_bytes(TpEngine *e)
 {
     const size_t es = e->esz();
-    const size_t arrays = 12 * (size_t)TP_NS * es + 3 * (size_t)TP_NS * 4;
+    const size_t arrays = (size_t)(TP_KB_THREADS / 32) * (TP_MAXPPC * 13 + TP_YCAP * 7) * es;      // ChunkPart<R>
     const size_t coef = ((size_t)12 * e->Nmax_live * 3 + (size_t)6 * e->Mmax_live * 3 + e->Nmax_live + e->Mmax_live) * es;
     return ((arrays + 15) & ~(size_t)15) + coef + 64;
 }
@@ -463,8 +463,9 @@ static void ka_layout(TpEngine *e)
 {
     const int nmax = 1 + 2 * (e->Nmax_live - 1) + (e->Mmax_live - 1);
     const int hstride = (int)(((size_t)nmax * e->esz() + 15) / 16 * 16 / e->esz());
-    const size_t col = ((size_t)12 * e->Nmax_live + 6 * e->Mmax_live) * 8, hist = (size_t)4 * 2 * hstride * e->esz();
-    e->E.ka_col_bytes = (int)((std::max(col, hist) + 15) & ~(size_t)15);
+    const size_t col = ((size_t)12 * e->Nmax_live + 6 * e->Mmax_live) * 8, hist = (((size_t)4 * 2 * hstride * e->esz()) + 15) & ~(size_t)15;
+    e->E.ka_hist_bytes = (int)hist;                                             // behind the ring: 1 / ys and alpha of the two-loop (2 m doubles)
+    e->E.ka_col_bytes = (int)((std::max(col, hist + 2 * (size_t)e->p.mem_size * 8) + 15) & ~(size_t)15);
     e->E.ka_hist_stride = hstride;
 }
 static size_t ka_smem_bytes(TpEngine *e) { return (size_t)TP_KA_WARPS * (e->E.ka_col_bytes + 2 * TP_RING * TP_BLK * 8); }

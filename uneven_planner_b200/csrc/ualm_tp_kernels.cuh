@@ -49,7 +49,8 @@ namespace ualm_tp {
 #define TP_MAXPPC 7                     // pieces per sample chunk (<= TP_KB_THREADS / (K + 1))
 #define TP_MAX_TICKETS 64
 #define TP_SUBGROUPS 4                  // every batch in flight is split into up to this many independently advancing groups
-#define TP_NGROUPS (8 * TP_SUBGROUPS)   // lanes x subgroups: each group has its own stream, active list and round sequence
+#define TP_MAXLANES 16                  // batches in flight (= UALM_MAX_LANES of ualm_api.cu)
+#define TP_NGROUPS (TP_MAXLANES * TP_SUBGROUPS)   // lanes x subgroups: each group has its own stream, active list and round sequence
 
 #define TP_DELTA_SIGL 0.01
 #define TP_CUR_SCALE 10.0
@@ -95,7 +96,7 @@ struct TpState {
 };
 
 struct TpPool {
-    int capacity, m, K, Smax, use_tma, ka_col_bytes, ka_hist_stride, pad;
+    int capacity, m, K, Smax, use_tma, ka_col_bytes, ka_hist_stride, ka_hist_bytes;
     TpState *st;
     int *active;            // [TP_NGROUPS][capacity] active slot list per group
     int *n_active;          // [TP_NGROUPS]
@@ -771,6 +772,9 @@ __device__ int advance(const TpPool &E, const TpParams &p, const SlotView &v, in
                     const unsigned hring0 = (unsigned)__cvta_generic_to_shared(hring);
                     const int nchunk = (n * (int)sizeof(R) + 15) / 16;
                     const int nsteps = 2 * bound, ne = (n + 31) >> 5;
+                    // 1 / (y_j . s_j) of the steps and the alphas of the first loop sit in shared memory behind the ring (no global
+                    // load on the chain)
+                    double *rys_s = (double *)((char *)v.sm + E.ka_hist_bytes), *al_s = rys_s + m;
                     auto jof = [&](int t) { return t < bound ? (end + m - 1 - t % m + m) % m : (end - bound + (t - bound) + 2 * m) % m; };
                     auto hissue = [&](int t) {
                         if (t < nsteps) {
@@ -787,6 +791,7 @@ __device__ int advance(const TpPool &E, const TpParams &p, const SlotView &v, in
                     double dreg[NR];
 #pragma unroll
                     for (int e = 0; e < NR; e++) { const int q = lane + 32 * e; dreg[e] = q < n ? v.d[q] : 0.0; }
+                    for (int t = lane; t < bound; t += 32) rys_s[t] = lys[(end + m - 1 - t % m + m) % m];
                     __syncwarp();
                     hissue(0); hissue(1); hissue(2);
                     const double scl = ys / yy;
@@ -797,8 +802,9 @@ __device__ int advance(const TpPool &E, const TpParams &p, const SlotView &v, in
                         const int j = jof(t);
                         const R *sv = hring + (size_t)(t % HR) * 2 * hstride, *yv = sv + hstride;
                         const bool first = t < bound;
-                        const double rysj = lys[j];
-                        const double alj = first ? 0.0 : lal[j];
+                        const int tf = first ? t : nsteps - 1 - t;       // the first-loop step that handled this history vector
+                        const double rysj = rys_s[tf];
+                        const double alj = first ? 0.0 : al_s[tf];
                         double pacc = 0.0;
                         double ax[NR];
 #pragma unroll
@@ -813,7 +819,7 @@ __device__ int advance(const TpPool &E, const TpParams &p, const SlotView &v, in
                         }
                         pacc = warp_sum(pacc);
                         double cf;
-                        if (first) { cf = -(pacc * rysj); if (lane == 0) lal[j] = -cf; }
+                        if (first) { cf = -(pacc * rysj); if (lane == 0) al_s[tf] = -cf; }
                         else cf = alj - pacc * rysj;
 #pragma unroll
                         for (int e = 0; e < NR; e++) if (e < ne) dreg[e] += cf * ax[e];

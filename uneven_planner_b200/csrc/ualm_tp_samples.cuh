@@ -220,69 +220,84 @@ __device__ __forceinline__ bool stencil_cell(const TpMap &m, R px, R py, R pw, i
     return true;
 }
 
-#define TP_NS 136            // per-chunk sample arrays: >= max(TP_KB_THREADS, K + 1) for K <= 128
-// per-sample products handed to the in-CTA reductions (SoA in shared memory)
+#define TP_YCAP 32           // yaw pieces per sample chunk that take the deterministic path (relative to the chunk's first one)
+// Reduction of the per-sample gradient products onto the control points (alm_traj_opt.cpp:969-985, 827), without atomics on the
+// common path: every thread forms its own contributions (basis x gradient), a segmented warp-shuffle reduction sums them per
+// piece (xy coefficients, xy time gradient) resp. per yaw piece (yaw coefficients, yaw time gradient), the run heads park the
+// per-warp partial sums in shared memory, and after one barrier a fixed-order sum over the warps writes the result.  The order of
+// every sum is fixed by the sample index, so a trajectory's result does not depend on what else runs.
 template <class R>
-struct ChunkArrays {
-    R gp0[TP_NS], gp1[TP_NS], gv0[TP_NS], gv1[TP_NS], ga0[TP_NS], ga1[TP_NS], gy[TP_NS], gdy[TP_NS], tx[TP_NS], ty[TP_NS], cost[TP_NS], sy1[TP_NS];
-    int yi[TP_NS];
-    int ylo[TP_NS], yhi[TP_NS];     // per yaw piece (index m - ymin of the chunk): first / last sample of the chunk that falls into it
+struct ChunkPart {
+    R xy[TP_KB_THREADS / 32][TP_MAXPPC][13];   // per warp, per piece of the chunk: 12 coefficient-gradient sums + the time-gradient sum
+    R yw[TP_KB_THREADS / 32][TP_YCAP][7];      // per warp, per yaw piece (index - ybase): 6 coefficient-gradient sums + the time-gradient sum
 };
-
-// in-CTA reduction of one chunk (pieces p0 .. p0 + np - 1, sample q = pl * (K + 1) + j) onto the control points:
-//   dcost/dc_xy block i  += sum_j beta0_k gp + beta1_k gv + beta2_k ga      (alm_traj_opt.cpp:969-972)   -> global, written once
-//   dcost/dT_xy(i)        = sum_j tx                                        (:827, 973-975, 984-985)     -> global
-//   dcost/dc_yaw block m += sum over samples with yaw_idx == m              (:977-983)                   -> shared accumulators
-//   dcost/dT_yaw(m)      += sum ty
 template <class R>
-__device__ __forceinline__ void reduce_chunk(const ChunkArrays<R> &A, int p0, int np, int K, R step, int N, int ymin, int ymax, int ybase, R *gdc_xy, R *gdt_xy,
-                                             R *accY, R *accTy, int tid, int nthreads)
+__device__ __forceinline__ void chunk_part_zero(ChunkPart<R> &P, int tid)
 {
-    const int nx = 6 * N, K1 = K + 1;
-    for (int t = tid; t < np * 13; t += nthreads) {
-        const int pl = t / 13, rem = t - 13 * pl, i = p0 + pl;
-        if (rem == 12) {
-            R acc = 0;
-            for (int j = 0; j < K1; j++) acc += A.tx[pl * K1 + j];
-            gdt_xy[i] = acc;
-        } else {
-            const int d = rem / 6, k = rem - 6 * d;
-            const R *gp = d ? A.gp1 : A.gp0, *gv = d ? A.gv1 : A.gv0, *ga = d ? A.ga1 : A.ga0;
-            R acc = 0;
-            for (int j = 0; j < K1; j++) {
-                const R s1 = (R)j * step;
-                R pw = 1, pw1 = 0, pw2 = 0;                 // s1^k, k s1^(k-1), k (k-1) s1^(k-2)
-                for (int e = 0; e < k; e++) { pw2 = pw2 * s1 + 2 * pw1; pw1 = pw1 * s1 + pw; pw = pw * s1; }
-                const int q = pl * K1 + j;
-                acc += pw * gp[q] + pw1 * gv[q] + pw2 * ga[q];
+    R *z = &P.xy[0][0][0];
+    for (int q = tid; q < (int)(sizeof(ChunkPart<R>) / sizeof(R)); q += TP_KB_THREADS) z[q] = 0;
+}
+// all 32 lanes of every warp call this (lanes without a sample pass on = false)
+template <class R>
+__device__ __forceinline__ void chunk_scatter(ChunkPart<R> &P, bool on, int pl, int yrel, R (&cx)[13], R (&cw)[7], R *accY, R *accTy, int ybase, int M)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k1 = on ? pl : -1, k2 = on ? yrel : -1;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int o1 = __shfl_down_sync(0xffffffffu, k1, off), o2 = __shfl_down_sync(0xffffffffu, k2, off);
+        const bool t1 = (lane + off < 32) && o1 == k1, t2 = (lane + off < 32) && o2 == k2;
+#pragma unroll
+        for (int e = 0; e < 13; e++) { const R v = __shfl_down_sync(0xffffffffu, cx[e], off); if (t1) cx[e] += v; }
+#pragma unroll
+        for (int e = 0; e < 7; e++) { const R v = __shfl_down_sync(0xffffffffu, cw[e], off); if (t2) cw[e] += v; }
+    }
+    const int p1 = __shfl_up_sync(0xffffffffu, k1, 1), p2 = __shfl_up_sync(0xffffffffu, k2, 1);
+    if (on && (lane == 0 || p1 != k1)) {
+#pragma unroll
+        for (int e = 0; e < 13; e++) P.xy[warp][pl][e] = cx[e];
+    }
+    if (on && (lane == 0 || p2 != k2)) {
+        if (yrel < TP_YCAP) {
+            // two runs of one yaw piece inside a warp only happen when rounding swaps two samples at a piece boundary: two addends commute
+#pragma unroll
+            for (int e = 0; e < 7; e++) atomicAdd(&P.yw[warp][yrel][e], cw[e]);
+        } else {           // more yaw pieces per chunk than the table holds (M >> N): straight onto the accumulators
+            const int m = ybase + yrel;
+            if (m < M) {
+#pragma unroll
+                for (int e = 0; e < 6; e++) atomicAdd(&accY[6 * m + e], cw[e]);
+                atomicAdd(&accTy[m], cw[6]);
             }
-            gdc_xy[d * nx + 6 * i + k] = acc;
         }
     }
-    const int ny = ymax - ymin + 1, ns = np * K1;
-    (void)ns;
-    for (int t = tid; t < ny * 7; t += nthreads) {
-        const int ml = t / 7, k = t - 7 * ml, m = ymin + ml;
-        R acc = 0;
-        const int qlo = A.ylo[m - ybase], qhi = A.yhi[m - ybase];
-        for (int q = qlo; q <= qhi; q++) {
-            if (A.yi[q] != m) continue;
-            if (k == 6) acc += A.ty[q];
-            else {
-                const R y1 = A.sy1[q];
-                R pw = 1, pw1 = 0;
-                for (int e = 0; e < k; e++) { pw1 = pw1 * y1 + pw; pw = pw * y1; }
-                acc += pw * A.gy[q] + pw1 * A.gdy[q];
-            }
-        }
-        if (k == 6) accTy[m] += acc; else accY[6 * m + k] += acc;
+}
+// after a barrier: fixed-order sums over the warps
+template <class R>
+__device__ __forceinline__ void chunk_gather(const ChunkPart<R> &P, int p0, int np, int N, int M, int ybase, R *gdc_xy, R *gdt_xy, R *accY, R *accTy, int tid)
+{
+    const int nx = 6 * N;
+    for (int t = tid; t < np * 13; t += TP_KB_THREADS) {
+        const int pl = t / 13, e = t - 13 * pl;
+        R s = 0;
+#pragma unroll
+        for (int w = 0; w < TP_KB_THREADS / 32; w++) s += P.xy[w][pl][e];
+        if (e < 12) gdc_xy[(e / 6) * nx + 6 * (p0 + pl) + (e % 6)] = s;
+        else gdt_xy[p0 + pl] = s;
+    }
+    for (int t = tid; t < TP_YCAP * 7; t += TP_KB_THREADS) {
+        const int yr = t / 7, e = t - 7 * yr, m = ybase + yr;
+        if (m >= M) continue;
+        R s = 0;
+#pragma unroll
+        for (int w = 0; w < TP_KB_THREADS / 32; w++) s += P.yw[w][yr][e];
+        if (e < 6) accY[6 * m + e] += s; else accTy[m] += s;
     }
 }
 
 struct KbShared {     // fixed part of kb_kernel's shared memory; the dynamic part follows (coefficients, yaw accumulators, tiles)
     uint64_t bar;
     int org[TP_MAXPPC][4];
-    int ymin, ymax;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -299,10 +314,10 @@ __global__ void __launch_bounds__(TP_KB_THREADS) kb_kernel(const __grid_constant
     if (ph != PH_REQ_FIRST && ph != PH_REQ_LS && ph != PH_REQ_EVALONLY) return;
     const int N = st->N, M = st->M, S = st->S, K = p.int_K, K1 = K + 1, nx = 6 * N, ny = 6 * M, tid = threadIdx.x;
     extern __shared__ __align__(128) unsigned char kb_smem[];
-    // layout: tiles (128-byte aligned, first) | ChunkArrays | c_xy (12N) | c_yaw (6M) | accY (6M) | accTy (M) | double red[8]
+    // layout: tiles (128-byte aligned, first) | ChunkPart | c_xy (12N) | c_yaw (6M) | accY (6M) | accTy (M)
     float4 *tiles = (float4 *)kb_smem;
-    ChunkArrays<R> &A = *(ChunkArrays<R> *)(kb_smem + (TMA ? TP_MAXPPC * TP_TILE_BYTES : 0));
-    R *cxy = (R *)(&A + 1);
+    ChunkPart<R> &P = *(ChunkPart<R> *)(kb_smem + (TMA ? TP_MAXPPC * TP_TILE_BYTES : 0));
+    R *cxy = (R *)(&P + 1);
     R *cyaw = cxy + 12 * N;
     R *accY = cyaw + ny;
     R *accTy = accY + ny;
@@ -333,25 +348,35 @@ __global__ void __launch_bounds__(TP_KB_THREADS) kb_kernel(const __grid_constant
         const int np = min(ppc, N - p0), ns = np * K1;
         // K + 1 > blockDim is handled by the stride loop below (one pass for the default K = 16: 7 pieces x 17 samples = 119 threads)
         if (tid < TP_MAXPPC) { sh.org[tid][0] = sh.org[tid][1] = sh.org[tid][2] = 0x7fffffff; sh.org[tid][3] = 0; }
-        if (tid == 0) { sh.ymin = 0x7fffffff; sh.ymax = -1; }
-        for (int q = tid; q < TP_NS; q += TP_KB_THREADS) { A.ylo[q] = 0x7fffffff; A.yhi[q] = -1; }
+        chunk_part_zero(P, tid);
         const int ybase = max(0, min((int)((R)p0 * Tx / Ty), M - 1) - 1);     // yaw piece of the chunk's first sample, one spare for rounding
         __syncthreads();
-        for (int qb = 0; qb < ns; qb += TP_KB_THREADS) {
-            const int q = qb + tid;
+        {
+            const int qb = 0, q = tid;       // one pass: ns <= TP_KB_THREADS (int_K <= 127 on this path)
             const bool on = q < ns;
+            R cx[13], cw[7], cost = 0;
+#pragma unroll
+            for (int e = 0; e < 13; e++) cx[e] = 0;
+#pragma unroll
+            for (int e = 0; e < 7; e++) cw[e] = 0;
             Kin<R> kq;
+            kq.yaw_idx = 0;
             R pos[2] = {0, 0}, yawn = 0;
             int pl = 0, j = 0, i = 0, s = 0;
             int ci0 = 0, ci1 = 0, ci2 = 0;
             bool inmap = false;
+            R lam = 0, mu6[6] = {0, 0, 0, 0, 0, 0}, sc7[7] = {1, 1, 1, 1, 1, 1, 1};
             if (on) {
                 pl = q / K1; j = q - pl * K1; i = p0 + pl; s = i * K1 + j;
+                // duals and scales of this sample (coalesced SoA): in flight while the spline is evaluated and the tiles arrive
+                lam = du[s];
+#pragma unroll
+                for (int t = 0; t < 6; t++) mu6[t] = du[(1 + t) * S + s];
+#pragma unroll
+                for (int t = 0; t < 7; t++) sc7[t] = du[(7 + t) * S + s];
                 kin_spline<R>(cxy + 6 * i, cxy + nx + 6 * i, cyaw, M, (R)j * step, (R)i * Tx, Ty, kq, pos);
                 yawn = norm_yaw(kq.yaw);
                 inmap = stencil_cell<R>(map, pos[0], pos[1], yawn, ci0, ci1, ci2);
-                atomicMin(&sh.ymin, kq.yaw_idx); atomicMax(&sh.ymax, kq.yaw_idx);
-                atomicMin(&A.ylo[kq.yaw_idx - ybase], q); atomicMax(&A.yhi[kq.yaw_idx - ybase], q);
                 if (TMA && inmap && qb == 0) { atomicMin(&sh.org[pl][0], ci0); atomicMin(&sh.org[pl][1], ci1); atomicMin(&sh.org[pl][2], ci2); }
             }
             if (qb == 0) kp.mark(1);
@@ -372,18 +397,12 @@ __global__ void __launch_bounds__(TP_KB_THREADS) kb_kernel(const __grid_constant
                 const bool has_tile = TMA && qb == 0 && sh.org[pl][3];
                 kin_terrain<R>(map, gravity, pos, yawn, tiles + (size_t)pl * (TP_TILE_BYTES / 16), sh.org[pl][0], sh.org[pl][1], sh.org[pl][2], has_tile, kq);
                 // ---- the seven penalty terms (alm_traj_opt.cpp:819-946) ----
-                const R lam = du[s];
-                R mu6[6], sc7[7];
-#pragma unroll
-                for (int t = 0; t < 6; t++) mu6[t] = du[(1 + t) * S + s];
-#pragma unroll
-                for (int t = 0; t < 7; t++) sc7[t] = du[(7 + t) * S + s];
                 R grad_p[2] = {0, 0}, grad_v[2] = {0, 0}, grad_a[2] = {0, 0}, grad_se2[3] = {0, 0, 0};
                 R grad_yaw = 0, grad_dyaw = 0, grad_vx2 = 0, grad_wz = 0, grad_ax = 0, grad_ay = 0;
                 const R icx = kq.tv[0], icy = kq.tv[2], cos_xi = kq.tv[4], inv_cos_xi = kq.tv[5], sigma = kq.tv[6];
                 const R omega = ((j == 0 || j == K) ? (R)0.5 : (R)1) * rho_ter * step * scale_fx;
                 const R user_cost = omega * sigma * sigma;
-                R cost = user_cost;
+                cost = user_cost;
 #pragma unroll
                 for (int k = 0; k < 3; k++) grad_se2[k] += omega * kq.tg[6][k] * sigma * 2;
                 {   // non-holonomic equality
@@ -461,26 +480,32 @@ __global__ void __launch_bounds__(TP_KB_THREADS) kb_kernel(const __grid_constant
                 // products for the reductions; direct time-gradient terms (alm_traj_opt.cpp:827, 973-975, 984-985; Q3: user_cost / K)
                 const R alpha = (R)j / (R)K;
                 const R ydot = grad_yaw * kq.dyaw + grad_dyaw * kq.d2yaw;
-                A.gp0[q] = grad_p[0]; A.gp1[q] = grad_p[1]; A.gv0[q] = grad_v[0]; A.gv1[q] = grad_v[1]; A.ga0[q] = grad_a[0]; A.ga1[q] = grad_a[1];
-                A.gy[q] = grad_yaw; A.gdy[q] = grad_dyaw; A.sy1[q] = kq.sy1; A.yi[q] = kq.yaw_idx;
-                A.tx[q] = user_cost / (R)K +
-                          ((grad_p[0] * kq.vel[0] + grad_p[1] * kq.vel[1]) + (grad_v[0] * kq.acc[0] + grad_v[1] * kq.acc[1]) + (grad_a[0] * kq.jer[0] + grad_a[1] * kq.jer[1])) * alpha +
-                          ydot * (alpha + (R)i);
-                A.ty[q] = -ydot * (R)kq.yaw_idx;
-                A.cost[q] = cost;
+                // this sample's contributions: basis x gradient (alm_traj_opt.cpp:969-983), the direct time-gradient terms (:827, 973-975, 984-985)
+#pragma unroll
+                for (int k = 0; k < 6; k++) {
+                    cx[k] = kq.b0[k] * grad_p[0] + kq.b1[k] * grad_v[0] + kq.b2[k] * grad_a[0];
+                    cx[6 + k] = kq.b0[k] * grad_p[1] + kq.b1[k] * grad_v[1] + kq.b2[k] * grad_a[1];
+                }
+                cx[12] = user_cost / (R)K +
+                         ((grad_p[0] * kq.vel[0] + grad_p[1] * kq.vel[1]) + (grad_v[0] * kq.acc[0] + grad_v[1] * kq.acc[1]) + (grad_a[0] * kq.jer[0] + grad_a[1] * kq.jer[1])) * alpha +
+                         ydot * (alpha + (R)i);
+                {
+                    const R y1 = kq.sy1;
+                    R pw = 1, pw1 = 0;
+#pragma unroll
+                    for (int k = 0; k < 6; k++) { cw[k] = pw * grad_yaw + pw1 * grad_dyaw; pw1 = pw1 * y1 + pw; pw = pw * y1; }
+                }
+                cw[6] = -ydot * (R)kq.yaw_idx;
             }
+            kp.mark(3);
+            chunk_scatter<R>(P, on, pl, kq.yaw_idx - ybase, cx, cw, accY, accTy, ybase, M);
+            cost_acc += (double)cost;
         }
         parity ^= 1u;
-        kp.mark(3);
         __syncthreads();
         kp.mark(4);
-        reduce_chunk<R>(A, p0, np, K, step, N, sh.ymin, sh.ymax, ybase, gdc, gdt, accY, accTy, tid, TP_KB_THREADS);
+        chunk_gather<R>(P, p0, np, N, M, ybase, gdc, gdt, accY, accTy, tid);
         kp.mark(5);
-        {
-            double c = 0.0;
-            for (int q = tid; q < ns; q += TP_KB_THREADS) c += (double)A.cost[q];
-            cost_acc += c;
-        }
         __syncthreads();
     }
     // yaw accumulators and the cost out
@@ -512,16 +537,15 @@ __global__ void __launch_bounds__(TP_KB_THREADS) ks_kernel(const __grid_constant
     if (!st->need_scale || st->phase == PH_NEW || st->phase == PH_DONE || st->phase == PH_FREE) return;
     const int N = st->N, M = st->M, S = st->S, K = p.int_K, K1 = K + 1, nx = 6 * N, ny = 6 * M, tid = threadIdx.x;
     extern __shared__ __align__(128) unsigned char ks_smem[];
-    // layout: ChunkArrays | c_xy (12N) | c_yaw (6M) | gf_xy (12N) | gf_yaw (6M) | gT (N + M) | z_xy (12N) | z_yaw (6M)
-    ChunkArrays<R> &A = *(ChunkArrays<R> *)ks_smem;
-    R *cxy = (R *)(&A + 1);
+    // layout: ChunkPart | c_xy (12N) | c_yaw (6M) | gf_xy (12N) | gf_yaw (6M) | gT (N + M) | z_xy (12N) | z_yaw (6M)
+    ChunkPart<R> &P = *(ChunkPart<R> *)ks_smem;
+    R *cxy = (R *)(&P + 1);
     R *cyaw = cxy + 12 * N;
     R *gfx = cyaw + ny;
     R *gfy = gfx + 12 * N;
     R *gT = gfy + ny;
     R *zx = gT + N + M;
     R *zy = zx + 12 * N;
-    __shared__ int s_ymin, s_ymax;
     __shared__ double s_red[TP_KB_THREADS / 32][3];
     const double *cd = E.cd + (size_t)slot * TP_CSTRIDE, *zd = E.gw + (size_t)slot * TP_CSTRIDE;
     for (int q = tid; q < 2 * nx; q += TP_KB_THREADS) { cxy[q] = (R)cd[q]; zx[q] = (R)zd[q]; }
@@ -539,20 +563,26 @@ __global__ void __launch_bounds__(TP_KB_THREADS) ks_kernel(const __grid_constant
     __syncthreads();
     for (int p0 = 0; p0 < N; p0 += ppc) {
         const int np = min(ppc, N - p0), ns = np * K1;
-        if (tid == 0) { s_ymin = 0x7fffffff; s_ymax = -1; }
-        for (int q = tid; q < TP_NS; q += TP_KB_THREADS) { A.ylo[q] = 0x7fffffff; A.yhi[q] = -1; }
+        chunk_part_zero(P, tid);
         const int ybase = max(0, min((int)((R)p0 * Tx / Ty), M - 1) - 1);
         __syncthreads();
-        for (int qb = 0; qb < ns; qb += TP_KB_THREADS) {
-            const int q = qb + tid;
-            if (q >= ns) continue;
-            const int pl = q / K1, j = q - pl * K1, i = p0 + pl, s = i * K1 + j;
+        {
+            const int q = tid;               // one pass: ns <= TP_KB_THREADS (int_K <= 127 on this path)
+            const bool on = q < ns;
+            R cx[13], cw[7];
+#pragma unroll
+            for (int e = 0; e < 13; e++) cx[e] = 0;
+#pragma unroll
+            for (int e = 0; e < 7; e++) cw[e] = 0;
             Kin<R> kq;
+            kq.yaw_idx = 0;
+            int pl = 0;
+            if (on) {
+            pl = q / K1;
+            const int j = q - pl * K1, i = p0 + pl, s = i * K1 + j;
             R pos[2];
             kin_spline<R>(cxy + 6 * i, cxy + nx + 6 * i, cyaw, M, (R)j * step, (R)i * Tx, Ty, kq, pos);
             kin_terrain<R>(map, gravity, pos, norm_yaw(kq.yaw), nullptr, 0, 0, 0, false, kq);
-            atomicMin(&s_ymin, kq.yaw_idx); atomicMax(&s_ymax, kq.yaw_idx);
-            atomicMin(&A.ylo[kq.yaw_idx - ybase], q); atomicMax(&A.yhi[kq.yaw_idx - ybase], q);
             const R alpha = (R)j / (R)K;
             const int yi = kq.yaw_idx;
             const R icx = kq.tv[0], icy = kq.tv[2], inv_cos_xi = kq.tv[5];
@@ -636,14 +666,21 @@ __global__ void __launch_bounds__(TP_KB_THREADS) ks_kernel(const __grid_constant
             const R user_cost = omega * sigma * sigma;
             R gs[3];
             for (int k = 0; k < 3; k++) gs[k] = omega * kq.tg[6][k] * sigma * 2;
-            A.gp0[q] = gs[0]; A.gp1[q] = gs[1]; A.gv0[q] = 0; A.gv1[q] = 0; A.ga0[q] = 0; A.ga1[q] = 0; A.gy[q] = gs[2]; A.gdy[q] = 0;
-            A.sy1[q] = kq.sy1; A.yi[q] = yi;
-            A.tx[q] = user_cost / (R)K + (gs[0] * kq.vel[0] + gs[1] * kq.vel[1]) * alpha + gs[2] * kq.dyaw * (alpha + (R)i);
-            A.ty[q] = -(gs[2] * kq.dyaw) * (R)yi;
-            A.cost[q] = 0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) { cx[k] = kq.b0[k] * gs[0]; cx[6 + k] = kq.b0[k] * gs[1]; }
+            cx[12] = user_cost / (R)K + (gs[0] * kq.vel[0] + gs[1] * kq.vel[1]) * alpha + gs[2] * kq.dyaw * (alpha + (R)i);
+            {
+                const R y1 = kq.sy1;
+                R pw = 1;
+#pragma unroll
+                for (int k = 0; k < 6; k++) { cw[k] = pw * gs[2]; pw *= y1; }
+            }
+            cw[6] = -(gs[2] * kq.dyaw) * (R)yi;
+            }
+            chunk_scatter<R>(P, on, pl, kq.yaw_idx - ybase, cx, cw, gfy, gT + N, ybase, M);
         }
         __syncthreads();
-        reduce_chunk<R>(A, p0, np, K, step, N, s_ymin, s_ymax, ybase, gfx, gT, gfy, gT + N, tid, TP_KB_THREADS);
+        chunk_gather<R>(P, p0, np, N, M, ybase, gfx, gT, gfy, gT + N, tid);
         __syncthreads();
     }
     // f gradient: + jerk part (no x1000 factor here: Q7), then waypoint rows / time part as above
