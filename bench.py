@@ -449,13 +449,10 @@ def main():
                     "traffic": traffic.get("penalty_only_kernel_bytes_per_launch_config%d" % args.config), "kernel_ms": pms}
         out = {}
         for tma in (1, 0):
-            if tma:
-                os.environ.pop("UALM_TP_NOTMA", None)
-            else:
-                os.environ["UALM_TP_NOTMA"] = "1"
+            os.environ["UALM_TP_TMA"] = "1" if tma else "0"
             pms, pbytes = o.time_penalty_kernel(10)
-            out["tma_tiles" if tma else "direct_gather"] = {"kernel_ms": pms, "achieved": pbytes / (pms * 1e-3) / 1e9, "frac": pbytes / (pms * 1e-3) / 1e9 / peak}
-        os.environ.pop("UALM_TP_NOTMA", None)
+            out["tma_tiles" if tma else "direct_gather (default)"] = {"kernel_ms": pms, "achieved": pbytes / (pms * 1e-3) / 1e9, "frac": pbytes / (pms * 1e-3) / 1e9 / peak}
+        os.environ.pop("UALM_TP_TMA", None)
         best = max(out.values(), key=lambda v: v["achieved"])
         return {"kernel": "ualm_tp::kb_kernel<%s> (calConstrainCostGrad: thread per sample, CTA per trajectory, 1 evaluation per trajectory, the whole batch in one launch)" % ("float" if precision == 32 else "double"),
                 "bound": "hbm", "achieved": best["achieved"], "peak": peak, "unit": "GB/s", "frac": best["frac"], "kernel_ms": best["kernel_ms"],

@@ -142,7 +142,7 @@ def test_results_do_not_depend_on_batching_or_tile_staging(gpu, hill_map):
         opt.submit(pbs[1], depth=1)
     opt.wait(t)
     opt.close()
-    for env in ({"UALM_TP_NOTMA": "1"}, {"UALM_TP_SUBGROUPS": "4"}):
+    for env in ({"UALM_TP_TMA": "1"}, {"UALM_TP_SUBGROUPS": "4"}):      # TMA-staged map tiles instead of the direct gather; more groups per batch
         os.environ.update(env)
         try:
             o2 = gpu.BatchALMTrajOpt(precision=32).init(params).set_environment(hill_map)

@@ -91,7 +91,7 @@ if what in ("all", "perf"):
         print("PERF prec %d B=%d depth %d: %.1f ms/step, %.0f conv/s, %.0f solved/s (conv %d)" % (prec, B, depth, ms / steps, conv * steps / ms * 1e3, B * steps / ms * 1e3, conv), flush=True)
     opt.select_lane(0); opt.upload(pb)
     for tma in (1, 0):
-        if not tma: os.environ["UALM_TP_NOTMA"] = "1"
+        os.environ["UALM_TP_TMA"] = "1" if tma else "0"
         pms, pbytes = opt.time_penalty_kernel(10)
         print("PENALTY prec %d B=%d tma=%d: %.4f ms/launch, %.1f MB algorithmic, %.1f GB/s" % (prec, B, tma, pms, pbytes / 1e6, pbytes / pms / 1e6), flush=True)
 opt.close()

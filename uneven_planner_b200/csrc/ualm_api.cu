@@ -837,7 +837,7 @@ extern "C" int ualm_init_scaling_batch(ualm_ctx_t *c, double *scale_fx, double *
 extern "C" int ualm_time_penalty_kernel(ualm_ctx_t *c, int reps, float *ms_per_launch, double *algorithmic_bytes)
 {
     if (reps < 1) return fail(UALM_EINVAL, "reps < 1");
-    if (c && c->tp) TP_CALL(ualm_tp::tp_time_penalty(c->tp, c->cur, reps, getenv("UALM_TP_NOTMA") ? 0 : 1, ms_per_launch, algorithmic_bytes, err));
+    if (c && c->tp) TP_CALL(ualm_tp::tp_time_penalty(c->tp, c->cur, reps, (getenv("UALM_TP_TMA") && atoi(getenv("UALM_TP_TMA"))) ? 1 : 0, ms_per_launch, algorithmic_bytes, err));
     if (!c || !c->b->have_batch || !c->have_map) return fail(UALM_ESTATE, "upload and set_map first");
     Lane *l = c->b;
     if (l->n_active != l->B) return fail(UALM_ELIMIT, "ualm_time_penalty_kernel: the uploaded batch holds problems over the compiled limits");

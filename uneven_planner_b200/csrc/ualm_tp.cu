@@ -67,7 +67,7 @@ struct TpEngine {
     TpMap map;
     CUtensorMap tmap;
     bool have_tmap = false;
-    int use_tma = 1;
+    int use_tma = 0;              // map corners of kb_kernel: 0 = direct gather through L1 (default: measured faster), 1 = TMA-staged tiles (UALM_TP_TMA=1)
     Buf<float4> cells;
     // pool
     TpPool E;
@@ -140,7 +140,8 @@ int tp_create(TpEngine **out, int device, int precision, std::string *err)
     TCK(cudaSetDevice(device));
     TpEngine *e = new TpEngine();
     e->device = device; e->precision = precision;
-    if (const char *s = getenv("UALM_TP_NOTMA")) e->use_tma = atoi(s) ? 0 : 1;
+    if (const char *s = getenv("UALM_TP_TMA")) e->use_tma = atoi(s) ? 1 : 0;
+    if (const char *s = getenv("UALM_TP_NOTMA")) { if (atoi(s)) e->use_tma = 0; }
     if (const char *s = getenv("UALM_TP_CHUNK")) e->chunk = std::max(1, atoi(s));
     if (const char *s = getenv("UALM_TP_PROFILE")) e->prof = atoi(s) != 0;
     if (const char *s = getenv("UALM_TP_SUBGROUPS")) e->sg = std::min(TP_SUBGROUPS, std::max(1, atoi(s)));
