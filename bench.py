@@ -33,6 +33,15 @@ UNIT = "traj/s"
 ROUND = "r02"
 
 
+_T0 = time.perf_counter()
+
+
+def note(msg):
+    """progress on stderr (stdout carries the one JSON line)"""
+    sys.stderr.write("[bench %7.1f s] %s\n" % (time.perf_counter() - _T0, msg))
+    sys.stderr.flush()
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -334,8 +343,10 @@ def main():
         for lane in range(depth):
             opt.select_lane(lane)
             opt.upload(pb)
+        note("precision %d: uploaded, warm-up" % precision)
         run_steps(max(warmup, 1))
         barrier()
+        note("precision %d: timed region (%d steps, depth %d)" % (precision, steps, depth))
         sampler = ClockSampler(local_rank)
         if rank == 0 and with_clocks:
             sampler.start()
@@ -378,6 +389,7 @@ def main():
                 conv += sum(1 for q in r if q.ret_code == 0)
             return conv
         e2e_steps = max(depth, min(steps, 2 * depth))
+        note("precision %d: value done (%.1f ms/step), e2e" % (precision, ms / steps))
         run_e2e(depth)
         barrier()
         t0 = time.perf_counter()
@@ -399,7 +411,7 @@ def main():
         """independent check of a solved, collected batch (outside the timed region): the reference's post-solve scan
         (getMaxVxAxAyCurAttSig + getNonHolError, 0.01 s sampling) on the GPU, rank-local"""
         feas = opt.feasibility(0.01)
-        okc = np.array([r.ret_code == 0 for r in res])
+        okc = np.array([r.ret_code == 0 for r in res]) & (feas[:, 7] >= 0)
         tol = 1.05
         within = (np.abs(feas[:, 0]) <= params.max_vel * tol) & (np.abs(feas[:, 1]) <= params.max_acc_lon * tol) & \
                  (np.abs(feas[:, 2]) <= params.max_acc_lat * tol) & (np.abs(feas[:, 3]) <= params.max_kap * tol) & \
@@ -476,9 +488,10 @@ def main():
     fast = None
     if head_prec == 64 and not args.no_fast:
         fdepth = 8
-        rf = measure(32, fdepth, max(args.steps, 2 * fdepth), max(args.warmup, fdepth), False)
+        rf = measure(32, fdepth, max(args.steps, fdepth + 4), max(min(args.warmup, fdepth), 2), False)
         fo = rf["opt"]
         fo.select_lane(0)
+        note("fast path measured; post-solve scan")
         fq = quality_of(fo, rf["res"])
         fev = np.array([r.n_evals for r in rf["res"]])
         fo.select_lane(0); fo.upload(pb)
@@ -492,6 +505,7 @@ def main():
         fo.close()
 
     # ---------------- CPU baseline on this box's host cores (rank 0, bounded sample) ----------------
+    note("GPU arms done; cpu baseline")
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))

@@ -176,7 +176,8 @@ int ualm_profile(ualm_ctx_t *ctx, int enable, long long *out16);
 /* Post-solve quality scan of the solved resident batch: ALMTrajOpt::getMaxVxAxAyCurAttSig
  * (alm_traj_opt.h:170-229) and SE2Trajectory::getNonHolError (se2traj.hpp:551-561), sampled every dt (0.01 in the
  * reference).  out10[10 * b + ...] = {max_vx, max_ax, max_ay, max_cur, max_att (= -min cos xi), max_sig, nonhol_error,
- * number of samples, T_xy piece duration, T_yaw piece duration}. */
+ * number of samples, T_xy piece duration, T_yaw piece duration}.  A trajectory whose duration would need more than 4e6 samples (a
+ * diverged solve) is not scanned: zeros and a sample count of -1. */
 int ualm_feasibility_batch(ualm_ctx_t *ctx, double dt, double *out10);
 
 /* UnevenMap construction on the GPU (UnevenMap::init preprocessing on the host, then constructMap + filter,

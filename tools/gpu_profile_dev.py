@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 from uneven_planner_b200 import maps, problems, _lib, api
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 m = maps.get_terrain("hill") or maps.synthetic_terrain("bumps")
-pb = problems.generate(m, B, seed=1)
+pb = problems.generate(m, B, seed=0)
 opt = api.BatchALMTrajOpt().init(_lib.default_params()).set_environment(m)
 opt.upload(pb)
 opt.profile(True)

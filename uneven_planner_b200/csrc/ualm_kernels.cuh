@@ -2292,6 +2292,16 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) feasibility_kernel(co
     for (int i = 0; i < N; i++) tot_xy += Tx;
     for (int i = 0; i < M; i++) tot_yaw += Ty;
     const R total = tot_xy < tot_yaw ? tot_xy : tot_yaw;
+    // a diverged solve can leave an astronomically long (or non-finite) duration: the reference's scan would then run (almost) forever.
+    // Such a trajectory is reported as "not scanned": zeros and a sample count of -1.
+    if (!(total / dt < 4.0e6)) {
+        if (lane == 0) {
+            R *o = out + 10 * (size_t)prob;
+            for (int q = 0; q < 7; q++) o[q] = 0.0;
+            o[7] = -1.0; o[8] = Tx; o[9] = Ty;
+        }
+        return;
+    }
     AbsMax mvx, max_, may, mcur;
     mvx.init(); max_.init(); may.init(); mcur.init();
     R matt = -1.0, msig = 0.0, err = 0.0;

@@ -83,7 +83,7 @@ struct TpEngine {
     int gscale[TP_NGROUPS] = {};          // rounds that still have to run ks_kernel
     bool gcompact[TP_NGROUPS] = {};
     long long grounds[TP_NGROUPS] = {};
-    int sg = 2;                           // subgroups per batch in use (UALM_TP_SUBGROUPS, <= TP_SUBGROUPS)
+    int sg = 1;                           // subgroups per batch in use (UALM_TP_SUBGROUPS, <= TP_SUBGROUPS); 1 measured best: the batches in flight already are the groups
     int Nmax_live = 1, Mmax_live = 1;
     Buf<TpState> st;
     Buf<int> active, n_active, remaining;
