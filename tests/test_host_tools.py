@@ -169,3 +169,13 @@ def test_config_table_matches_reference_yaml(built):
     assert p4.max_kap == 0.3 and p4.int_K == 64 and p4.max_sig == 0.08 and p4.use_scaling == 1
     pf = configs.params_for("forest")
     assert pf.use_scaling == 0 and pf.rho_T == 500.0 and pf.max_sig == 0.001
+
+
+def test_snapshot_to_the_gpu_box_includes_every_map():
+    """maps_built/*.umap travel with the gpurun snapshot (they cannot be rebuilt on the GPU box, which has no reference clouds): a
+    development-time exclusion left in .gpurunignore would silently turn configs 3-5 into the synthetic fallback"""
+    import os
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), ".gpurunignore")
+    if os.path.exists(p):
+        lines = [l.strip() for l in open(p) if l.strip() and not l.startswith("#")]
+        assert not [l for l in lines if "maps_built" in l or "umap" in l or "libualm" in l or "_ref" in l], lines

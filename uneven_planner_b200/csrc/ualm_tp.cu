@@ -87,10 +87,9 @@ struct TpEngine {
     int Nmax_live = 1, Mmax_live = 1;
     Buf<TpState> st;
     Buf<int> active, n_active, remaining;
-    Buf<double> vec, cd, gw, kb_cost, lm_ys, lm_alpha, lu;
+    Buf<double> vec, cd, gw, kb_cost, lm_ys, lm_alpha, wf, wt;
     Buf<unsigned char> cr, gdc, gdt, dual, hs, hy, wway;
-    Buf<int> lu_off;
-    Buf<long long> wway_off, kprof;
+    Buf<long long> wf_off, wway_off, kprof;
     int *h_remaining = nullptr;   // pinned
     TpLane lanes[TP_LANES];
     long long rounds_total = 0;
@@ -98,35 +97,44 @@ struct TpEngine {
     bool prof = false;            // developer profile (UALM_TP_PROFILE=1): in-kernel phase cycle counters, printed at destroy
 };
 
+// The columns of A(1)^-1 a MINCO right-hand side can excite, for every piece count (ualm_tp_kernels.cuh: w_tables_kernel).  The LU
+// factors they are solved with are scratch
 static int build_tables(TpEngine *e, std::string *err)
 {
     const int Pmax = TP_MMAX;
     std::vector<int> lu_off(Pmax + 1, 0);
-    std::vector<long long> w_off(Pmax + 1, 0);
-    size_t lu_tot = 0, w_tot = 0;
+    std::vector<long long> wf_off(Pmax + 1, 0), w_off(Pmax + 1, 0);
+    size_t lu_tot = 0, wf_tot = 0, w_tot = 0;
     for (int P = 1; P <= Pmax; P++) {
         lu_off[P] = (int)(lu_tot + (size_t)TP_FPAD * TP_FW);
         lu_tot += (size_t)(6 * P + 2 * TP_FPAD) * TP_FW;
+        wf_off[P] = (long long)wf_tot;
+        wf_tot += (size_t)(P + 5) * 6 * P;
         w_off[P] = (long long)w_tot;
         w_tot += (size_t)std::max(P - 1, 0) * 6 * P;
     }
-    TCK(e->lu.ensure(lu_tot));
-    TCK(e->lu_off.ensure(Pmax + 1));
+    Buf<double> lu;
+    Buf<int> d_lu_off;
+    TCK(lu.ensure(lu_tot));
+    TCK(d_lu_off.ensure(Pmax + 1));
+    TCK(e->wf_off.ensure(Pmax + 1));
     TCK(e->wway_off.ensure(Pmax + 1));
+    TCK(e->wf.ensure(wf_tot));
+    TCK(e->wt.ensure(w_tot));
     TCK(e->wway.ensure(w_tot * e->esz()));
-    TCK(cudaMemcpyAsync(e->lu_off.p, lu_off.data(), sizeof(int) * (Pmax + 1), cudaMemcpyHostToDevice, e->stream));
+    TCK(cudaMemcpyAsync(d_lu_off.p, lu_off.data(), sizeof(int) * (Pmax + 1), cudaMemcpyHostToDevice, e->stream));
+    TCK(cudaMemcpyAsync(e->wf_off.p, wf_off.data(), sizeof(long long) * (Pmax + 1), cudaMemcpyHostToDevice, e->stream));
     TCK(cudaMemcpyAsync(e->wway_off.p, w_off.data(), sizeof(long long) * (Pmax + 1), cudaMemcpyHostToDevice, e->stream));
-    lu_tables_kernel<<<(Pmax + 31) / 32, 32, 0, e->stream>>>(e->lu.p, e->lu_off.p, Pmax);
+    lu_tables_kernel<<<(Pmax + 31) / 32, 32, 0, e->stream>>>(lu.p, d_lu_off.p, Pmax);
     TCK(cudaGetLastError());
-    Buf<double> scratch;
-    const int tpb = 64, gx = (Pmax - 1 + tpb - 1) / tpb;
-    TCK(scratch.ensure((size_t)(Pmax - 1) * gx * tpb * 6 * TP_MMAX));
-    dim3 grid(gx, Pmax - 1);
-    if (e->f32()) wway_tables_kernel<float><<<grid, tpb, 0, e->stream>>>(e->lu.p, e->lu_off.p, (float *)e->wway.p, e->wway_off.p, scratch.p, Pmax);
-    else wway_tables_kernel<double><<<grid, tpb, 0, e->stream>>>(e->lu.p, e->lu_off.p, (double *)e->wway.p, e->wway_off.p, scratch.p, Pmax);
+    const int tpb = 32, gx = (Pmax + 5 + tpb - 1) / tpb;
+    dim3 grid(gx, Pmax);
+    if (e->f32()) w_tables_kernel<float><<<grid, tpb, 0, e->stream>>>(lu.p, d_lu_off.p, e->wf.p, e->wf_off.p, e->wt.p, (float *)e->wway.p, e->wway_off.p, Pmax);
+    else w_tables_kernel<double><<<grid, tpb, 0, e->stream>>>(lu.p, d_lu_off.p, e->wf.p, e->wf_off.p, e->wt.p, (double *)e->wway.p, e->wway_off.p, Pmax);
     TCK(cudaGetLastError());
     TCK(cudaStreamSynchronize(e->stream));
-    scratch.release();
+    lu.release();
+    d_lu_off.release();
     return UALM_OK;
 }
 
@@ -200,8 +208,8 @@ void tp_destroy(TpEngine *e)
         if (l.ev1) cudaEventDestroy(l.ev1);
     }
     e->cells.release(); e->st.release(); e->active.release(); e->n_active.release(); e->remaining.release(); e->vec.release(); e->cd.release(); e->gw.release();
-    e->kb_cost.release(); e->lm_ys.release(); e->lm_alpha.release(); e->lu.release(); e->cr.release(); e->gdc.release(); e->gdt.release(); e->dual.release();
-    e->hs.release(); e->hy.release(); e->wway.release(); e->lu_off.release(); e->wway_off.release();
+    e->kb_cost.release(); e->lm_ys.release(); e->lm_alpha.release(); e->cr.release(); e->gdc.release(); e->gdt.release(); e->dual.release();
+    e->hs.release(); e->hy.release(); e->wway.release(); e->wf.release(); e->wt.release(); e->wf_off.release(); e->wway_off.release();
     if (e->h_remaining) cudaFreeHost(e->h_remaining);
     if (e->evA) cudaEventDestroy(e->evA);
     if (e->evB) cudaEventDestroy(e->evB);
@@ -289,7 +297,7 @@ static int pool_alloc(TpEngine *e, int cap, std::string *err)
     E.st = e->st.p; E.active = e->active.p; E.n_active = e->n_active.p; E.remaining = e->remaining.p;
     E.vec = e->vec.p; E.cd = e->cd.p; E.gw = e->gw.p; E.cr = e->f32() ? (void *)e->cr.p : (void *)e->cd.p; E.gdc = e->gdc.p; E.gdt = e->gdt.p;
     E.kb_cost = e->kb_cost.p; E.dual = e->dual.p; E.hs = e->hs.p; E.hy = e->hy.p; E.lm_ys = e->lm_ys.p; E.lm_alpha = e->lm_alpha.p;
-    E.lu = e->lu.p; E.lu_off = e->lu_off.p; E.wway = e->wway.p; E.wway_off = e->wway_off.p;
+    E.wf = e->wf.p; E.wf_off = e->wf_off.p; E.wt = e->wt.p; E.wway = e->wway.p; E.wway_off = e->wway_off.p;
     E.prof = nullptr;
     if (e->prof) { TCK(e->kprof.ensure(32)); TCK(cudaMemsetAsync(e->kprof.p, 0, 32 * sizeof(long long), e->stream)); E.prof = e->kprof.p; }
     e->capacity = cap;
@@ -458,8 +466,8 @@ static size_t ks_smem_bytes(TpEngine *e)
     const size_t coef = ((size_t)12 * e->Nmax_live * 3 + (size_t)6 * e->Mmax_live * 3 + e->Nmax_live + e->Mmax_live) * es;
     return ((arrays + 15) & ~(size_t)15) + coef + 64;
 }
-// ka_kernel's shared memory per warp: column buffer (12 N + 6 M doubles of the largest live problem), aliased by the two-loop's
-// history ring (4 slots x {s, y} x n elements), followed by the factor ring
+// ka_kernel's shared memory per warp: the C^-1 dcost/dc vector (12 N + 6 M doubles of the largest live problem), aliased by the
+// right-hand sides of the forward pass and by the two-loop's history ring (4 slots x {s, y} x n elements)
 static void ka_layout(TpEngine *e)
 {
     const int nmax = 1 + 2 * (e->Nmax_live - 1) + (e->Mmax_live - 1);
@@ -469,7 +477,7 @@ static void ka_layout(TpEngine *e)
     e->E.ka_col_bytes = (int)((std::max(col, hist + 2 * (size_t)e->p.mem_size * 8) + 15) & ~(size_t)15);
     e->E.ka_hist_stride = hstride;
 }
-static size_t ka_smem_bytes(TpEngine *e) { return (size_t)TP_KA_WARPS * (e->E.ka_col_bytes + 2 * TP_RING * TP_BLK * 8); }
+static size_t ka_smem_bytes(TpEngine *e) { return (size_t)TP_KA_WARPS * e->E.ka_col_bytes; }
 
 // one round of group g on its stream: ka -> [ks] -> kb
 template <class R>

@@ -5,19 +5,22 @@
 //
 //   * LOCKSTEP EVALUATION ROUNDS with continuous batching.  A pool of trajectory slots holds every problem in flight (several
 //     batches).  One round = one cost/gradient evaluation of every active trajectory, as three bulk kernels:
-//       ka_kernel  one WARP per trajectory: finishes the previous evaluation (adjoint banded solve, gradient assembly), runs the
+//       ka_kernel  one WARP per trajectory: finishes the previous evaluation (gradient assembly through the tables), runs the
 //                  per-trajectory control flow up to the next evaluation request (Lewis-Overton line search, L-BFGS two-loop on the
-//                  coalesced [slot][n] history, ALM dual update / convergence) and the MINCO forward solve for the new point;
+//                  coalesced [slot][n] history, ALM dual update / convergence) and the MINCO coefficients of the new point;
 //       ks_kernel  (rounds after an admission only) initScaling, one CTA per new trajectory, one thread per constraint sample;
 //       kb_kernel  the per-constraint-sample penalty cost + gradient (calConstrainCostGrad): one CTA per trajectory, one thread per
 //                  sample, the UnevenMap tiles of the pieces staged into shared memory by TMA (cp.async.bulk.tensor + mbarrier),
 //                  duals / scales / constraint values streamed as coalesced SoA arrays, gradients reduced onto the control
 //                  points in shared memory.
 //     Finished trajectories leave the active list, new ones join between rounds: no trajectory waits for a batch mate.
-//   * The MINCO system is NONDIMENSIONALISED: piece durations are uniform (alm_traj_opt.h:257-261), so A(T) = R(T) A(1) C(T) with
-//     diagonal R, C; A(1) depends only on the piece count and is LU-factored ONCE per piece count at engine creation.  An
-//     evaluation only runs the triangular sweeps.  initScaling uses the waypoint rows of A(1)^-T (dense, precomputed per piece
-//     count) and one extra forward solve instead of one adjoint solve per constraint.
+//   * The MINCO system is NONDIMENSIONALISED AND SOLVED ONCE: piece durations are uniform (alm_traj_opt.h:257-261), so
+//     A(T) = R(T) A(1) C(T) with diagonal R = diag(T^-ord), C = diag(T^k), and A(1) depends only on the piece count P.  A MINCO
+//     right-hand side is non-zero in P + 5 rows only (head / tail position, velocity, acceleration and the P - 1 waypoints), so
+//     the P + 5 columns of A(1)^-1 those rows excite are tabulated per piece count at engine creation and an evaluation needs NO
+//     banded solve at all:  c = C^-1 W b^ (rows over lanes),  dcost/dq = W^T C^-1 dcost/dc (waypoints over lanes),  and because the
+//     T-dependence of c is explicit (c^ = c^0 + T c^1 + T^2 c^2) so is dc/dT -- the adjoint solve and the B1/B2 contraction of
+//     calGradCTtoQT (se2traj.hpp:751-816) collapse into one dot product with z = dc/dT.  initScaling uses the same tables.
 //   * Mixed precision: ka_kernel (short serial chains, latency bound) always computes in double; the penalty kernel computes
 //     in R = float (precision 32) or double (precision 65); duals, constraint values, exchanged gradients and the L-BFGS history are
 //     stored in R.
@@ -103,7 +106,7 @@ struct TpPool {
     int *remaining;         // per ticket: trajectories not yet done
     double *vec;            // [cap][5][TP_NVAR]  x | g | xp | gp | d
     double *cd;             // [cap][TP_CSTRIDE]  coefficients of the last forward solve (double)
-    double *gw;             // [cap][TP_CSTRIDE]  adjoint workspace / the z vectors of initScaling
+    double *gw;             // [cap][TP_CSTRIDE]  z = dc/dT(piece) of the last forward solve (same layout as cd)
     void *cr;               // [cap][TP_CSTRIDE]  R copy of the coefficients for the sample kernels (== cd when R is double)
     void *gdc;              // [cap][TP_CSTRIDE]  R  constraint part of dcost/dc from kb_kernel
     void *gdt;              // [cap][TP_TSTRIDE]  R  constraint part of dcost/dT
@@ -111,9 +114,10 @@ struct TpPool {
     void *dual;             // [cap][TP_NDUAL * Smax]  R  (field f of slot s at s * 21 * Smax + f * S_slot)
     void *hs, *hy;          // [cap][m][TP_NVAR]  R  L-BFGS history, vector j of slot s at (s * m + j) * TP_NVAR
     double *lm_ys, *lm_alpha;   // [cap][m]
-    const double *lu;       // factor tables of A(1): table of P pieces at lu_off[P] (row 0; TP_FPAD zero rows on both sides)
-    const int *lu_off;      // [TP_MMAX + 1]
-    const void *wway;       // R  waypoint rows of A(1)^-T: (P - 1) x 6P at wway_off[P]
+    const double *wf;       // W[P][j][r]  = A(1)^-1 (r, J(j)), j < P + 5 (rhs_row): (P + 5) x 6P at wf_off[P]
+    const long long *wf_off;
+    const double *wt;       // WT[P][r][w] = A(1)^-1 (r, 6w + 5): 6P x (P - 1) at wway_off[P] (the waypoint columns, transposed)
+    const void *wway;       // R  the waypoint columns again, [w][r]: (P - 1) x 6P at wway_off[P]  (ks_kernel)
     const long long *wway_off;
     long long *prof;        // developer profile: [16] SM-cycle sums per ka phase (lane 0 of every warp), or null
 };
@@ -234,171 +238,35 @@ __device__ inline void solve_a1_serial(const double *F, int n6, double *b)
         b[r] = v * F[r * TP_FW + 13];
     }
 }
-// Wway[P][w][c] = (A(1)^-T)(6w+5, c) = (A(1)^-1 e_{6w+5})(c)
+// Row of the MINCO right-hand side that column j < P + 5 of the tables belongs to (se2traj.hpp:609-674): 0..2 head position /
+// velocity / acceleration, then the P - 1 waypoint rows 6w + 5, then the three tail rows
+__device__ __host__ __forceinline__ int rhs_row(int P, int j) { return j < 3 ? j : (j < P + 2 ? 6 * (j - 3) + 5 : 6 * P - 3 + (j - (P + 2))); }
+
+// One thread per (piece count, column): solve A(1) x = e_row in place in the W table, then scatter the waypoint columns into
+// the transposed table and the R copy ks_kernel reads
 template <class R>
-__global__ void wway_tables_kernel(const double *lu, const int *lu_off, R *wway, const long long *wway_off, double *scratch, int Pmax)
+__global__ void w_tables_kernel(const double *lu, const int *lu_off, double *wf, const long long *wf_off, double *wt, R *wway, const long long *wway_off, int Pmax)
 {
-    const int P = blockIdx.y + 2;
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (P > Pmax || w >= P - 1) return;
+    const int P = blockIdx.y + 1;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (P > Pmax || j >= P + 5) return;
     const int n6 = 6 * P;
-    double *b = scratch + ((size_t)(blockIdx.y * gridDim.x * blockDim.x) + w) * (6 * TP_MMAX);
+    double *b = wf + wf_off[P] + (size_t)j * n6;
     for (int r = 0; r < n6; r++) b[r] = 0.0;
-    b[6 * w + 5] = 1.0;
+    b[rhs_row(P, j)] = 1.0;
     solve_a1_serial(lu + lu_off[P], n6, b);
-    R *o = wway + wway_off[P] + (size_t)w * n6;
-    for (int r = 0; r < n6; r++) o[r] = (R)b[r];
+    if (j >= 3 && j < P + 2) {
+        const int w = j - 3;
+        double *t = wt + wway_off[P];
+        R *o = wway + wway_off[P] + (size_t)w * n6;
+        for (int r = 0; r < n6; r++) { t[(size_t)r * (P - 1) + w] = b[r]; o[r] = (R)b[r]; }
+    }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// triangular sweeps of the prefactored A(1): lanes 0 / 1 solve the x / y columns of the xy system, lane 2 the yaw column,
-// in lockstep (rolling 6-entry register window, static indices after unrolling)
-// ---------------------------------------------------------------------------------------------------------------------
-// One pass over the prefactored A(1) of both systems.  The factor rows stream through a per-warp shared-memory ring by cp.async
-// (all 32 lanes stage; prefetch distance two blocks of six rows), lanes 0 / 1 / 2 run the dependent chains of the x / y / yaw
-// columns with a rolling six-entry register window (static indices after unrolling); the right-hand sides of the next block are
-// fetched while the current block is solved, so no global-memory latency sits on the chain.
-//   KIND 0: L y = b      ascending,   L(r, r-d)  = F[r][6-d]
-//   KIND 1: U x = y      descending,  U(r, r+d)  = F[r][6+d], then * F[r][13] (= 1 / U(r, r))
-//   KIND 2: U^T y = b    ascending,   U(r-d, r)  = F[r-d][6+d], then * F[r][13]
-//   KIND 3: L^T x = y    descending,  L(r+d, r)  = F[r+d][6-d]
-#define TP_RING 5
-#define TP_BLK (6 * TP_FW)
-// Static non-zero structure of the LU factors of the MINCO matrix (symbolic elimination; period 6 in the row index, the last
-// block -- tail position / velocity / acceleration rows -- is dense for the L-based kinds): bit d-1 of the mask of row type
-// t = r mod 6 says whether the term with offset d can be non-zero.  Supersets of the numeric pattern, so skipped terms are exact zeros.
-__host__ __device__ constexpr unsigned long long tp_pack6(int a, int b, int c, int d, int e, int f)
-{
-    return (unsigned long long)a | ((unsigned long long)b << 6) | ((unsigned long long)c << 12) | ((unsigned long long)d << 18) |
-           ((unsigned long long)e << 24) | ((unsigned long long)f << 30);
-}
-__host__ __device__ constexpr int tp_sweep_mask(int kind, int t)
-{
-    return (int)(((kind == 0 ? tp_pack6(0x3f, 0x3e, 0x3c, 0x00, 0x00, 0x1f)      // L rows
-                 : kind == 1 ? tp_pack6(0x0c, 0x06, 0x03, 0x23, 0x21, 0x18)      // U rows
-                 : kind == 2 ? tp_pack6(0x00, 0x00, 0x00, 0x2f, 0x3f, 0x03)      // U columns
-                             : tp_pack6(0x30, 0x38, 0x3c, 0x1e, 0x0f, 0x07))     // L columns
-                  >> (6 * t)) & 0x3f);
-}
 __device__ __forceinline__ void cp_async16(unsigned dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int NP>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NP) : "memory"); }
-
-struct SweepSys {
-    const double *Fxy, *Fyaw;   // row 0 of the factor tables
-    int N, M;                   // blocks (= pieces) of the xy / yaw system
-    double *col;                // this lane's column (lanes 0, 1: xy; lane 2: yaw), else unused
-    double *ring;               // this warp's ring: [2][TP_RING][TP_BLK]
-};
-
-// six rows of one block.  Dependent-chain discipline (an fp64 FMA that waits for its operand costs a full pipeline latency): per
-// row only ONE FMA may wait for the previous row's result -- terms with older neighbours (d = 3..6) are summed first on two
-// accumulators, then d = 2, and the newest neighbour (d = 1) enters last; divisions are folded into pre-scaled factors off the chain.
-template <int KIND, bool FULL>
-__device__ __forceinline__ void block_rows(const double *f, const double *g, bool hasg, const double (&rhs)[6], double (&w)[6], double (&out)[6])
-{
-    constexpr bool ASC = (KIND == 0 || KIND == 2);
-#pragma unroll
-    for (int tt = 0; tt < 6; tt++) {
-        const int t = ASC ? tt : 5 - tt;
-        const int mask = FULL ? 0x3f : tp_sweep_mask(KIND, t);
-        double fs[7];
-#pragma unroll
-        for (int d = 1; d <= 6; d++) {
-            double fv = 0.0;
-            if ((mask >> (d - 1)) & 1) {
-                if (KIND == 0) fv = f[t * TP_FW + 6 - d];
-                else if (KIND == 1) fv = f[t * TP_FW + 6 + d];
-                else if (KIND == 2) fv = (t - d >= 0) ? f[(t - d) * TP_FW + 6 + d] : (hasg ? g[(t - d + 6) * TP_FW + 6 + d] : 0.0);
-                else fv = (t + d <= 5) ? f[(t + d) * TP_FW + 6 - d] : (hasg ? g[(t + d - 6) * TP_FW + 6 - d] : 0.0);
-            }
-            fs[d] = fv;
-        }
-        double r0 = rhs[t];
-        if (KIND == 1 || KIND == 2) {
-            const double rd = f[t * TP_FW + 13];
-            r0 *= rd;
-#pragma unroll
-            for (int d = 1; d <= 6; d++) if ((mask >> (d - 1)) & 1) fs[d] *= rd;
-        }
-#define TP_W(d) (ASC ? w[(t - (d) + 6) % 6] : w[(t + (d)) % 6])
-#define TP_TERM(d) (((mask >> ((d) - 1)) & 1) ? fs[d] * TP_W(d) : 0.0)
-        const double pa = r0 - TP_TERM(6) - TP_TERM(4);
-        const double pb = -TP_TERM(5) - TP_TERM(3);
-        double v = (pa + pb) - TP_TERM(2);
-        v -= TP_TERM(1);
-#undef TP_TERM
-#undef TP_W
-        w[t] = v;
-        out[t] = v;
-    }
-}
-
-template <int KIND>
-__device__ __forceinline__ void sweep_pass(const SweepSys &s, int lane)
-{
-    constexpr bool ASC = (KIND == 0 || KIND == 2);
-    const int nb = max(s.N, s.M);
-    const int sys = lane == 2 ? 1 : 0, P = sys ? s.M : s.N;
-    const bool consumer = lane < 3;
-    const unsigned ring0 = (unsigned)__cvta_generic_to_shared(s.ring);
-    auto issue = [&](int c) {
-        if (c < s.N) {
-            const int blk = ASC ? c : s.N - 1 - c;
-            const double *src = s.Fxy + (size_t)blk * TP_BLK;
-            const unsigned dst = ring0 + 8u * (unsigned)((c % TP_RING) * TP_BLK);
-            for (int q = lane; q < TP_BLK / 2; q += 32) cp_async16(dst + 16u * q, src + 2 * q);
-        }
-        if (c < s.M) {
-            const int blk = ASC ? c : s.M - 1 - c;
-            const double *src = s.Fyaw + (size_t)blk * TP_BLK;
-            const unsigned dst = ring0 + 8u * (unsigned)((TP_RING + c % TP_RING) * TP_BLK);
-            for (int q = lane; q < TP_BLK / 2; q += 32) cp_async16(dst + 16u * q, src + 2 * q);
-        }
-        cp_async_commit();
-    };
-    const double *myring = s.ring + (size_t)sys * TP_RING * TP_BLK;
-    double w[6] = {0, 0, 0, 0, 0, 0}, rhs[6] = {0, 0, 0, 0, 0, 0}, nrhs[6] = {0, 0, 0, 0, 0, 0};
-    issue(0);
-    issue(1);
-    issue(2);
-    if (consumer && 0 < P) {
-        const int blk = ASC ? 0 : P - 1;
-#pragma unroll
-        for (int t = 0; t < 6; t++) rhs[t] = s.col[6 * blk + t];
-    }
-    for (int c = 0; c < nb; c++) {
-        issue(c + 3);
-        cp_async_wait<3>();
-        __syncwarp();
-        const bool on = consumer && c < P;
-        const int blk = ASC ? c : P - 1 - c;
-        if (consumer && c + 1 < P) {          // right-hand sides of the next block
-            const int nblk = ASC ? c + 1 : P - 2 - c;
-#pragma unroll
-            for (int t = 0; t < 6; t++) nrhs[t] = s.col[6 * nblk + t];
-        }
-        if (on) {
-            const double *f = myring + (size_t)(c % TP_RING) * TP_BLK;               // this block's six factor rows
-            const double *g = myring + (size_t)((c + TP_RING - 1) % TP_RING) * TP_BLK;   // the block processed just before
-            const bool hasg = c > 0;
-            double out[6];
-            if ((KIND == 0 || KIND == 3) && blk == P - 1) block_rows<KIND, true>(f, g, hasg, rhs, w, out);
-            else block_rows<KIND, false>(f, g, hasg, rhs, w, out);
-#pragma unroll
-            for (int t = 0; t < 6; t++) s.col[6 * blk + t] = out[t];
-        }
-#pragma unroll
-        for (int t = 0; t < 6; t++) rhs[t] = nrhs[t];
-        __syncwarp();
-    }
-    cp_async_wait<0>();
-    __syncwarp();
-}
-// A(1) x = b and A(1)^T x = b, in place
-__device__ __forceinline__ void sweep_forward(const SweepSys &s, int lane) { sweep_pass<0>(s, lane); sweep_pass<1>(s, lane); }
-__device__ __forceinline__ void sweep_adjoint(const SweepSys &s, int lane) { sweep_pass<2>(s, lane); sweep_pass<3>(s, lane); }
 
 // jerk energy of one piece and its T-derivative (se2traj.hpp:702-707, 739-744); a = first column block, b = second (or null)
 __device__ __forceinline__ void jerk_piece(const double *a, const double *b, double T1, double T2, double T3, double T4, double T5, double &e, double &gt)
@@ -416,178 +284,165 @@ __device__ __forceinline__ double jerk_gc(const double *c6, int k, double T1, do
     if (k == 3) return 72.0 * c3 * T1 + 144.0 * c4 * T2 + 240.0 * c5 * T3;
     return 0.0;
 }
-// the B1 / B2 vectors of calGradCTtoQT (se2traj.hpp:763-814): coefficient k of row j of piece i's time-gradient contraction
-__device__ __forceinline__ void time_b(const double *cc, double T1, double T2, double T3, double T4, double &nv, double &na, double &nj, double &ns, double &nc)
-{
-    nv = -(cc[1] + 2.0 * T1 * cc[2] + 3.0 * T2 * cc[3] + 4.0 * T3 * cc[4] + 5.0 * T4 * cc[5]);
-    na = -(2.0 * cc[2] + 6.0 * T1 * cc[3] + 12.0 * T2 * cc[4] + 20.0 * T3 * cc[5]);
-    nj = -(6.0 * cc[3] + 24.0 * T1 * cc[4] + 60.0 * T2 * cc[5]);
-    ns = -(24.0 * cc[4] + 120.0 * T1 * cc[5]);
-    nc = -120.0 * cc[5];
-}
-
 struct SlotView {
     TpState *st;
     double *x, *g, *xp, *gp, *d;
     double *cd, *gw;
-    const double *Fxy, *Fyaw;
-    double *ring;              // this warp's factor ring in shared memory
-    double *sm;                // this warp's column buffer in shared memory (12N + 6M doubles; aliased by the two-loop's history ring)
+    double *sm;                // this warp's buffer in shared memory (12N + 6M doubles; aliased by the two-loop's history ring)
     int N, M, n, S, slot;
 };
 
-__device__ __forceinline__ SlotView slot_view(const TpPool &E, int slot, double *sm, double *ring)
+__device__ __forceinline__ SlotView slot_view(const TpPool &E, int slot, double *sm)
 {
     SlotView v;
     v.slot = slot;
     v.sm = sm;
-    v.ring = ring;
     v.st = E.st + slot;
     v.N = v.st->N; v.M = v.st->M; v.n = v.st->n; v.S = v.st->S;
     double *vb = E.vec + (size_t)slot * 5 * TP_NVAR;
     v.x = vb; v.g = vb + TP_NVAR; v.xp = vb + 2 * TP_NVAR; v.gp = vb + 3 * TP_NVAR; v.d = vb + 4 * TP_NVAR;
     v.cd = E.cd + (size_t)slot * TP_CSTRIDE;
     v.gw = E.gw + (size_t)slot * TP_CSTRIDE;
-    v.Fxy = E.lu + E.lu_off[v.N];
-    v.Fyaw = E.lu + E.lu_off[v.M];
     return v;
 }
 
-// The three columns live in the warp's shared-memory column buffer during a solve: x at [0, 6N), y at [6N, 12N), yaw at [12N, 12N + 6M)
-// (global coefficient blocks keep the yaw column at TP_CYAW).  sweeps in place on v.sm.
-__device__ __forceinline__ void solve_sm(const SlotView &v, bool adjoint, int lane)
+__device__ __forceinline__ void load6(const double *p, double (&w)[6])
 {
-    SweepSys sc;
-    sc.Fxy = v.Fxy; sc.Fyaw = v.Fyaw; sc.N = v.N; sc.M = v.M; sc.ring = v.ring;
-    sc.col = v.sm + (lane == 2 ? 12 * v.N : (lane == 1 ? 6 * v.N : 0));
-    __syncwarp();
-    if (adjoint) sweep_adjoint(sc, lane); else sweep_forward(sc, lane);
-    __syncwarp();
+    const double2 a = __ldg((const double2 *)p), b = __ldg((const double2 *)p + 1), c = __ldg((const double2 *)p + 2);
+    w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y; w[4] = c.x; w[5] = c.y;
 }
 
-// MINCO forward for the decision vector in v.x (alm_traj_opt.cpp:293-299 + se2traj.hpp:595-680, nondimensionalised):
-// leaves the coefficients in v.cd (and their R copy), T / Tx / Ty / jerk_raw in the state
+// one 6-coefficient block out of the table pass: c_k = c^_k T^-k, z_k = dc_k/dT = T^-k dc^_k/dT - k c_k / T; stores c (double and
+// the sample kernels' R copy) and z, returns the block's jerk energy
+// (se2traj.hpp:697-710, 852-855: per piece 36 c3^2 T + 144 c3 c4 T^2 + 192 c4^2 T^3 + 240 c3 c5 T^3 + 720 c4 c5 T^4 + 720 c5^2 T^5)
+template <class R>
+__device__ __forceinline__ double emit_block(const double (&ch)[6], const double (&eh)[6], double T1, double *c, R *cr, double *z)
+{
+    const double rT = 1.0 / T1;
+    double inv[6];
+    inv[0] = 1.0;
+#pragma unroll
+    for (int k = 1; k < 6; k++) inv[k] = inv[k - 1] * rT;
+    double c6[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        c6[k] = ch[k] * inv[k];
+        c[k] = c6[k];
+        if (sizeof(R) != sizeof(double)) cr[k] = (R)c6[k];
+        z[k] = eh[k] * inv[k] - (double)k * c6[k] * rT;
+    }
+    const double T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2, T5 = T4 * T1;
+    return 36.0 * c6[3] * c6[3] * T1 + 144.0 * c6[4] * c6[3] * T2 + 192.0 * c6[4] * c6[4] * T3 + 240.0 * c6[5] * c6[3] * T3 + 720.0 * c6[5] * c6[4] * T4 +
+           720.0 * c6[5] * c6[5] * T5;
+}
+
+// MINCO forward for the decision vector in v.x (alm_traj_opt.cpp:293-299 + se2traj.hpp:595-680) through the tabulated columns of
+// A(1)^-1: one lane per piece (both columns of an xy piece share the table loads), a loop over the P + 5 excitable right-hand-side
+// rows, no dependence between lanes.  Leaves the coefficients in v.cd (and their R copy), z = dc/dT(piece) in v.gw, and
+// T / Tx / Ty / jerk_raw in the state
 template <class R>
 __device__ void minco_forward(const TpPool &E, const SlotView &v, int lane, KProf &kp)
 {
     TpState *st = v.st;
-    const int N = v.N, M = v.M, nx = 6 * N, ny = 6 * M;
+    const int N = v.N, M = v.M, nx = 6 * N;
     const double tau = v.x[0];
     const double T = expC2(tau), Tx = T / (double)N, Ty = T / (double)M;
-    double *sm = v.sm;
-    for (int q = lane; q < 2 * nx + ny; q += 32) sm[q] = 0.0;
-    __syncwarp();
+    // nondimensional right-hand sides (se2traj.hpp:615-617, 672-674 scaled by T^ord): [head p, v T, a T^2 | waypoints | tail p, v T, a T^2]
+    double *bx = v.sm, *by = bx + (N + 5), *bw = by + (N + 5);
     const double *bnd = st->bnd;
     const double *Pxy = v.x + 1, *Pyaw = v.x + 1 + 2 * (N - 1);
-    if (lane < 2) {       // head / tail position, velocity, acceleration rows scaled by T^ord (se2traj.hpp:615-617, 672-674)
+    if (lane < 2) {
         const int d = lane;
-        sm[0 + d * nx] = bnd[d]; sm[1 + d * nx] = bnd[d + 2] * Tx; sm[2 + d * nx] = bnd[d + 4] * Tx * Tx;
-        sm[nx - 3 + d * nx] = bnd[6 + d]; sm[nx - 2 + d * nx] = bnd[6 + d + 2] * Tx; sm[nx - 1 + d * nx] = bnd[6 + d + 4] * Tx * Tx;
+        double *b = d ? by : bx;
+        b[0] = bnd[d]; b[1] = bnd[d + 2] * Tx; b[2] = bnd[d + 4] * Tx * Tx;
+        b[N + 2] = bnd[6 + d]; b[N + 3] = bnd[6 + d + 2] * Tx; b[N + 4] = bnd[6 + d + 4] * Tx * Tx;
     }
     if (lane == 2) {
-        double *y = sm + 2 * nx;
-        y[0] = bnd[12]; y[1] = bnd[13] * Ty; y[2] = bnd[14] * Ty * Ty;
-        y[ny - 3] = bnd[15]; y[ny - 2] = bnd[16] * Ty; y[ny - 1] = bnd[17] * Ty * Ty;
+        bw[0] = bnd[12]; bw[1] = bnd[13] * Ty; bw[2] = bnd[14] * Ty * Ty;
+        bw[M + 2] = bnd[15]; bw[M + 3] = bnd[16] * Ty; bw[M + 4] = bnd[17] * Ty * Ty;
     }
-    for (int i = lane; i < N - 1; i += 32) { sm[6 * i + 5] = Pxy[2 * i]; sm[6 * i + 5 + nx] = Pxy[2 * i + 1]; }
-    for (int i = lane; i < M - 1; i += 32) sm[2 * nx + 6 * i + 5] = Pyaw[i];
+    for (int i = lane; i < N - 1; i += 32) { bx[3 + i] = Pxy[2 * i]; by[3 + i] = Pxy[2 * i + 1]; }
+    for (int i = lane; i < M - 1; i += 32) bw[3 + i] = Pyaw[i];
+    __syncwarp();
     kp.mark(KP_FWD_PRE);
-    solve_sm(v, false, lane);
-    kp.mark(KP_FWD_SWEEP);
-    // c_k = c^_k T^-k: one lane per 6-coefficient block; out to global (double + the sample kernels' R copy); jerk energy on the way
-    // (se2traj.hpp:697-710, 852-855: per piece 36 c3^2 T + 144 c3 c4 T^2 + 192 c4^2 T^3 + 240 c3 c5 T^3 + 720 c4 c5 T^4 + 720 c5^2 T^5)
-    double ix[6], iy[6];
-    ix[0] = iy[0] = 1.0;
-#pragma unroll
-    for (int k = 1; k < 6; k++) { ix[k] = ix[k - 1] / Tx; iy[k] = iy[k - 1] / Ty; }
-    const double X1 = Tx, X2 = Tx * Tx, X3 = X2 * Tx, X4 = X2 * X2, X5 = X4 * Tx;
-    const double Y1 = Ty, Y2 = Ty * Ty, Y3 = Y2 * Ty, Y4 = Y2 * Y2, Y5 = Y4 * Ty;
-    double *c = v.cd;
+    const double *Wn = E.wf + E.wf_off[N], *Wm = E.wf + E.wf_off[M];
+    double *c = v.cd, *z = v.gw;
     R *cr = (R *)E.cr + (size_t)v.slot * TP_CSTRIDE;
     double e = 0.0;
-    for (int blk = lane; blk < 2 * N + M; blk += 32) {
-        const bool isy = blk >= 2 * N;
-        const int off = isy ? TP_CYAW + 6 * (blk - 2 * N) : 6 * blk;
-        double c6[6];
+    // One code path for xy and yaw pieces (a yaw lane carries an unused second column): lanes only differ in trip count, so the
+    // warp never executes the two kinds one after the other.  Four table rows in flight per step: the loop is bound by the latency
+    // of its loads, not by their number; rows past the end are clamped and weighted zero.
+    for (int q = lane; q < N + M; q += 32) {
+        const bool isy = q >= N;
+        const int P = isy ? M : N, i = isy ? q - N : q, n6 = 6 * P, nj = P + 5;
+        const double *Wp = (isy ? Wm : Wn) + 6 * i;
+        const double *b0 = isy ? bw : bx, *b1 = isy ? bw : by;
+        const double T1 = isy ? Ty : Tx;
+        double a0[6] = {0, 0, 0, 0, 0, 0}, a1[6] = {0, 0, 0, 0, 0, 0};
+        for (int j0 = 0; j0 < nj; j0 += 4) {
+            double wa[6], wb[6], wc[6], wd[6];
+            const int j1 = min(j0 + 1, nj - 1), j2 = min(j0 + 2, nj - 1), j3 = min(j0 + 3, nj - 1);
+            load6(Wp + (size_t)j0 * n6, wa); load6(Wp + (size_t)j1 * n6, wb); load6(Wp + (size_t)j2 * n6, wc); load6(Wp + (size_t)j3 * n6, wd);
+            const double xa = b0[j0], ya = b1[j0];
+            const double xb = j0 + 1 < nj ? b0[j1] : 0.0, yb = j0 + 1 < nj ? b1[j1] : 0.0;
+            const double xc = j0 + 2 < nj ? b0[j2] : 0.0, yc = j0 + 2 < nj ? b1[j2] : 0.0;
+            const double xd = j0 + 3 < nj ? b0[j3] : 0.0, yd = j0 + 3 < nj ? b1[j3] : 0.0;
 #pragma unroll
-        for (int k = 0; k < 6; k++) c6[k] = sm[6 * blk + k] * (isy ? iy[k] : ix[k]);
-#pragma unroll
-        for (int k = 0; k < 6; k++) c[off + k] = c6[k];
-        if (sizeof(R) != sizeof(double)) {
-#pragma unroll
-            for (int k = 0; k < 6; k++) cr[off + k] = (R)c6[k];
+            for (int k = 0; k < 6; k++) {
+                a0[k] += wa[k] * xa; a1[k] += wa[k] * ya; a0[k] += wb[k] * xb; a1[k] += wb[k] * yb;
+                a0[k] += wc[k] * xc; a1[k] += wc[k] * yc; a0[k] += wd[k] * xd; a1[k] += wd[k] * yd;
+            }
         }
-        const double T1 = isy ? Y1 : X1, T2 = isy ? Y2 : X2, T3 = isy ? Y3 : X3, T4 = isy ? Y4 : X4, T5 = isy ? Y5 : X5;
-        e += 36.0 * c6[3] * c6[3] * T1 + 144.0 * c6[4] * c6[3] * T2 + 192.0 * c6[4] * c6[4] * T3 + 240.0 * c6[5] * c6[3] * T3 + 720.0 * c6[5] * c6[4] * T4 +
-             720.0 * c6[5] * c6[5] * T5;
+        // dc^/dT: the velocity (T) and acceleration (T^2) columns only
+        double e0[6], e1[6];
+        {
+            double wa[6], wb[6], wc[6], wd[6];
+            load6(Wp + (size_t)1 * n6, wa); load6(Wp + (size_t)(P + 3) * n6, wb); load6(Wp + (size_t)2 * n6, wc); load6(Wp + (size_t)(P + 4) * n6, wd);
+            const double t2 = 2.0 * T1;
+            const double vh0 = isy ? bnd[13] : bnd[2], vt0 = isy ? bnd[16] : bnd[8], ah0 = t2 * (isy ? bnd[14] : bnd[4]), at0 = t2 * (isy ? bnd[17] : bnd[10]);
+            const double vh1 = bnd[3], vt1 = bnd[9], ah1 = t2 * bnd[5], at1 = t2 * bnd[11];
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                e0[k] = vh0 * wa[k] + vt0 * wb[k] + (ah0 * wc[k] + at0 * wd[k]);
+                e1[k] = vh1 * wa[k] + vt1 * wb[k] + (ah1 * wc[k] + at1 * wd[k]);
+            }
+        }
+        const int off0 = isy ? TP_CYAW + 6 * i : 6 * i;
+        e += emit_block<R>(a0, e0, T1, c + off0, cr + off0, z + off0);
+        if (!isy) e += emit_block<R>(a1, e1, T1, c + nx + 6 * i, cr + nx + 6 * i, z + nx + 6 * i);
     }
+    kp.mark(KP_FWD_SWEEP);
     e = warp_sum(e);
     if (lane == 0) { st->tau = tau; st->T = T; st->Tx = Tx; st->Ty = Ty; st->jerk_raw = e; }
     __syncwarp();
     kp.mark(KP_FWD_POST);
 }
 
-// initScaling support: z = A(T)^-1 u with u the B1 / B2 contraction vectors of calGradCTtoQT, so that for any dcost/dc vector g
-// sum_i (B . adjoint)(i) = z . g  (one extra forward solve instead of one adjoint solve per constraint).  z -> v.gw
-__device__ void scaling_z(const SlotView &v, int lane)
-{
-    const TpState *st = v.st;
-    const int N = v.N, M = v.M, nx = 6 * N, ny = 6 * M;
-    const double Tx = st->Tx, Ty = st->Ty;
-    double *sm = v.sm;
-    const double *c = v.cd;
-    for (int q = lane; q < 2 * nx + ny; q += 32) sm[q] = 0.0;
-    __syncwarp();
-    for (int q = lane; q < 2 * N + M; q += 32) {
-        const bool isy = q >= 2 * N;
-        const int P = isy ? M : N, i = isy ? q - 2 * N : q % N, d = isy ? 0 : q / N;
-        const double T1 = isy ? Ty : Tx, T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2;
-        const double *cc = c + (isy ? TP_CYAW : d * nx) + 6 * i;
-        double *u = sm + (isy ? 2 * nx : d * nx);
-        double nv, na, nj, ns, nc;
-        time_b(cc, T1, T2, T3, T4, nv, na, nj, ns, nc);
-        // rows 6i+3..6i+8 (orders 3, 4, 0, 0, 1, 2) resp. the last three rows (orders 0, 1, 2); right-hand side scaled by T^ord
-        if (i < P - 1) {
-            u[6 * i + 3] = ns * T3; u[6 * i + 4] = nc * T4; u[6 * i + 5] = nv; u[6 * i + 6] = nv; u[6 * i + 7] = na * T1; u[6 * i + 8] = nj * T2;
-        } else {
-            u[6 * P - 3] = nv; u[6 * P - 2] = na * T1; u[6 * P - 1] = nj * T2;
-        }
-    }
-    solve_sm(v, false, lane);
-    double ix[6], iy[6];
-    ix[0] = iy[0] = 1.0;
-#pragma unroll
-    for (int k = 1; k < 6; k++) { ix[k] = ix[k - 1] / Tx; iy[k] = iy[k - 1] / Ty; }
-    double *z = v.gw;
-    for (int q = lane; q < 2 * nx; q += 32) z[q] = sm[q] * ix[q % 6];
-    for (int q = lane; q < ny; q += 32) z[TP_CYAW + q] = sm[2 * nx + q] * iy[q % 6];
-    __syncwarp();
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
 // ka_kernel pieces
 // ---------------------------------------------------------------------------------------------------------------------
 // finish the evaluation whose sample part kb_kernel left in gdc / gdt / kb_cost: f -> st->f_last, gradient -> v.g
-// (alm_traj_opt.cpp:318-346, se2traj.hpp:751-816)
+// (alm_traj_opt.cpp:318-346; se2traj.hpp:751-816 through the tables: dq = W^T C^-1 dcost/dc, dT = z . dcost/dc + explicit terms)
 template <class R>
 __device__ void finish_eval(const TpPool &E, const TpParams &p, const SlotView &v, int lane, KProf &kp)
 {
     TpState *st = v.st;
-    const int N = v.N, M = v.M, nx = 6 * N, ny = 6 * M;
+    const int N = v.N, M = v.M, nx = 6 * N;
     const double Tx = st->Tx, Ty = st->Ty, scale_fx = st->scale_fx;
     const double js = (p.use_scaling ? TP_SCALE_TRICK_JERK : 1.0) * scale_fx;
     const double X1 = Tx, X2 = Tx * Tx, X3 = X2 * Tx, X4 = X2 * X2, X5 = X4 * Tx;
     const double Y1 = Ty, Y2 = Ty * Ty, Y3 = Y2 * Ty, Y4 = Y2 * Y2, Y5 = Y4 * Ty;
-    const double *c = v.cd;
-    double *sm = v.sm;
+    const double *c = v.cd, *z = v.gw;
+    double *sm = v.sm;             // g^ = C^-1 dcost/dc: x at [0, 6N), y at [6N, 12N), yaw at [12N, 12N + 6M)
     const R *gdc = (const R *)E.gdc + (size_t)v.slot * TP_CSTRIDE;
     const R *gdt = (const R *)E.gdt + (size_t)v.slot * TP_TSTRIDE;
     double ix[6], iy[6];
     ix[0] = iy[0] = 1.0;
 #pragma unroll
     for (int k = 1; k < 6; k++) { ix[k] = ix[k - 1] / Tx; iy[k] = iy[k - 1] / Ty; }
-    // dcost/dc = jerk part + constraint part, scaled by T^-k for the nondimensional adjoint (alm_traj_opt.cpp:322-332);
-    // one lane per 6-coefficient block: the jerk gradient needs c3..c5 of the block only (se2traj.hpp:719-737)
+    // dcost/dc = jerk part + constraint part (alm_traj_opt.cpp:322-332); one lane per 6-coefficient block: the jerk gradient
+    // needs c3..c5 of the block only (se2traj.hpp:719-737).  Its dot product with z is the implicit part of the time gradient
+    double sx = 0.0, sy = 0.0;
     for (int blk = lane; blk < 2 * N + M; blk += 32) {
         const bool isy = blk >= 2 * N;
         const int off = isy ? TP_CYAW + 6 * (blk - 2 * N) : 6 * blk;
@@ -599,34 +454,62 @@ __device__ void finish_eval(const TpPool &E, const TpParams &p, const SlotView &
         g6[3] += (72.0 * c3 * T1 + 144.0 * c4 * T2 + 240.0 * c5 * T3) * js;
         g6[4] += (144.0 * c3 * T2 + 384.0 * c4 * T3 + 720.0 * c5 * T4) * js;
         g6[5] += (240.0 * c3 * T3 + 720.0 * c4 * T4 + 1440.0 * c5 * T5) * js;
+        double td = 0.0;
 #pragma unroll
-        for (int k = 0; k < 6; k++) sm[6 * blk + k] = g6[k] * (isy ? iy[k] : ix[k]);
+        for (int k = 0; k < 6; k++) td += g6[k] * z[off + k];
+        if (isy) {
+            sy += td;
+            double *o = sm + 12 * N + 6 * (blk - 2 * N);
+#pragma unroll
+            for (int k = 0; k < 6; k++) o[k] = g6[k] * iy[k];
+        } else {
+            sx += td;
+            double *o = sm + 6 * blk;
+#pragma unroll
+            for (int k = 0; k < 6; k++) o[k] = g6[k] * ix[k];
+        }
     }
-    kp.mark(KP_FIN_PRE);
-    solve_sm(v, true, lane);
-    kp.mark(KP_FIN_SWEEP);
-    // adjoint row r of the dimensional system = w_r T^ord(r).  Time gradients (se2traj.hpp:763-814) and their sums
-    double sx = 0.0, sy = 0.0;
+    // explicit time dependence of the jerk energy and of the constraint samples, per piece (se2traj.hpp:739-744; gdt from kb_kernel)
     for (int q = lane; q < N + M; q += 32) {
         const bool isy = q >= N;
-        const int P = isy ? M : N, i = isy ? q - N : q;
+        const int i = isy ? q - N : q;
         const double T1 = isy ? Ty : Tx, T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2, T5 = T4 * T1;
         double e, gj;
         jerk_piece(c + (isy ? TP_CYAW : 0) + 6 * i, isy ? nullptr : c + nx + 6 * i, T1, T2, T3, T4, T5, e, gj);
-        double gt = gj * js + (double)gdt[isy ? TP_NMAX + i : i];
-        for (int d = 0; d < (isy ? 1 : 2); d++) {
-            const double *cc = c + (isy ? TP_CYAW : d * nx) + 6 * i;
-            const double *a = sm + (isy ? 2 * nx : d * nx);
-            double nv, na, nj, ns, nc;
-            time_b(cc, T1, T2, T3, T4, nv, na, nj, ns, nc);
-            if (i < P - 1) gt += ns * T3 * a[6 * i + 3] + nc * T4 * a[6 * i + 4] + nv * (a[6 * i + 5] + a[6 * i + 6]) + na * T1 * a[6 * i + 7] + nj * T2 * a[6 * i + 8];
-            else gt += nv * a[6 * P - 3] + na * T1 * a[6 * P - 2] + nj * T2 * a[6 * P - 1];
-        }
+        const double gt = gj * js + (double)gdt[isy ? TP_NMAX + i : i];
         if (isy) sy += gt; else sx += gt;
     }
     sx = warp_sum(sx); sy = warp_sum(sy);
-    for (int i = lane; i < N - 1; i += 32) { v.g[1 + 2 * i] = sm[6 * i + 5]; v.g[2 + 2 * i] = sm[6 * i + 5 + nx]; }
-    for (int i = lane; i < M - 1; i += 32) v.g[1 + 2 * (N - 1) + i] = sm[2 * nx + 6 * i + 5];
+    __syncwarp();
+    kp.mark(KP_FIN_PRE);
+    // waypoint gradients: one lane per waypoint (x and y of an xy waypoint share the table loads), a loop over the rows.  One code
+    // path for both kinds (a yaw lane reads its vector twice); twelve table rows in flight per step, the second six weighted zero
+    // past the end (branch-free, so that all loads are issued before the first use)
+    const double *WTn = E.wt + E.wway_off[N], *WTm = E.wt + E.wway_off[M];
+    for (int q = lane; q < (N - 1) + (M - 1); q += 32) {
+        const bool isy = q >= N - 1;
+        const int w = isy ? q - (N - 1) : q, sd = isy ? M - 1 : N - 1, nr = isy ? 6 * M : nx;
+        const double *t = (isy ? WTm : WTn) + w;
+        const double *ga = isy ? sm + 2 * nx : sm, *gb = isy ? ga : sm + nx;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
+        for (int r = 0; r < nr; r += 12) {
+            const bool h2 = r + 6 < nr;
+            const int r2 = h2 ? r + 6 : r;
+            const double hw = h2 ? 1.0 : 0.0;
+            const double w0 = __ldg(t + (size_t)r * sd), w1 = __ldg(t + (size_t)(r + 1) * sd), w2 = __ldg(t + (size_t)(r + 2) * sd);
+            const double w3 = __ldg(t + (size_t)(r + 3) * sd), w4 = __ldg(t + (size_t)(r + 4) * sd), w5 = __ldg(t + (size_t)(r + 5) * sd);
+            const double u0 = __ldg(t + (size_t)r2 * sd), u1 = __ldg(t + (size_t)(r2 + 1) * sd), u2 = __ldg(t + (size_t)(r2 + 2) * sd);
+            const double u3 = __ldg(t + (size_t)(r2 + 3) * sd), u4 = __ldg(t + (size_t)(r2 + 4) * sd), u5 = __ldg(t + (size_t)(r2 + 5) * sd);
+            a0 += w0 * ga[r]; b0 += w0 * gb[r]; a1 += w1 * ga[r + 1]; b1 += w1 * gb[r + 1]; a2 += w2 * ga[r + 2]; b2 += w2 * gb[r + 2];
+            a0 += w3 * ga[r + 3]; b0 += w3 * gb[r + 3]; a1 += w4 * ga[r + 4]; b1 += w4 * gb[r + 4]; a2 += w5 * ga[r + 5]; b2 += w5 * gb[r + 5];
+            const double v0 = u0 * hw, v1 = u1 * hw, v2 = u2 * hw, v3 = u3 * hw, v4 = u4 * hw, v5 = u5 * hw;
+            a0 += v0 * ga[r2]; b0 += v0 * gb[r2]; a1 += v1 * ga[r2 + 1]; b1 += v1 * gb[r2 + 1]; a2 += v2 * ga[r2 + 2]; b2 += v2 * gb[r2 + 2];
+            a0 += v3 * ga[r2 + 3]; b0 += v3 * gb[r2 + 3]; a1 += v4 * ga[r2 + 4]; b1 += v4 * gb[r2 + 4]; a2 += v5 * ga[r2 + 5]; b2 += v5 * gb[r2 + 5];
+        }
+        if (isy) v.g[1 + 2 * (N - 1) + w] = (a0 + a1) + a2;
+        else { v.g[1 + 2 * w] = (a0 + a1) + a2; v.g[2 + 2 * w] = (b0 + b1) + b2; }
+    }
+    kp.mark(KP_FIN_SWEEP);
     if (lane == 0) {
         const double tau = st->tau;
         v.g[0] = (p.rho_T * scale_fx + sx / (double)N + sy / (double)M) * dTdtau(tau);
@@ -882,14 +765,14 @@ __device__ int advance(const TpPool &E, const TpParams &p, const SlotView &v, in
 }
 
 template <class R>
-__global__ void __launch_bounds__(32 * TP_KA_WARPS) ka_kernel(const __grid_constant__ TpPool E, const __grid_constant__ TpParams p, int group)
+__global__ void __launch_bounds__(32 * TP_KA_WARPS, 4) ka_kernel(const __grid_constant__ TpPool E, const __grid_constant__ TpParams p, int group)
 {
     const int lane = threadIdx.x & 31, widx = blockIdx.x * TP_KA_WARPS + (threadIdx.x >> 5);
     if (widx >= E.n_active[group]) return;
-    extern __shared__ __align__(16) unsigned char ka_smem[];     // per warp: column buffer (ka_col_bytes) | factor ring
-    unsigned char *wbase = ka_smem + (size_t)(threadIdx.x >> 5) * (E.ka_col_bytes + 2 * TP_RING * TP_BLK * 8);
+    extern __shared__ __align__(16) unsigned char ka_smem[];     // per warp: ka_col_bytes
+    unsigned char *wbase = ka_smem + (size_t)(threadIdx.x >> 5) * E.ka_col_bytes;
     const int slot = E.active[(size_t)group * E.capacity + widx];
-    SlotView v = slot_view(E, slot, (double *)wbase, (double *)(wbase + E.ka_col_bytes));
+    SlotView v = slot_view(E, slot, (double *)wbase);
     TpState *st = v.st;
     const int ph = st->phase;
     if (ph == PH_DONE || ph == PH_FREE) return;
@@ -918,7 +801,6 @@ __global__ void __launch_bounds__(32 * TP_KA_WARPS) ka_kernel(const __grid_const
         return;
     }
     minco_forward<R>(E, v, lane, kp);
-    if (ph == PH_NEW && st->need_scale) { scaling_z(v, lane); kp.mark(KP_SCALEZ); }
     if (lane == 0) st->phase = next;
 }
 
