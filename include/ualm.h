@@ -180,6 +180,20 @@ int ualm_profile(ualm_ctx_t *ctx, int enable, long long *out16);
  * diverged solve) is not scanned: zeros and a sample count of -1. */
 int ualm_feasibility_batch(ualm_ctx_t *ctx, double dt, double *out10);
 
+/* Hand-over to the MPC for the solved batch of the selected lane, on the device:
+ *   (1) the mpc_controller/SE2Traj message PlanManager publishes (plan_manager.cpp:151-185, msg/SE2Traj.msg:1-9): pos_pts = the
+ *       start point of every xy piece and the end point, (N + 1) x {x, y} per problem, posT_pts = the N piece durations,
+ *       angle_pts (M + 1) / angleT_pts (M) likewise for yaw; problems packed back to back;
+ *   (2) the trajectory the MPC tracks: TrajAnalyzer::setTraj (traj_anal.hpp:125-181) re-solves MINCO over those points with the
+ *       message's init_v / init_a = {x, y, yaw} (NULL = zero, what the reference publishes) and zero tail derivatives, using
+ *       MinJerkOpt::generate (minco_traj.hpp:365-444): c_mpc_xy / c_mpc_yaw in the layout of ualm_solve_batch's c_xy / c_yaw,
+ *       bit-identical to that header compiled unmodified (tests/test_ref_pin.py + tests/test_gpu_mpc_export.py);
+ *   (3) dev4[4 * b + ..] = {max |planned - tracked| position (m), its time, max |planned - tracked| yaw (rad), its time}, sampled
+ *       every dt: the planned spline carries the boundary speed of plan_manager.cpp:93-94, the message does not.
+ * Any output pointer may be NULL.  Unsolved problems (ret_code UALM_ELIMIT) produce zeros. */
+int ualm_mpc_export_batch(ualm_ctx_t *ctx, double dt, const double *init_v, const double *init_a, double *pos_pts, double *posT_pts,
+                          double *angle_pts, double *angleT_pts, double *c_mpc_xy, double *c_mpc_yaw, double *dev4);
+
 /* UnevenMap construction on the GPU (UnevenMap::init preprocessing on the host, then constructMap + filter,
  * uneven_map.cpp:317-398, 5-43, one thread per (x, y, yaw) cell).  Same arguments and the same arithmetic as ualm_map_build
  * below (csrc/map_cell.h is compiled for both sides): the cells are bit-identical to the host builder's.  cells: host

@@ -205,6 +205,15 @@ public:
     }
     void waitBatch(int ticket, ualm_result_t *results, double *c_xy, double *c_yaw) { check(ualm_wait_batch(ctx_, ticket, results, c_xy, c_yaw), "ualm_wait_batch"); }
 
+    // What the MPC receives and tracks, for the batch solved last on the selected lane (ualm_mpc_export_batch): the SE2Traj message
+    // arrays of PlanManager (plan_manager.cpp:151-185), the MPC side's own MINCO over them (traj_anal.hpp:125-181) and the largest
+    // planned-vs-tracked deviation.  Any pointer may be null.
+    void exportToMpcBatch(double dt, double *pos_pts, double *posT_pts, double *angle_pts, double *angleT_pts, double *c_mpc_xy, double *c_mpc_yaw,
+                          double *dev4, const double *init_v = nullptr, const double *init_a = nullptr)
+    {
+        check(ualm_mpc_export_batch(ctx_, dt, init_v, init_a, pos_pts, posT_pts, angle_pts, angleT_pts, c_mpc_xy, c_mpc_yaw, dev4), "ualm_mpc_export_batch");
+    }
+
     ualm_ctx_t *handle() { return ctx_; }
 
 private:

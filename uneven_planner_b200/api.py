@@ -186,6 +186,21 @@ class BatchALMTrajOpt:
         _check(self.L.ualm_time_penalty_kernel(self.h, reps, C.byref(ms), C.byref(by)))
         return ms.value, by.value
 
+    def mpc_export(self, N, M, dt=0.01, init_v=None, init_a=None):
+        """SE2Traj message arrays, the MPC side's re-solved coefficients and the planned-vs-tracked deviation of the resident solved
+        batch (see ualm_mpc_export_batch).  N, M: the piece counts of the batch."""
+        N = np.asarray(N, dtype=np.int64); M = np.asarray(M, dtype=np.int64)
+        B, sN, sM = len(N), int(N.sum()), int(M.sum())
+        out = dict(pos_pts=np.zeros(2 * (sN + B)), posT_pts=np.zeros(sN), angle_pts=np.zeros(sM + B), angleT_pts=np.zeros(sM),
+                   c_mpc_xy=np.zeros(12 * sN), c_mpc_yaw=np.zeros(6 * sM), dev=np.zeros((B, 4)))
+        dp = C.POINTER(C.c_double)
+        P = lambda a: a.ctypes.data_as(dp)
+        iv = None if init_v is None else np.ascontiguousarray(init_v, dtype=np.float64)
+        ia = None if init_a is None else np.ascontiguousarray(init_a, dtype=np.float64)
+        _check(self.L.ualm_mpc_export_batch(self.h, float(dt), None if iv is None else P(iv), None if ia is None else P(ia), P(out["pos_pts"]), P(out["posT_pts"]),
+                                            P(out["angle_pts"]), P(out["angleT_pts"]), P(out["c_mpc_xy"]), P(out["c_mpc_yaw"]), P(out["dev"])))
+        return out
+
     def feasibility(self, dt=0.01):
         """Post-solve scan of the resident batch: array [B, 10] (see ualm_feasibility_batch)."""
         out = np.zeros((self.pb.B, 10))

@@ -948,6 +948,69 @@ extern "C" int ualm_feasibility_batch(ualm_ctx_t *c, double dt, double *out10)
 }
 
 // ---------------------------------------------------------------------------------------------
+// SE2Traj message + the MPC side's MINCO re-solve + planned-vs-tracked deviation for a solved batch (mpc_export_kernel)
+// ---------------------------------------------------------------------------------------------
+static int mpc_export_run(ualm_ctx *c, const BatchPtrs &bp, int B, const int32_t *N, const int32_t *M, double dt, const double *init_v, const double *init_a,
+                          double *pos_pts, double *posT_pts, double *angle_pts, double *angleT_pts, double *c_mpc_xy, double *c_mpc_yaw, double *dev4, cudaStream_t st)
+{
+    long long sN = 0, sM = 0;
+    for (int b = 0; b < B; b++) { sN += N[b]; sM += M[b]; }
+    struct Tmp { DevBuf<double> buf; ~Tmp() { buf.release(); } } t;
+    const size_t n_pp = 2 * (size_t)(sN + B), n_pt = (size_t)sN, n_ap = (size_t)(sM + B), n_at = (size_t)sM, n_cx = 12 * (size_t)sN, n_cy = 6 * (size_t)sM, n_dv = 4 * (size_t)B;
+    const size_t n_band = 13 * (6 * (size_t)sN + 6 * (size_t)sM);
+    CK(t.buf.ensure(n_pp + n_pt + n_ap + n_at + n_cx + n_cy + n_dv + n_band));
+    MpcOut o;
+    double *q = t.buf.p;
+    o.pos_pts = q; q += n_pp; o.posT_pts = q; q += n_pt; o.angle_pts = q; q += n_ap; o.angleT_pts = q; q += n_at;
+    o.c_mpc_xy = q; q += n_cx; o.c_mpc_yaw = q; q += n_cy; o.dev = q; q += n_dv; o.band = q;
+    for (int k = 0; k < 3; k++) { o.init_v[k] = init_v ? init_v[k] : 0.0; o.init_a[k] = init_a ? init_a[k] : 0.0; }
+    mpc_export_kernel<<<(B + UALM_WPB - 1) / UALM_WPB, UALM_THREADS * UALM_WPB, 0, st>>>(bp, dt, o);
+    CK(cudaGetLastError());
+    struct { double *h; const double *d; size_t n; } cp[7] = {{pos_pts, o.pos_pts, n_pp}, {posT_pts, o.posT_pts, n_pt}, {angle_pts, o.angle_pts, n_ap},
+        {angleT_pts, o.angleT_pts, n_at}, {c_mpc_xy, o.c_mpc_xy, n_cx}, {c_mpc_yaw, o.c_mpc_yaw, n_cy}, {dev4, o.dev, n_dv}};
+    for (auto &e : cp) if (e.h && e.n) CK(cudaMemcpyAsync(e.h, e.d, sizeof(double) * e.n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return UALM_OK;
+}
+
+extern "C" int ualm_mpc_export_batch(ualm_ctx_t *c, double dt, const double *init_v, const double *init_a, double *pos_pts, double *posT_pts, double *angle_pts,
+                                     double *angleT_pts, double *c_mpc_xy, double *c_mpc_yaw, double *dev4)
+{
+    if (!c || !(dt > 0.0)) return fail(UALM_EINVAL, "null ctx or dt <= 0");
+    if (c->tp) {
+        const ualm_result_t *d_res; const double *d_cxy, *d_cyaw;
+        int B = 0; const int32_t *N = nullptr, *M = nullptr;
+        if (ualm_tp::tp_lane_outputs(c->tp, c->cur, &d_res, &d_cxy, &d_cyaw, &B, &N, &M) != UALM_OK)
+            return fail(UALM_ESTATE, "ualm_mpc_export_batch needs a solved, collected batch (ualm_sync / ualm_download first)");
+        CK(cudaSetDevice(c->device));
+        if (B == 0) return UALM_OK;
+        struct Tmp { DevBuf<ProbDesc> desc; DevBuf<double> pt; ~Tmp() { desc.release(); pt.release(); } } t;
+        std::vector<ProbDesc> desc(B);
+        long long ocx = 0, ocy = 0;
+        for (int b = 0; b < B; b++) {
+            memset(&desc[b], 0, sizeof(ProbDesc));
+            desc[b].N = N[b]; desc[b].M = M[b]; desc[b].off_cxy = ocx; desc[b].off_cyaw = ocy;
+            desc[b].S = (N[b] > UALM_NMAX || M[b] > UALM_MMAX) ? 0 : 1;
+            ocx += 12LL * N[b]; ocy += 6LL * M[b];
+        }
+        CK(t.desc.ensure(B)); CK(t.pt.ensure(2 * (size_t)B));
+        CK(cudaMemcpy(t.desc.p, desc.data(), sizeof(ProbDesc) * B, cudaMemcpyHostToDevice));
+        piece_T_from_results<<<(B + 127) / 128, 128>>>(d_res, B, t.pt.p);
+        BatchPtrs bp;
+        memset(&bp, 0, sizeof(bp));
+        bp.B = B; bp.desc = t.desc.p; bp.c_xy = const_cast<double *>(d_cxy); bp.c_yaw = const_cast<double *>(d_cyaw); bp.piece_T = t.pt.p;
+        return mpc_export_run(c, bp, B, N, M, dt, init_v, init_a, pos_pts, posT_pts, angle_pts, angleT_pts, c_mpc_xy, c_mpc_yaw, dev4, 0);
+    }
+    Lane *l = c->b;
+    if (!l->have_batch || !l->solved) return fail(UALM_ESTATE, "ualm_mpc_export_batch needs a solved resident batch");
+    CK(cudaSetDevice(c->device));
+    if (l->B == 0) return UALM_OK;
+    std::vector<int32_t> N(l->B), M(l->B);
+    for (int b = 0; b < l->B; b++) { N[b] = l->desc[b].N; M[b] = l->desc[b].M; }
+    return mpc_export_run(c, batch_ptrs(c), l->B, N.data(), M.data(), dt, init_v, init_a, pos_pts, posT_pts, angle_pts, angleT_pts, c_mpc_xy, c_mpc_yaw, dev4, l->stream);
+}
+
+// ---------------------------------------------------------------------------------------------
 // UnevenMap construction on the device.  HBM-bound gather: one thread per cell, yaw fastest so that the 64
 // threads of a CTA share (x, y) and read the same few cloud bins through L1.
 // ---------------------------------------------------------------------------------------------

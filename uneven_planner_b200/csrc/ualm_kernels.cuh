@@ -2362,6 +2362,155 @@ __global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) feasibility_kernel(co
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// the hand-over to the MPC, for the whole batch on the device.
+//   (1) the SE2Traj message PlanManager publishes (plan_manager.cpp:151-185, msg/SE2Traj.msg:1-9): start point of every piece
+//       (Piece::getValue(0), se2traj.hpp:106-118), the end point (PolyTrajectory::getValue(total), :363-368) and the piece durations;
+//   (2) the trajectory the MPC then tracks: TrajAnalyzer::setTraj (traj_anal.hpp:125-181) feeds those points, the message's (zero)
+//       boundary velocity / acceleration and zero tail derivatives to its own MinJerkOpt::generate (minco_traj.hpp:365-444 -- the same
+//       banded LU without pivoting as the back-end's, banded_system.hpp:66-118, restated here operation for operation);
+//   (3) how far (2) is from the planned spline (the back-end plans with a boundary speed of init_sig_vel, plan_manager.cpp:93-94,
+//       which the message does not carry): the largest position / yaw deviation over t = 0, dt, 2dt, .. and where it occurs.
+// One warp per problem: lane 0 solves the xy system (one factorization, two right-hand sides), lane 1 the yaw system, every lane
+// takes a slice of the samples of (3).  band: scratch, 13 * (6N + 6M) doubles per problem at 13 * (off_cxy / 2 + off_cyaw).
+// dev[4 * problem + ..] = {max |p_plan - p_mpc|, its time, max |yaw_plan - yaw_mpc|, its time}
+// ---------------------------------------------------------------------------------------------
+struct BandView {      // BandedSystem storage (banded_system.hpp:25-64): entry (i, j) at [(i - j + 6) * n + j]
+    R *d; int n;
+    __device__ __forceinline__ R &operator()(int i, int j) const { return d[(size_t)(i - j + 6) * n + j]; }
+};
+// MinJerkOpt::generate for Dim right-hand sides sharing one matrix (minco_traj.hpp:365-444 == se2traj.hpp:595-680); c: 6P x Dim
+// column-major (column stride 6P); point i of column d at pts[i * pst + d * cst]; all pieces last T
+__device__ void mpc_minco_serial(BandView A, int P, int Dim, R T, const R *pts, int pst, int cst, const R *v0, const R *a0, R *c)
+{
+    const int n = 6 * P;
+    for (int q = 0; q < 13 * n; q++) A.d[q] = 0.0;
+    for (int q = 0; q < n * Dim; q++) c[q] = 0.0;
+    const R T1 = T, T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2, T5 = T4 * T1;
+    A(0, 0) = 1.0; A(1, 1) = 1.0; A(2, 2) = 2.0;
+    for (int d = 0; d < Dim; d++) { c[0 + d * n] = pts[d * cst]; c[1 + d * n] = v0[d]; c[2 + d * n] = a0[d]; }
+    for (int i = 0; i < P - 1; i++) {
+        const int r = 6 * i;
+        A(r + 3, r + 3) = 6.0; A(r + 3, r + 4) = 24.0 * T1; A(r + 3, r + 5) = 60.0 * T2; A(r + 3, r + 9) = -6.0;
+        A(r + 4, r + 4) = 24.0; A(r + 4, r + 5) = 120.0 * T1; A(r + 4, r + 10) = -24.0;
+        A(r + 5, r) = 1.0; A(r + 5, r + 1) = T1; A(r + 5, r + 2) = T2; A(r + 5, r + 3) = T3; A(r + 5, r + 4) = T4; A(r + 5, r + 5) = T5;
+        A(r + 6, r) = 1.0; A(r + 6, r + 1) = T1; A(r + 6, r + 2) = T2; A(r + 6, r + 3) = T3; A(r + 6, r + 4) = T4; A(r + 6, r + 5) = T5;
+        A(r + 6, r + 6) = -1.0;
+        A(r + 7, r + 1) = 1.0; A(r + 7, r + 2) = 2.0 * T1; A(r + 7, r + 3) = 3.0 * T2; A(r + 7, r + 4) = 4.0 * T3; A(r + 7, r + 5) = 5.0 * T4;
+        A(r + 7, r + 7) = -1.0;
+        A(r + 8, r + 2) = 2.0; A(r + 8, r + 3) = 6.0 * T1; A(r + 8, r + 4) = 12.0 * T2; A(r + 8, r + 5) = 20.0 * T3; A(r + 8, r + 8) = -2.0;
+        for (int d = 0; d < Dim; d++) c[r + 5 + d * n] = pts[(i + 1) * pst + d * cst];
+    }
+    A(n - 3, n - 6) = 1.0; A(n - 3, n - 5) = T1; A(n - 3, n - 4) = T2; A(n - 3, n - 3) = T3; A(n - 3, n - 2) = T4; A(n - 3, n - 1) = T5;
+    A(n - 2, n - 5) = 1.0; A(n - 2, n - 4) = 2.0 * T1; A(n - 2, n - 3) = 3.0 * T2; A(n - 2, n - 2) = 4.0 * T3; A(n - 2, n - 1) = 5.0 * T4;
+    A(n - 1, n - 4) = 2.0; A(n - 1, n - 3) = 6.0 * T1; A(n - 1, n - 2) = 12.0 * T2; A(n - 1, n - 1) = 20.0 * T3;
+    for (int d = 0; d < Dim; d++) c[n - 3 + d * n] = pts[P * pst + d * cst];   // tail velocity / acceleration stay zero (traj_anal.hpp:162-163)
+    // factorizeLU (banded_system.hpp:66-91): no pivoting, exact-zero multipliers skipped
+    for (int k = 0; k <= n - 2; k++) {
+        const int iM = min(k + 6, n - 1), jM = min(k + 6, n - 1);
+        R cVl = A(k, k);
+        for (int i = k + 1; i <= iM; i++) if (A(i, k) != 0.0) A(i, k) /= cVl;
+        for (int j = k + 1; j <= jM; j++) {
+            cVl = A(k, j);
+            if (cVl != 0.0)
+                for (int i = k + 1; i <= iM; i++) if (A(i, k) != 0.0) A(i, j) -= A(i, k) * cVl;
+        }
+    }
+    // solve (banded_system.hpp:96-118)
+    for (int j = 0; j <= n - 1; j++) {
+        const int iM = min(j + 6, n - 1);
+        for (int i = j + 1; i <= iM; i++)
+            if (A(i, j) != 0.0) for (int d = 0; d < Dim; d++) c[i + d * n] -= A(i, j) * c[j + d * n];
+    }
+    for (int j = n - 1; j >= 0; j--) {
+        for (int d = 0; d < Dim; d++) c[j + d * n] /= A(j, j);
+        const int iM = max(0, j - 6);
+        for (int i = iM; i <= j - 1; i++)
+            if (A(i, j) != 0.0) for (int d = 0; d < Dim; d++) c[i + d * n] -= A(i, j) * c[j + d * n];
+    }
+}
+struct MpcOut { R *pos_pts, *posT_pts, *angle_pts, *angleT_pts, *c_mpc_xy, *c_mpc_yaw, *dev, *band; R init_v[3], init_a[3]; };
+__global__ void __launch_bounds__(UALM_THREADS * UALM_WPB) mpc_export_kernel(const __grid_constant__ BatchPtrs bp, R dt, const __grid_constant__ MpcOut o)
+{
+    const int lane = threadIdx.x & 31, prob = blockIdx.x * UALM_WPB + (threadIdx.x >> 5);
+    if (prob >= bp.B) return;
+    const ProbDesc *pd = bp.desc + prob;
+    const int N = pd->N, M = pd->M, nx = 6 * N;
+    const long long sN = pd->off_cxy / 12, sM = pd->off_cyaw / 6;         // pieces of the problems before this one
+    R *pp = o.pos_pts + 2 * (sN + prob), *pt = o.posT_pts + sN, *ap = o.angle_pts + (sM + prob), *at = o.angleT_pts + sM;
+    R *mxy = o.c_mpc_xy + pd->off_cxy, *myaw = o.c_mpc_yaw + pd->off_cyaw;
+    R *dv = o.dev + 4 * (size_t)prob;
+    if (pd->S == 0) {            // over the compiled limits: not solved
+        for (int q = lane; q < 2 * (N + 1); q += 32) pp[q] = 0.0;
+        for (int q = lane; q < N; q += 32) pt[q] = 0.0;
+        for (int q = lane; q <= M; q += 32) ap[q] = 0.0;
+        for (int q = lane; q < M; q += 32) at[q] = 0.0;
+        for (int q = lane; q < 12 * N; q += 32) mxy[q] = 0.0;
+        for (int q = lane; q < 6 * M; q += 32) myaw[q] = 0.0;
+        if (lane < 4) dv[lane] = 0.0;
+        return;
+    }
+    const R *cxy = bp.c_xy + pd->off_cxy, *cyaw = bp.c_yaw + pd->off_cyaw;
+    const R Tx = bp.piece_T[2 * prob], Ty = bp.piece_T[2 * prob + 1];
+    R tot_xy = 0.0, tot_yaw = 0.0;
+    for (int i = 0; i < N; i++) tot_xy += Tx;
+    for (int i = 0; i < M; i++) tot_yaw += Ty;
+    // (1) the message: piece start points are the constant coefficients (getValue(0) only adds exact zeros to them); the end point is
+    // PolyTrajectory::getValue at the summed duration
+    for (int i = lane; i < N; i += 32) { pp[2 * i] = cxy[6 * i]; pp[2 * i + 1] = cxy[nx + 6 * i]; pt[i] = Tx; }
+    for (int i = lane; i < M; i += 32) { ap[i] = cyaw[6 * i]; at[i] = Ty; }
+    if (lane == 0) {
+        R t = tot_xy, d1, d2;
+        const int ip = locate_piece(N, Tx, t);
+        piece_eval(cxy + 6 * ip, t, pp[2 * N], d1, d2);
+        piece_eval(cxy + nx + 6 * ip, t, pp[2 * N + 1], d1, d2);
+        t = tot_yaw;
+        const int iy = locate_piece(M, Ty, t);
+        piece_eval(cyaw + 6 * iy, t, ap[M], d1, d2);
+    }
+    __syncwarp();
+    // (2) the MPC's own MINCO over the message
+    R *band = o.band + 13 * (pd->off_cxy / 2 + pd->off_cyaw);
+    if (lane == 0) mpc_minco_serial(BandView{band, nx}, N, 2, Tx, pp, 2, 1, o.init_v, o.init_a, mxy);
+    if (lane == 1) mpc_minco_serial(BandView{band + 13 * nx, 6 * M}, M, 1, Ty, ap, 1, 0, o.init_v + 2, o.init_a + 2, myaw);
+    __syncwarp();
+    // (3) planned against tracked, over the shorter of the two durations like every scan of the reference (se2traj.hpp:415-418)
+    const R total = tot_xy < tot_yaw ? tot_xy : tot_yaw;
+    if (!(total / dt < 4.0e6)) {
+        if (lane == 0) { dv[0] = -1.0; dv[1] = 0.0; dv[2] = -1.0; dv[3] = 0.0; }
+        return;
+    }
+    R bp_ = 0.0, bpt = 0.0, by_ = 0.0, byt = 0.0;
+    R tbase = 0.0;
+    while (true) {
+        R tm = 0.0, tt = tbase;
+        for (int i = 0; i < 32; i++) { if (i == lane) tm = tt; tt = tt + dt; }
+        const bool valid = tm < total;
+        if (valid) {
+            R tl = tm, d1, d2, px, py, qx, qy, ya, yb;
+            const int ip = locate_piece(N, Tx, tl);
+            piece_eval(cxy + 6 * ip, tl, px, d1, d2); piece_eval(cxy + nx + 6 * ip, tl, py, d1, d2);
+            piece_eval(mxy + 6 * ip, tl, qx, d1, d2); piece_eval(mxy + nx + 6 * ip, tl, qy, d1, d2);
+            R ty = tm;
+            const int iy = locate_piece(M, Ty, ty);
+            piece_eval(cyaw + 6 * iy, ty, ya, d1, d2); piece_eval(myaw + 6 * iy, ty, yb, d1, d2);
+            const R ep = sqrt((px - qx) * (px - qx) + (py - qy) * (py - qy)), ey = fabs(ya - yb);
+            if (bp_ < ep) { bp_ = ep; bpt = tm; }
+            if (by_ < ey) { by_ = ey; byt = tm; }
+        }
+        if (__popc(__ballot_sync(0xffffffffu, valid)) < 32) break;
+        tbase = tt;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {      // largest value, earliest time among equals
+        const R op = __shfl_xor_sync(0xffffffffu, bp_, off), opt = __shfl_xor_sync(0xffffffffu, bpt, off);
+        const R oy = __shfl_xor_sync(0xffffffffu, by_, off), oyt = __shfl_xor_sync(0xffffffffu, byt, off);
+        if (bp_ < op || (bp_ == op && opt < bpt)) { bp_ = op; bpt = opt; }
+        if (by_ < oy || (by_ == oy && oyt < byt)) { by_ = oy; byt = oyt; }
+    }
+    if (lane == 0) { dv[0] = bp_; dv[1] = bpt; dv[2] = by_; dv[3] = byt; }
+}
+
 // fixed-stride result records for the multi-GPU all-gather
 __global__ void pack_records_kernel(BatchPtrs bp, int B, R *rec, int stride)
 {
