@@ -81,6 +81,13 @@ def get_map(name):
     return maps.synthetic_terrain("bumps", seed=0), "synthetic-bumps (maps_built/%s.umap missing)" % name
 
 
+def make_problems(args, m, total, gen):
+    from uneven_planner_b200 import problems
+    if getattr(args, "front_end", "dubins") == "astar":
+        return problems.generate_astar(m, total, seed=args.seed, **gen)
+    return problems.generate(m, total, seed=args.seed, **gen)
+
+
 def workload(args, world):
     """(terrain, params, generator kwargs, per-GPU batch, total batch, scaling, description) of the selected BASELINE config"""
     from uneven_planner_b200 import configs
@@ -230,7 +237,7 @@ def run_reference(args):
     terrain, params, gen, total, scaling, desc = workload(args, world)
     m, mname = get_map(terrain)
     threads, core_info = usable_cores()
-    pb_all = problems.generate(m, total, seed=args.seed, **gen)
+    pb_all = make_problems(args, m, total, gen)
     sample = total if args.ref_sample <= 0 else min(args.ref_sample, total)
     pb = pb_all if sample == total else pb_all.select(np.arange(sample))
     for _ in range(min(args.warmup, 1)):
@@ -246,7 +253,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": desc.replace(terrain + " UnevenMap", mname + " UnevenMap"), "global_batch": total, "batch_per_step": sample,
+            "config": {"workload": desc.replace(terrain + " UnevenMap", mname + " UnevenMap") + ("" if args.front_end == "dubins" else "; initial paths from KinoAstar"), "global_batch": total, "batch_per_step": sample,
                        "same_config": sample == total,
                        "note": ("the whole batch per step" if sample == total else "a bounded sample of the batch per step: throughput is per trajectory, so the ratio stands") +
                                ", all usable host threads; inputs generated by libualm's HOST tools (Dubins + PlanManager resampler, no GPU code), the solve is oracle/liboracle.so"},
@@ -267,6 +274,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override: problems per GPU per step (weak configs) / in total (config 3)")
     ap.add_argument("--map", default="", help="override the config's terrain")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--front-end", default="dubins", choices=["dubins", "astar"], dest="front_end",
+                    help="initial paths of the synthetic problems: one Dubins curve per pair (default, the workload every committed number uses) or the reference's own "
+                         "front-end, KinoAstar::plan restated in libualm (ualm_front_end_batch)")
     ap.add_argument("--depth", type=int, default=0, help="batches in flight (lanes); 0 = 3 for the parity path, 8 for the throughput path; 1 = every step waits for its slowest trajectory")
     ap.add_argument("--precision", type=int, default=64, choices=[64, 65, 32], help="path of the HEADLINE numbers: 64 = parity path (default), 65 / 32 = throughput path")
     ap.add_argument("--no-fast", action="store_true", help="skip the separately labelled throughput-path measurement")
@@ -294,7 +304,7 @@ def main():
     terrain, params, gen, Btot, scaling, desc = workload(args, world)
     m, mname = get_map(terrain)
     K = params.int_K
-    pb_all = problems.generate(m, Btot, seed=args.seed, **gen)          # identical on every rank (counter-based RNG)
+    pb_all = make_problems(args, m, Btot, gen)          # identical on every rank (counter-based RNG)
     shards = D.shard_indices(pb_all.nsamples(K), world)
     pb = pb_all.select(shards[rank])
     stride = D.record_stride(pb_all.N.max(), pb_all.M.max())
@@ -536,7 +546,7 @@ def main():
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
                 "dtype": "f64" if head_prec != 32 else "f32 penalty samples / f64 solver state",
                 "data": "synthetic",
-                "config": {"workload": desc.replace(terrain + " UnevenMap", mname + " UnevenMap"), "precision": head_prec,
+                "config": {"workload": desc.replace(terrain + " UnevenMap", mname + " UnevenMap") + ("" if args.front_end == "dubins" else "; initial paths from KinoAstar"), "precision": head_prec,
                            "global_batch": Btot, "parallelism": "dp%d (independent shards, final NCCL all-gather of result records)" % world,
                            "converged_per_step": conv_total, "solved_per_step": Btot, "batches_in_flight": depth,
                            "pipelining": "steps are launched on %d lanes round robin; a lane is re-used only after its previous step is complete; all %d steps "

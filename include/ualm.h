@@ -231,6 +231,46 @@ int ualm_resample_path(const double *path_xyyaw, int npts, double piece_len, dou
                        double *inner_xy, int max_inner_xy, double *inner_yaw, int max_inner_yaw, int32_t *N,
                        int32_t *M, double *total_time);
 
+/* ---- front-end: KinoAstar ---- */
+/* kino_astar/* parameters (front_end/src/kino_astar.cpp:7-20) */
+typedef struct {
+    double yaw_resolution, lambda_heu, weight_r2, weight_so2, weight_v_change, weight_delta_change, weight_sigma;
+    double time_interval, collision_interval, oneshot_range, wheel_base, max_steer, max_vel;
+} ualm_astar_params_t;
+/* plan_manager/params/run_*.yaml:16-30 (the same values in every terrain file) */
+void ualm_astar_default_params(ualm_astar_params_t *p);
+/* what KinoAstar reads of UnevenMap (isOccupancy, isOccupancyXY, isInMap, getTerrainSig; uneven_map.h:389-500): the cell grid
+ * ([X][Y][Yaw][4] = z, sigma, zb.x, zb.y; float as ualm_set_map takes it, or double as ualm_set_map_f64 does -- one of the two) and
+ * the occupancy grids of ualm_map_occupancy (occ3: [X][Y][Yaw], occ2: [X][Y]) */
+typedef struct {
+    const ualm_map_geom_t *geom;
+    const float *cells;
+    const double *cells64;
+    const uint8_t *occ3, *occ2;
+} ualm_astar_map_t;
+/* plan_manager/* parameters of the resampler (plan_manager.cpp:24-30; run_hill.yaml:57-62) */
+typedef struct { double piece_len, yaw_piece_times, mean_vel, init_time_times, init_sig_vel; } ualm_resample_params_t;
+
+/* KinoAstar::plan(start_state, end_state) (front_end/src/kino_astar.cpp:67-236): hybrid A* over (x, y, yaw) with 3 x 5 motion
+ * primitives and a Dubins one-shot near the goal.  Writes the (x, y, yaw) polyline start .. goal and returns its number of points;
+ * 0 = no path (start or goal occupied, open set exhausted, node pool exhausted), like the reference's empty vector.
+ * n_expanded (optional): nodes closed.  The Dubins curve is OMPL's in the reference (absent here): csrc/dubins.h restates it. */
+int ualm_kino_astar_plan(const ualm_astar_map_t *map, const ualm_astar_params_t *p, const double start[3], const double goal[3],
+                         double *path_xyyaw, int max_pts, int *n_expanded);
+
+/* The one-shot curve of KinoAstar::asignShotTraj alone (kino_astar.h:246-258, without its occupancy test): the shortest Dubins curve of
+ * turning radius `radius` sampled every `interval` metres from its start; *length (optional) receives its length. */
+int ualm_dubins_shot(const double start[3], const double goal[3], double radius, double interval, double *path_xyyaw, int max_pts, double *length);
+
+/* The reference's whole front half for B (start, goal) pairs, one search per host thread (nthreads <= 0: all cores):
+ * KinoAstar::plan -> PlanManager's resampler (ualm_resample_path).  Outputs are the ragged arrays ualm_solve_batch /
+ * ualm_submit_batch take, packed back to back for the problems that have a path and fit the optimizer's limits; packed[b] = index of
+ * pair b in them or -1; n_expanded[b] (optional) = nodes closed.  Returns the number of packed problems (or a negative error;
+ * UALM_ELIMIT when cap_xy / cap_yaw doubles are not enough). */
+int ualm_front_end_batch(const ualm_astar_map_t *map, const ualm_astar_params_t *ap, const ualm_resample_params_t *rp, int B,
+                         const double *starts, const double *goals, int nthreads, int32_t *N, int32_t *M, double *bnd, double *total_time,
+                         double *inner_xy, long long cap_xy, double *inner_yaw, long long cap_yaw, int32_t *packed, int32_t *n_expanded);
+
 #ifdef __cplusplus
 }
 #endif

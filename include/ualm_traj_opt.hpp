@@ -214,6 +214,26 @@ public:
         check(ualm_mpc_export_batch(ctx_, dt, init_v, init_a, pos_pts, posT_pts, angle_pts, angleT_pts, c_mpc_xy, c_mpc_yaw, dev4), "ualm_mpc_export_batch");
     }
 
+    // The reference's whole chain for B (start, goal) pairs: KinoAstar::plan + PlanManager's resampler on host threads
+    // (ualm_front_end_batch), then the batched optimizer.  packed[b] = index of pair b in the outputs or -1 (no path / over the
+    // optimizer's limits); results / c_xy / c_yaw hold the packed problems back to back like optimizeBatch.  Returns their number.
+    int planAndOptimizeBatch(const ualm_astar_map_t &map, const ualm_astar_params_t &ap, const ualm_resample_params_t &rp, int B, const double *starts,
+                             const double *goals, std::vector<int32_t> &packed, std::vector<int32_t> &N, std::vector<int32_t> &M, std::vector<ualm_result_t> &results,
+                             std::vector<double> &c_xy, std::vector<double> &c_yaw, int nthreads = 0)
+    {
+        packed.assign(B, -1); N.assign(B, 0); M.assign(B, 0);
+        std::vector<double> bnd(18 * (size_t)B), T(B), ixy(2 * 63 * (size_t)B + 2), iyaw(127 * (size_t)B + 1);
+        const int k = ualm_front_end_batch(&map, &ap, &rp, B, starts, goals, nthreads, N.data(), M.data(), bnd.data(), T.data(), ixy.data(), (long long)ixy.size(),
+                                           iyaw.data(), (long long)iyaw.size(), packed.data(), nullptr);
+        if (k < 0) throw std::runtime_error("ualm_front_end_batch failed");
+        N.resize(k); M.resize(k);
+        size_t ncx = 0, ncy = 0;
+        for (int i = 0; i < k; i++) { ncx += 12 * (size_t)N[i]; ncy += 6 * (size_t)M[i]; }
+        results.assign(k, ualm_result_t{}); c_xy.assign(ncx, 0.0); c_yaw.assign(ncy, 0.0);
+        if (k > 0) optimizeBatch(k, N.data(), M.data(), bnd.data(), T.data(), ixy.data(), iyaw.data(), results.data(), c_xy.data(), c_yaw.data());
+        return k;
+    }
+
     ualm_ctx_t *handle() { return ctx_; }
 
 private:

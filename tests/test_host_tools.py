@@ -179,3 +179,64 @@ def test_snapshot_to_the_gpu_box_includes_every_map():
     if os.path.exists(p):
         lines = [l.strip() for l in open(p) if l.strip() and not l.startswith("#")]
         assert not [l for l in lines if "maps_built" in l or "umap" in l or "libualm" in l or "_ref" in l], lines
+
+
+def test_dubins_curves_reach_the_goal_with_every_word(built):
+    """csrc/dubins.h through ualm_kino_astar_plan's one-shot is exercised by the A* pins; here the curve family itself: whatever word
+    wins, walking it ends at the goal pose, it is at least as long as the straight line, and all six words occur"""
+    import ctypes as C
+    from uneven_planner_b200 import _lib, problems
+    rng = np.random.default_rng(5)
+    radius = 0.26 / np.tan(0.5)
+    turns = set()
+    for _ in range(300):
+        s = np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(-np.pi, np.pi)])
+        e = np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(-np.pi, np.pi)])
+        p = problems.dubins(s, e, radius=radius, ds=0.01)
+        seg = np.hypot(np.diff(p[:, 0]), np.diff(p[:, 1])).sum()
+        assert seg >= np.hypot(*(e[:2] - s[:2])) - 1e-9
+        assert np.hypot(*(p[-1, :2] - e[:2])) < 1e-9 and abs(np.angle(np.exp(1j * (p[-1, 2] - e[2])))) < 1e-6
+        assert np.hypot(*(p[-2, :2] - e[:2])) <= 0.01 + 1e-9          # the sampled curve itself arrives there, not only the appended goal
+        dyaw = np.diff(np.unwrap(p[:-1, 2]))
+        sign = np.sign(np.round(dyaw, 9))
+        runs = [int(v) for k, v in enumerate(sign) if v != 0 and (k == 0 or sign[k - 1] != v)]
+        turns.add(tuple(runs[:3]))
+        # the front-end's own curve (csrc/dubins.h, the restatement of OMPL's DubinsStateSpace) describes the same shortest curve
+        buf = np.zeros((4096, 3)); ln = C.c_double()
+        dp = C.POINTER(C.c_double)
+        n = _lib.lib().ualm_dubins_shot(s.ctypes.data_as(dp), e.ctypes.data_as(dp), radius, 0.01, buf.ctypes.data_as(dp), 4096, C.byref(ln))
+        assert n >= 1 and abs(ln.value - (len(p) - 2) * 0.01) <= 0.01 + 1e-9 and np.allclose(buf[0], [s[0], s[1], np.angle(np.exp(1j * s[2]))], atol=1e-12)
+        m_ = min(n, len(p) - 1)
+        assert np.abs(buf[:m_, :2] - p[:m_, :2]).max() < 1e-8
+    assert {(1,), (-1,), (1, -1), (-1, 1)} <= turns or len(turns) >= 4
+
+
+def test_front_end_batch_equals_the_sequential_front_end(built, bumps_map):
+    """ualm_front_end_batch = KinoAstar::plan + PlanManager's resampler per pair, whatever the number of host threads; pairs without a
+    path are left out and reported"""
+    from uneven_planner_b200 import front_end, problems
+    view = front_end.MapView(bumps_map, 0.8, 0.003)
+    rng = np.random.default_rng(2)
+    B = 24
+    starts = np.column_stack([rng.uniform(-4.3, 4.3, B), rng.uniform(-4.3, 4.3, B), rng.uniform(-np.pi, np.pi, B)])
+    goals = np.column_stack([rng.uniform(-4.3, 4.3, B), rng.uniform(-4.3, 4.3, B), rng.uniform(-np.pi, np.pi, B)])
+    ox, oy = np.argwhere(view.occ2)[7]
+    g = bumps_map.geom
+    goals[5, :2] = [g.origin[0] + (ox + 0.5) * g.xy_resolution, g.origin[1] + (oy + 0.5) * g.xy_resolution]      # goal inside an obstacle
+    pb1, packed1, nexp1 = front_end.plan_batch(view, starts, goals, nthreads=1)
+    pb4, packed4, nexp4 = front_end.plan_batch(view, starts, goals, nthreads=4)
+    assert np.array_equal(packed1, packed4) and np.array_equal(nexp1, nexp4)
+    for a, b in zip((pb1.N, pb1.M, pb1.bnd, pb1.total_time, pb1.inner_xy, pb1.inner_yaw), (pb4.N, pb4.M, pb4.bnd, pb4.total_time, pb4.inner_xy, pb4.inner_yaw)):
+        assert np.array_equal(a, b)
+    assert packed1[5] == -1 and (packed1 >= 0).sum() == pb1.B >= B // 2
+    oxy, oyaw, _, _ = pb1.offsets()
+    for b in range(B):
+        path, nexp = front_end.plan(view, starts[b], goals[b])
+        assert nexp == nexp1[b]
+        k = packed1[b]
+        if k < 0:
+            assert len(path) < 2 or problems.resample(path)[0] > 64 or problems.resample(path)[1] > 128
+            continue
+        N, M, bnd, T, ixy, iyaw = problems.resample(path)
+        assert (N, M, T) == (pb1.N[k], pb1.M[k], pb1.total_time[k]) and np.array_equal(bnd, pb1.bnd[k])
+        assert np.array_equal(ixy, pb1.inner_xy[oxy[k]:oxy[k + 1]]) and np.array_equal(iyaw, pb1.inner_yaw[oyaw[k]:oyaw[k + 1]])

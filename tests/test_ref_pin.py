@@ -433,3 +433,83 @@ def test_reference_constructMap_matches_host_builder(built):
     # the empty-footprint branch (uneven_map.cpp:379-386) is exercised: cells over the hole keep the default normal and sigma
     flat = (ref[..., 1] == 0.0) & (ref[..., 2] == 0.0) & (ref[..., 3] == 0.0)
     assert flat.any() and not flat.all()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# KinoAstar::plan (front_end/src/kino_astar.cpp:67-236) compiled UNMODIFIED against the shim (oracle/_ref/librefkino.so,
+# oracle/ref_kino_driver.cpp) versus the product's restatement (uneven_planner_b200/csrc/kino_astar.cpp).  OMPL is absent: both sides get
+# their Dubins curves from csrc/dubins.h (through oracle/shim/ompl on the reference side), so the pin covers the search itself -- motion
+# primitives, NaN states of the v = 0 primitives, costs incl. getTerrainSig, collision checks, the in-place update of OPEN nodes without
+# re-sorting, the one-shot trigger and the path assembly -- and the UnevenMap helpers it calls, not OMPL's arithmetic.
+# ---------------------------------------------------------------------------------------------------------------------------------
+REFKINO = os.path.join(ROOT, "oracle", "_ref", "librefkino.so")
+
+
+@pytest.fixture(scope="module")
+def refkino(ref):
+    if not os.path.exists(REFKINO):
+        pytest.skip("oracle/_ref/librefkino.so not built")
+    L = C.CDLL(REFKINO)
+    u8 = C.POINTER(C.c_uint8)
+    L.ref_kino_plan.argtypes = [dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp, dp, dp, C.c_int, u8, u8]
+    return L
+
+
+def _ref_plan(refkino, m, cells64, min_cnormal, max_rho, ap, s, e):
+    from uneven_planner_b200 import _lib
+    g = m.geom
+    X, Y, W = m.shape
+    kp = np.array([getattr(ap, n) for n, _ in _lib.AstarParams._fields_])
+    out = np.zeros((1 << 15, 3)); o3 = np.zeros((X, Y, W), np.uint8); o2 = np.zeros((X, Y), np.uint8)
+    u8 = C.POINTER(C.c_uint8)
+    s = np.ascontiguousarray(s, dtype=np.float64); e = np.ascontiguousarray(e, dtype=np.float64)
+    n = refkino.ref_kino_plan(P(cells64), -2 * g.origin[0], -2 * g.origin[1], g.xy_resolution, g.yaw_resolution, min_cnormal, max_rho, P(kp), P(s), P(e), P(out),
+                              out.shape[0], o3.ctypes.data_as(u8), o2.ctypes.data_as(u8))
+    assert n >= 0
+    return out[:n].copy(), o3, o2
+
+
+@pytest.mark.parametrize("which", ["bumps", "hill"])
+def test_kino_astar_matches_reference_bitwise(refkino, built, which, request):
+    from uneven_planner_b200 import front_end, maps
+    if which == "bumps":
+        m0 = request.getfixturevalue("bumps_map"); min_cnormal, max_rho = 0.8, 0.003      # ~10 % of the synthetic terrain becomes obstacle
+    else:
+        m0 = request.getfixturevalue("hill_map"); min_cnormal, max_rho = 0.8, 0.05          # run_hill.yaml
+    cells64 = np.ascontiguousarray(m0.cells, dtype=np.float64)
+    m = maps.UnevenMapData(m0.geom, m0.cells, which, cells64=cells64)
+    view = front_end.MapView(m, min_cnormal, max_rho)
+    ap = front_end.default_params()
+    rng = np.random.default_rng(11)
+    X, Y, W = m.shape
+    frac = view.occ2.mean()
+    assert 0.01 < frac < 0.6, frac
+    npath = nlong = 0
+    cases = [(rng.uniform(-4.3, 4.3, 2), rng.uniform(-np.pi, np.pi), rng.uniform(-4.3, 4.3, 2), rng.uniform(-np.pi, np.pi)) for _ in range(10)]
+    for k, (sp, sy, ep, ey) in enumerate(cases):
+        s = np.array([sp[0], sp[1], sy]); e = np.array([ep[0], ep[1], ey])
+        want, o3, o2 = _ref_plan(refkino, m, cells64, min_cnormal, max_rho, ap, s, e)
+        if k == 0:
+            assert np.array_equal(o3, view.occ3) and np.array_equal(o2, view.occ2)      # ualm_map_occupancy == uneven_map.cpp:169-179
+        got, nexp = front_end.plan(view, s, e, ap)
+        assert got.shape == want.shape and np.array_equal(got, want), (k, got.shape, want.shape)
+        npath += len(got) > 0
+        nlong += nexp > 500
+    assert npath >= 5 and nlong >= 1
+    # entry checks (kino_astar.cpp:85-95): an occupied start (3-D grid) or goal (2-D grid) gives an empty path on both sides
+    ox, oy = np.argwhere(view.occ2)[len(np.argwhere(view.occ2)) // 2]
+    g = m.geom
+    bad = np.array([g.origin[0] + (ox + 0.5) * g.xy_resolution, g.origin[1] + (oy + 0.5) * g.xy_resolution, 0.2])
+    free = np.array([cases[0][0][0], cases[0][0][1], cases[0][1]])
+    for s, e in ((free, bad),):
+        want, _, _ = _ref_plan(refkino, m, cells64, min_cnormal, max_rho, ap, s, e)
+        got, _ = front_end.plan(view, s, e, ap)
+        assert len(want) == 0 and len(got) == 0
+    # other parameters: finer yaw bins, no terrain term, a different primitive duration
+    ap2 = front_end.default_params()
+    ap2.yaw_resolution = 0.8; ap2.weight_sigma = 0.0; ap2.time_interval = 0.4; ap2.weight_v_change = 0.3; ap2.weight_delta_change = 0.2
+    for sp, sy, ep, ey in cases[:3]:
+        s = np.array([sp[0], sp[1], sy]); e = np.array([ep[0], ep[1], ey])
+        want, _, _ = _ref_plan(refkino, m, cells64, min_cnormal, max_rho, ap2, s, e)
+        got, _ = front_end.plan(view, s, e, ap2)
+        assert got.shape == want.shape and np.array_equal(got, want)

@@ -27,6 +27,20 @@ class MapGeom(C.Structure):
                 ("xy_resolution", C.c_double), ("yaw_resolution", C.c_double)]
 
 
+class AstarParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("yaw_resolution", "lambda_heu", "weight_r2", "weight_so2", "weight_v_change", "weight_delta_change", "weight_sigma",
+                                          "time_interval", "collision_interval", "oneshot_range", "wheel_base", "max_steer", "max_vel")]
+
+
+class AstarMap(C.Structure):
+    _fields_ = [("geom", C.POINTER(MapGeom)), ("cells", C.POINTER(C.c_float)), ("cells64", C.POINTER(C.c_double)), ("occ3", C.POINTER(C.c_uint8)),
+                ("occ2", C.POINTER(C.c_uint8))]
+
+
+class ResampleParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("piece_len", "yaw_piece_times", "mean_vel", "init_time_times", "init_sig_vel")]
+
+
 class Result(C.Structure):
     _fields_ = [("ret_code", C.c_int32), ("outer_iters", C.c_int32), ("n_evals", C.c_int32),
                 ("n_lbfgs_iters", C.c_int32), ("last_lbfgs_ret", C.c_int32), ("max_bound", C.c_int32), ("sum_bound", C.c_int32), ("reserved", C.c_int32),
@@ -56,6 +70,12 @@ def lib():
     L.ualm_map_occupancy.argtypes = [fp, C.POINTER(MapGeom), C.c_double, C.c_double, C.POINTER(C.c_uint8),
                                      C.POINTER(C.c_uint8)]
     L.ualm_dubins_path.argtypes = [dp, dp, C.c_double, C.c_double, dp, C.c_int]
+    L.ualm_dubins_shot.argtypes = [dp, dp, C.c_double, C.c_double, dp, C.c_int, dp]
+    L.ualm_astar_default_params.argtypes = [C.POINTER(AstarParams)]
+    L.ualm_astar_default_params.restype = None
+    L.ualm_kino_astar_plan.argtypes = [C.POINTER(AstarMap), C.POINTER(AstarParams), dp, dp, dp, C.c_int, C.POINTER(C.c_int)]
+    L.ualm_front_end_batch.argtypes = [C.POINTER(AstarMap), C.POINTER(AstarParams), C.POINTER(ResampleParams), C.c_int, dp, dp, C.c_int, ip, ip, dp, dp, dp,
+                                       C.c_longlong, dp, C.c_longlong, ip, ip]
     L.ualm_resample_path.argtypes = [dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp,
                                      C.c_int, dp, C.c_int, ip, ip, dp]
     L.ualm_map_preprocess_cloud.argtypes = [fp, C.c_int64, C.c_double, C.c_double, C.c_double, fp, C.c_int64]

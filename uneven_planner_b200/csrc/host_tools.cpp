@@ -154,8 +154,9 @@ extern "C" int ualm_map_occupancy(const float *cells, const ualm_map_geom_t *g, 
                 size_t a = (size_t)x * Y * W + (size_t)y * W + w;
                 const double zbx = cells[4 * a + 2], zby = cells[4 * a + 3];
                 const double c = std::sqrt(1.0 - zbx * zbx - zby * zby);
-                // !(c >= min) also flags NaN normals as occupied
-                const bool occ = !(c >= min_cnormal) || cells[4 * a + 1] > max_rho; // uneven_map.cpp:174
+                // the reference's rule as written (uneven_map.cpp:174): a NaN c (zb rounded to just over unit length) compares false
+                // and is NOT flagged by the first term
+                const bool occ = c < min_cnormal || cells[4 * a + 1] > max_rho;
                 if (occ3) occ3[a] = occ;
                 if (occ && occ2) occ2[(size_t)x * Y + y] = 1;
             }

@@ -158,3 +158,35 @@ def generate(mapdata, B, seed=0, max_rho=0.05, min_cnormal=0.8, lo=-4.5, hi=4.5,
     pb = from_paths(paths)
     pb.starts = np.array(starts); pb.goals = np.array(goals)
     return pb
+
+
+def generate_astar(mapdata, B, seed=0, max_rho=0.05, min_cnormal=0.8, lo=-4.5, hi=4.5, min_dist=1.5, nthreads=0):
+    """B random SE(2) start/goal problems whose initial paths come from the reference's own front-end (KinoAstar::plan restated in
+    libualm, ualm_front_end_batch) instead of one Dubins curve: same random stream and entry checks as generate(); pairs without a path or
+    over the optimizer's limits are skipped.  Deterministic in (map, B, seed), independent of the thread count."""
+    from . import front_end
+    g = mapdata.geom
+    view = front_end.MapView(mapdata, min_cnormal, max_rho)
+    rng = Rng(seed)
+    parts, starts, goals = [], [], []
+    have = 0
+    while have < B:
+        cs, cg = [], []
+        while len(cs) < max(2 * (B - have), 64):
+            s = np.array([rng.uniform(lo, hi), rng.uniform(lo, hi), rng.uniform(-np.pi, np.pi)])
+            e = np.array([rng.uniform(lo, hi), rng.uniform(lo, hi), rng.uniform(-np.pi, np.pi)])
+            if np.hypot(*(s[:2] - e[:2])) < min_dist:
+                continue
+            cs.append(s); cg.append(e)
+        pb, packed, _ = front_end.plan_batch(view, np.array(cs), np.array(cg), nthreads=nthreads)
+        take = min(pb.B, B - have)
+        if take > 0:
+            oxy, oyaw, _, _ = pb.offsets()
+            parts.append(ProblemBatch(pb.N[:take].copy(), pb.M[:take].copy(), pb.bnd[:take].copy(), pb.total_time[:take].copy(), pb.inner_xy[:oxy[take]].copy(),
+                                      pb.inner_yaw[:oyaw[take]].copy()))
+            starts.append(pb.starts[:take]); goals.append(pb.goals[:take])
+            have += take
+    out = ProblemBatch(np.concatenate([p.N for p in parts]), np.concatenate([p.M for p in parts]), np.concatenate([p.bnd for p in parts]),
+                       np.concatenate([p.total_time for p in parts]), np.concatenate([p.inner_xy for p in parts]), np.concatenate([p.inner_yaw for p in parts]))
+    out.starts = np.concatenate(starts); out.goals = np.concatenate(goals)
+    return out
