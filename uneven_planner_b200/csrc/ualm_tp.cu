@@ -94,6 +94,7 @@ struct TpEngine {
     TpLane lanes[TP_LANES];
     long long rounds_total = 0;
     int chunk = 8;
+    int ka_warps = 1;             // warps (= trajectories) per ka_kernel CTA: 1, 2 or 4 (UALM_TP_KA_WARPS); 1 measured best by ~1 %: no warp waits for a CTA mate
     bool prof = false;            // developer profile (UALM_TP_PROFILE=1): in-kernel phase cycle counters, printed at destroy
 };
 
@@ -151,6 +152,7 @@ int tp_create(TpEngine **out, int device, int precision, std::string *err)
     if (const char *s = getenv("UALM_TP_TMA")) e->use_tma = atoi(s) ? 1 : 0;
     if (const char *s = getenv("UALM_TP_NOTMA")) { if (atoi(s)) e->use_tma = 0; }
     if (const char *s = getenv("UALM_TP_CHUNK")) e->chunk = std::max(1, atoi(s));
+    if (const char *s = getenv("UALM_TP_KA_WARPS")) { const int w = atoi(s); if (w == 1 || w == 2 || w == 4) e->ka_warps = w; }
     if (const char *s = getenv("UALM_TP_PROFILE")) e->prof = atoi(s) != 0;
     if (const char *s = getenv("UALM_TP_SUBGROUPS")) e->sg = std::min(TP_SUBGROUPS, std::max(1, atoi(s)));
     memset(&e->E, 0, sizeof(e->E));
@@ -455,7 +457,7 @@ int tp_admit(TpEngine *e, int lane, std::string *err)
 static size_t kb_smem_bytes(TpEngine *e, bool tma)
 {
     const size_t es = e->esz();
-    const size_t arrays = (size_t)(TP_KB_THREADS / 32) * (TP_MAXPPC * 13 + TP_YCAP * 7) * es;      // ChunkPart<R>
+    const size_t arrays = 2 * (size_t)(TP_KB_THREADS / 32) * (TP_MAXPPC * 13 + TP_YCAP * 7) * es;      // two ChunkPart<R> tables
     const size_t coef = ((size_t)12 * e->Nmax_live + (size_t)6 * e->Mmax_live * 2 + e->Mmax_live) * es;
     return (tma ? (size_t)TP_MAXPPC * TP_TILE_BYTES : 0) + ((arrays + 15) & ~(size_t)15) + coef + 64;
 }
@@ -477,7 +479,7 @@ static void ka_layout(TpEngine *e)
     e->E.ka_col_bytes = (int)((std::max(col, hist + 2 * (size_t)e->p.mem_size * 8) + 15) & ~(size_t)15);
     e->E.ka_hist_stride = hstride;
 }
-static size_t ka_smem_bytes(TpEngine *e) { return (size_t)TP_KA_WARPS * e->E.ka_col_bytes; }
+static size_t ka_smem_bytes(TpEngine *e) { return (size_t)e->ka_warps * e->E.ka_col_bytes; }
 
 // one round of group g on its stream: ka -> [ks] -> kb
 template <class R>
@@ -485,7 +487,7 @@ static int launch_round(TpEngine *e, int g, bool with_ks, bool tma, std::string 
 {
     const int upper = e->glive[g];
     cudaStream_t st = e->gstream[g];
-    ka_kernel<R><<<(upper + TP_KA_WARPS - 1) / TP_KA_WARPS, 32 * TP_KA_WARPS, ka_smem_bytes(e), st>>>(e->E, e->p, g);
+    ka_kernel<R><<<(upper + e->ka_warps - 1) / e->ka_warps, 32 * e->ka_warps, ka_smem_bytes(e), st>>>(e->E, e->p, g);
     if (with_ks) ks_kernel<R><<<upper, TP_KB_THREADS, ks_smem_bytes(e), st>>>(e->E, e->p, e->map, g);
     if (tma) kb_kernel<R, true><<<upper, TP_KB_THREADS, kb_smem_bytes(e, true), st>>>(e->E, e->p, e->map, e->tmap, g);
     else kb_kernel<R, false><<<upper, TP_KB_THREADS, kb_smem_bytes(e, false), st>>>(e->E, e->p, e->map, e->tmap, g);
@@ -737,8 +739,8 @@ int tp_time_penalty(TpEngine *e, int lane, int reps, int use_tma, float *ms_per_
     e->gcompact[g] = false;
     const int upper = e->glive[g];
     const bool tma = e->have_tmap && use_tma;
-    if (e->f32()) ka_kernel<float><<<(upper + TP_KA_WARPS - 1) / TP_KA_WARPS, 32 * TP_KA_WARPS, ka_smem_bytes(e), st>>>(e->E, e->p, g);
-    else ka_kernel<double><<<(upper + TP_KA_WARPS - 1) / TP_KA_WARPS, 32 * TP_KA_WARPS, ka_smem_bytes(e), st>>>(e->E, e->p, g);
+    if (e->f32()) ka_kernel<float><<<(upper + e->ka_warps - 1) / e->ka_warps, 32 * e->ka_warps, ka_smem_bytes(e), st>>>(e->E, e->p, g);
+    else ka_kernel<double><<<(upper + e->ka_warps - 1) / e->ka_warps, 32 * e->ka_warps, ka_smem_bytes(e), st>>>(e->E, e->p, g);
     auto kb = [&]() {
         if (e->f32()) {
             if (tma) kb_kernel<float, true><<<upper, TP_KB_THREADS, kb_smem_bytes(e, true), st>>>(e->E, e->p, e->map, e->tmap, g);

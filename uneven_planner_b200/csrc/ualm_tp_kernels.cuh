@@ -764,10 +764,12 @@ __device__ int advance(const TpPool &E, const TpParams &p, const SlotView &v, in
     return PH_REQ_FIRST;           // next lbfgs_optimize starts with an evaluation at the current x
 }
 
+// 128 registers = 4 CTAs of four warps per SM.  Measured: allowing 6 / 8 CTAs (80 / 64 registers, 0.5 - 1 KB of spills) makes every warp-round
+// 1.5 - 2x longer (the table and history loads contend) and lowers the throughput by 8 / 17 %
 template <class R>
 __global__ void __launch_bounds__(32 * TP_KA_WARPS, 4) ka_kernel(const __grid_constant__ TpPool E, const __grid_constant__ TpParams p, int group)
 {
-    const int lane = threadIdx.x & 31, widx = blockIdx.x * TP_KA_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, widx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // 1, 2 or 4 warps per CTA (TpEngine::ka_warps)
     if (widx >= E.n_active[group]) return;
     extern __shared__ __align__(16) unsigned char ka_smem[];     // per warp: ka_col_bytes
     unsigned char *wbase = ka_smem + (size_t)(threadIdx.x >> 5) * E.ka_col_bytes;

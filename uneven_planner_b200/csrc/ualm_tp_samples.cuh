@@ -257,11 +257,20 @@ __device__ __forceinline__ void chunk_scatter(ChunkPart<R> &P, bool on, int pl, 
 #pragma unroll
         for (int e = 0; e < 13; e++) P.xy[warp][pl][e] = cx[e];
     }
-    if (on && (lane == 0 || p2 != k2)) {
+    const bool head2 = on && (lane == 0 || p2 != k2);
+    const unsigned heads2 = __ballot_sync(0xffffffffu, head2);
+    if (head2) {
+        // two runs of one yaw piece inside a warp only happen when rounding swaps two samples at a piece boundary (two addends commute):
+        // the common, unique run head stores; only such twins add atomically (the table is zeroed before every chunk)
+        const unsigned same = __match_any_sync(heads2, k2);
         if (yrel < TP_YCAP) {
-            // two runs of one yaw piece inside a warp only happen when rounding swaps two samples at a piece boundary: two addends commute
+            if ((same & (same - 1u)) == 0u) {
 #pragma unroll
-            for (int e = 0; e < 7; e++) atomicAdd(&P.yw[warp][yrel][e], cw[e]);
+                for (int e = 0; e < 7; e++) P.yw[warp][yrel][e] = cw[e];
+            } else {
+#pragma unroll
+                for (int e = 0; e < 7; e++) atomicAdd(&P.yw[warp][yrel][e], cw[e]);
+            }
         } else {           // more yaw pieces per chunk than the table holds (M >> N): straight onto the accumulators
             const int m = ybase + yrel;
             if (m < M) {
@@ -316,8 +325,8 @@ __global__ void __launch_bounds__(TP_KB_THREADS) kb_kernel(const __grid_constant
     extern __shared__ __align__(128) unsigned char kb_smem[];
     // layout: tiles (128-byte aligned, first) | ChunkPart | c_xy (12N) | c_yaw (6M) | accY (6M) | accTy (M)
     float4 *tiles = (float4 *)kb_smem;
-    ChunkPart<R> &P = *(ChunkPart<R> *)(kb_smem + (TMA ? TP_MAXPPC * TP_TILE_BYTES : 0));
-    R *cxy = (R *)(&P + 1);
+    ChunkPart<R> *Pbuf = (ChunkPart<R> *)(kb_smem + (TMA ? TP_MAXPPC * TP_TILE_BYTES : 0));      // two tables: chunk k scatters into one while the other is zeroed
+    R *cxy = (R *)(Pbuf + 2);
     R *cyaw = cxy + 12 * N;
     R *accY = cyaw + ny;
     R *accTy = accY + ny;
@@ -342,15 +351,15 @@ __global__ void __launch_bounds__(TP_KB_THREADS) kb_kernel(const __grid_constant
     KProf kp;
     kp.start(E.prof ? E.prof + 16 : nullptr, tid);       // developer profile: phases of thread 0
     if (kp.p) atomicAdd((unsigned long long *)&kp.p[7], 1ull);
+    if (tid < TP_MAXPPC) { sh.org[tid][0] = sh.org[tid][1] = sh.org[tid][2] = 0x7fffffff; sh.org[tid][3] = 0; }
+    chunk_part_zero(Pbuf[0], tid);
     __syncthreads();
     kp.mark(0);
-    for (int p0 = 0; p0 < N; p0 += ppc) {
+    int it = 0;
+    for (int p0 = 0; p0 < N; p0 += ppc, it++) {
         const int np = min(ppc, N - p0), ns = np * K1;
-        // K + 1 > blockDim is handled by the stride loop below (one pass for the default K = 16: 7 pieces x 17 samples = 119 threads)
-        if (tid < TP_MAXPPC) { sh.org[tid][0] = sh.org[tid][1] = sh.org[tid][2] = 0x7fffffff; sh.org[tid][3] = 0; }
-        chunk_part_zero(P, tid);
+        ChunkPart<R> &P = Pbuf[it & 1];
         const int ybase = max(0, min((int)((R)p0 * Tx / Ty), M - 1) - 1);     // yaw piece of the chunk's first sample, one spare for rounding
-        __syncthreads();
         {
             const int qb = 0, q = tid;       // one pass: ns <= TP_KB_THREADS (int_K <= 127 on this path)
             const bool on = q < ns;
@@ -504,7 +513,10 @@ __global__ void __launch_bounds__(TP_KB_THREADS) kb_kernel(const __grid_constant
         parity ^= 1u;
         __syncthreads();
         kp.mark(4);
+        // fixed-order sums of this chunk's table; meanwhile the other table and the tile origins are reset for the next chunk
         chunk_gather<R>(P, p0, np, N, M, ybase, gdc, gdt, accY, accTy, tid);
+        chunk_part_zero(Pbuf[(it + 1) & 1], tid);
+        if (tid < TP_MAXPPC) { sh.org[tid][0] = sh.org[tid][1] = sh.org[tid][2] = 0x7fffffff; sh.org[tid][3] = 0; }
         kp.mark(5);
         __syncthreads();
     }
