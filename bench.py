@@ -498,7 +498,9 @@ def main():
     fast = None
     if head_prec == 64 and not args.no_fast:
         fdepth = 8
-        rf = measure(32, fdepth, max(args.steps, fdepth + 4), max(min(args.warmup, fdepth), 2), False)
+        # three pipeline lengths of timed steps: the timed region starts and ends with an empty pipeline (synchronize on both sides), so a short one
+        # mostly measures filling and draining the eight lanes
+        rf = measure(32, fdepth, max(2 * args.steps, 3 * fdepth), max(args.warmup, fdepth), False)
         fo = rf["opt"]
         fo.select_lane(0)
         note("fast path measured; post-solve scan")

@@ -186,8 +186,8 @@ void tp_destroy(TpEngine *e)
     if (e->prof && e->kprof.p) {
         long long h[32];
         cudaMemcpy(h, e->kprof.p, sizeof(h), cudaMemcpyDeviceToHost);
-        const char *nm[KP_N] = {"finish:pre", "finish:adjoint-sweeps", "finish:post", "advance:line-search", "advance:post-ls", "two-loop", "alm-update", "forward:pre",
-                                "forward:sweeps", "forward:post", "scaling-z", "warps"};
+        const char *nm[KP_N] = {"finish:pre", "finish:gradient-tables", "finish:post", "advance:line-search", "advance:post-ls", "two-loop", "alm-update", "forward:pre",
+                                "forward:coefficient-tables", "forward:post", "(unused)", "warps"};
         long long tot = 0;
         for (int q = 0; q < KP_WARPS; q++) tot += h[q];
         fprintf(stderr, "[ualm-tp] ka phases (SM cycles per warp-round, %lld warp-rounds):", h[KP_WARPS]);
