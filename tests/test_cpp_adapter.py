@@ -89,3 +89,71 @@ def test_adapter_matches_batch_api(driver, bumps_map, tmp_path):
             assert np.array_equal(coeffs[i, d][::-1], c[6 * i + d * 6 * N: 6 * i + 6 + d * 6 * N])   # highest power first
     start = [float(x) for x in lines[1].split()[1:]]
     assert np.allclose(start, pb.bnd[1][:2], atol=1e-12)
+
+
+@pytest.fixture(scope="module")
+def chain_driver(built, tmp_path_factory):
+    d = tmp_path_factory.mktemp("cppchain")
+    exe = str(d / "chain_driver")
+    lib = os.path.join(ROOT, "uneven_planner_b200")
+    subprocess.run(["g++", "-O2", "-std=c++14", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "chain_driver.cpp"),
+                    "-o", exe, "-L", lib, "-lualm", "-Wl,-rpath," + lib], check=True)
+    return exe
+
+
+def _write_chain_case(path, m, starts, goals):
+    with open(path, "wb") as f:
+        f.write(struct.pack("<4i", *m.shape, len(starts)))
+        f.write(m.cells.tobytes())
+        f.write(np.ascontiguousarray(np.hstack([starts, goals]), dtype=np.float64).tobytes())
+
+
+def _chain_pairs(B=12):
+    rng = np.random.default_rng(9)
+    starts = np.column_stack([rng.uniform(-4.3, 4.3, B), rng.uniform(-4.3, 4.3, B), rng.uniform(-np.pi, np.pi, B)])
+    goals = np.column_stack([rng.uniform(-4.3, 4.3, B), rng.uniform(-4.3, 4.3, B), rng.uniform(-np.pi, np.pi, B)])
+    return starts, goals
+
+
+def test_chain_driver_plans_on_the_host_and_fails_loudly_without_gpu(chain_driver, bumps_map, tmp_path):
+    """planAndOptimizeBatch: the front-end half runs on host threads; without a CUDA device the optimizer half throws"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    starts, goals = _chain_pairs()
+    case = str(tmp_path / "chain.bin")
+    _write_chain_case(case, bumps_map, starts, goals)
+    r = subprocess.run([chain_driver, case, "64"], capture_output=True, text=True)
+    assert r.returncode == 10 and "EXCEPTION" in r.stdout and "CUDA" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", [64, 32])
+def test_chain_through_the_cpp_class_matches_the_c_abi(chain_driver, bumps_map, tmp_path, prec):
+    """(start, goal) pairs -> planAndOptimizeBatch -> exportToMpcBatch through include/ualm_traj_opt.hpp equals the same chain through the C ABI from Python"""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from uneven_planner_b200 import _lib, api, front_end
+    starts, goals = _chain_pairs()
+    case = str(tmp_path / "chain.bin")
+    _write_chain_case(case, bumps_map, starts, goals)
+    r = subprocess.run([chain_driver, case, str(prec)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.strip().splitlines()
+    head = [int(x) for x in lines[0].split()[1:]]
+    view = front_end.MapView(bumps_map, 0.8, 0.003)
+    pb, packed, _ = front_end.plan_batch(view, starts, goals, nthreads=2)
+    assert head[0] == pb.B and head[1:] == list(packed) and pb.B >= 4
+    opt = api.BatchALMTrajOpt(precision=prec).init(_lib.default_params()).set_environment(bumps_map)
+    res, cxy, cyaw = opt.optimize(pb)
+    ex = opt.mpc_export(pb.N, pb.M)
+    opt.close()
+    _, _, ocx, _ = pb.offsets()
+    sN = np.concatenate([[0], np.cumsum(pb.N)])
+    for i in range(pb.B):
+        v = lines[1 + i].split()
+        assert (int(v[0]), int(v[1]), int(v[2]), int(v[3])) == (int(pb.N[i]), int(pb.M[i]), res[i].ret_code, res[i].n_evals)
+        got = [float(x) for x in v[4:]]
+        want = [res[i].inner_cost, cxy[ocx[i] + 1], ex["pos_pts"][2 * (sN[i] + i)], ex["c_mpc_xy"][ocx[i] + 3], ex["dev"][i, 0]]
+        assert got == want, (i, got, want)
