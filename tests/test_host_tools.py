@@ -240,3 +240,14 @@ def test_front_end_batch_equals_the_sequential_front_end(built, bumps_map):
         N, M, bnd, T, ixy, iyaw = problems.resample(path)
         assert (N, M, T) == (pb1.N[k], pb1.M[k], pb1.total_time[k]) and np.array_equal(bnd, pb1.bnd[k])
         assert np.array_equal(ixy, pb1.inner_xy[oxy[k]:oxy[k + 1]]) and np.array_equal(iyaw, pb1.inner_yaw[oyaw[k]:oyaw[k + 1]])
+
+
+def test_astar_workload_generator_is_deterministic(built, bumps_map):
+    """problems.generate_astar: same (map, B, seed) -> same batch whatever the thread count; every problem within the optimizer's limits"""
+    from uneven_planner_b200 import problems
+    a = problems.generate_astar(bumps_map, 24, seed=4, max_rho=0.003, nthreads=1)
+    b = problems.generate_astar(bumps_map, 24, seed=4, max_rho=0.003, nthreads=3)
+    assert a.B == b.B == 24
+    for x, y in zip((a.N, a.M, a.bnd, a.total_time, a.inner_xy, a.inner_yaw, a.starts, a.goals), (b.N, b.M, b.bnd, b.total_time, b.inner_xy, b.inner_yaw, b.starts, b.goals)):
+        assert np.array_equal(x, y)
+    assert a.N.max() <= 64 and a.M.max() <= 128 and a.N.min() >= 1

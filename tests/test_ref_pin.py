@@ -469,13 +469,14 @@ def _ref_plan(refkino, m, cells64, min_cnormal, max_rho, ap, s, e):
     return out[:n].copy(), o3, o2
 
 
-@pytest.mark.parametrize("which", ["bumps", "hill"])
+@pytest.mark.parametrize("which", ["bumps", "hill", "desert", "volcano", "forest"])
 def test_kino_astar_matches_reference_bitwise(refkino, built, which, request):
-    from uneven_planner_b200 import front_end, maps
+    from uneven_planner_b200 import configs, front_end, maps
     if which == "bumps":
         m0 = request.getfixturevalue("bumps_map"); min_cnormal, max_rho = 0.8, 0.003      # ~10 % of the synthetic terrain becomes obstacle
     else:
-        m0 = request.getfixturevalue("hill_map"); min_cnormal, max_rho = 0.8, 0.05          # run_hill.yaml
+        m0 = request.getfixturevalue("terrain")(which)                                    # occupancy thresholds of the terrain's own yaml file
+        gk = configs.gen_kwargs(which); min_cnormal, max_rho = gk["min_cnormal"], gk["max_rho"]
     cells64 = np.ascontiguousarray(m0.cells, dtype=np.float64)
     m = maps.UnevenMapData(m0.geom, m0.cells, which, cells64=cells64)
     view = front_end.MapView(m, min_cnormal, max_rho)
@@ -483,7 +484,7 @@ def test_kino_astar_matches_reference_bitwise(refkino, built, which, request):
     rng = np.random.default_rng(11)
     X, Y, W = m.shape
     frac = view.occ2.mean()
-    assert 0.01 < frac < 0.6, frac
+    assert 0.005 < frac < 0.8, frac
     npath = nlong = 0
     cases = [(rng.uniform(-4.3, 4.3, 2), rng.uniform(-np.pi, np.pi), rng.uniform(-4.3, 4.3, 2), rng.uniform(-np.pi, np.pi)) for _ in range(10)]
     for k, (sp, sy, ep, ey) in enumerate(cases):
@@ -495,7 +496,7 @@ def test_kino_astar_matches_reference_bitwise(refkino, built, which, request):
         assert got.shape == want.shape and np.array_equal(got, want), (k, got.shape, want.shape)
         npath += len(got) > 0
         nlong += nexp > 500
-    assert npath >= 5 and nlong >= 1
+    assert npath >= 3 and (nlong >= 1 or which in ("desert",))
     # entry checks (kino_astar.cpp:85-95): an occupied start (3-D grid) or goal (2-D grid) gives an empty path on both sides
     ox, oy = np.argwhere(view.occ2)[len(np.argwhere(view.occ2)) // 2]
     g = m.geom
