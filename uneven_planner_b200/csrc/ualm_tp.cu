@@ -469,12 +469,12 @@ static size_t ks_smem_bytes(TpEngine *e)
     return ((arrays + 15) & ~(size_t)15) + coef + 64;
 }
 // ka_kernel's shared memory per warp: the C^-1 dcost/dc vector (12 N + 6 M doubles of the largest live problem), aliased by the
-// right-hand sides of the forward pass and by the two-loop's history ring (4 slots x {s, y} x n elements)
+// right-hand sides of the forward pass and by the two-loop's history ring (TP_HRING slots x {s, y} x n elements)
 static void ka_layout(TpEngine *e)
 {
     const int nmax = 1 + 2 * (e->Nmax_live - 1) + (e->Mmax_live - 1);
     const int hstride = (int)(((size_t)nmax * e->esz() + 15) / 16 * 16 / e->esz());
-    const size_t col = ((size_t)12 * e->Nmax_live + 6 * e->Mmax_live) * 8, hist = (((size_t)4 * 2 * hstride * e->esz()) + 15) & ~(size_t)15;
+    const size_t col = ((size_t)12 * e->Nmax_live + 6 * e->Mmax_live) * 8, hist = (((size_t)TP_HRING * 2 * hstride * e->esz()) + 15) & ~(size_t)15;
     e->E.ka_hist_bytes = (int)hist;                                             // behind the ring: 1 / ys and alpha of the two-loop (2 m doubles)
     e->E.ka_col_bytes = (int)((std::max(col, hist + 2 * (size_t)e->p.mem_size * 8) + 15) & ~(size_t)15);
     e->E.ka_hist_stride = hstride;

@@ -46,6 +46,7 @@ namespace ualm_tp {
 #define TP_FW 14                        // doubles per LU factor row: 13 band entries + 1 / diagonal
 #define TP_FPAD 6                       // zero rows before and after each factor table
 #define TP_KA_WARPS 4
+#define TP_HRING 8                      // two-loop history ring slots in shared memory (cp.async, TP_HRING - 1 steps ahead)
 #define TP_KB_THREADS 128
 #define TP_TILE 8                       // map tile = 8 x 8 cells x 8 yaw layers of float4 = 8 KB
 #define TP_TILE_BYTES (TP_TILE * TP_TILE * TP_TILE * 16)
@@ -649,7 +650,7 @@ __device__ int advance(const TpPool &E, const TpParams &p, const SlotView &v, in
                     // then oldest -> newest) stream through a four-slot shared-memory ring by cp.async, three steps ahead of the
                     // dependent chain (dot product -> warp reduction -> axpy), so no global-memory latency sits on it.
                     constexpr int NR = TP_NVAR / 32;
-                    constexpr int HR = 4;
+                    constexpr int HR = TP_HRING;                          // ring slots: HR - 1 steps in flight ahead of the chain (the history streams from DRAM)
                     const int hstride = E.ka_hist_stride;                 // elements per vector slot (n rounded up to 16 bytes)
                     R *hring = (R *)v.sm;                                 // [HR][2][hstride], aliases the column buffer (idle here)
                     const unsigned hring0 = (unsigned)__cvta_generic_to_shared(hring);
@@ -658,7 +659,12 @@ __device__ int advance(const TpPool &E, const TpParams &p, const SlotView &v, in
                     // 1 / (y_j . s_j) of the steps and the alphas of the first loop sit in shared memory behind the ring (no global
                     // load on the chain)
                     double *rys_s = (double *)((char *)v.sm + E.ka_hist_bytes), *al_s = rys_s + m;
-                    auto jof = [&](int t) { return t < bound ? (end + m - 1 - t % m + m) % m : (end - bound + (t - bound) + 2 * m) % m; };
+                    // ring index of the history pair step t works on: newest -> oldest, then oldest -> newest (t < 2 bound <= 2 m: no division needed)
+                    auto jof = [&](int t) {
+                        int j = t < bound ? end - 1 - t : end - bound + (t - bound);
+                        j += j < 0 ? m : 0; j += j < 0 ? m : 0;
+                        return j >= m ? j - m : j;
+                    };
                     auto hissue = [&](int t) {
                         if (t < nsteps) {
                             const int j = jof(t);
@@ -676,11 +682,12 @@ __device__ int advance(const TpPool &E, const TpParams &p, const SlotView &v, in
                     for (int e = 0; e < NR; e++) { const int q = lane + 32 * e; dreg[e] = q < n ? v.d[q] : 0.0; }
                     for (int t = lane; t < bound; t += 32) rys_s[t] = lys[(end + m - 1 - t % m + m) % m];
                     __syncwarp();
-                    hissue(0); hissue(1); hissue(2);
+#pragma unroll
+                    for (int t0 = 0; t0 < HR - 1; t0++) hissue(t0);
                     const double scl = ys / yy;
                     for (int t = 0; t < nsteps; t++) {
-                        hissue(t + 3);
-                        cp_async_wait<3>();
+                        hissue(t + HR - 1);
+                        cp_async_wait<HR - 1>();
                         __syncwarp();
                         const int j = jof(t);
                         const R *sv = hring + (size_t)(t % HR) * 2 * hstride, *yv = sv + hstride;
