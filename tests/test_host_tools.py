@@ -251,3 +251,21 @@ def test_astar_workload_generator_is_deterministic(built, bumps_map):
     for x, y in zip((a.N, a.M, a.bnd, a.total_time, a.inner_xy, a.inner_yaw, a.starts, a.goals), (b.N, b.M, b.bnd, b.total_time, b.inner_xy, b.inner_yaw, b.starts, b.goals)):
         assert np.array_equal(x, y)
     assert a.N.max() <= 64 and a.M.max() <= 128 and a.N.min() >= 1
+
+
+def test_kino_astar_reproduces_the_reference_golden_paths(built, bumps_map):
+    """tests/golden/kino_astar_golden.npz holds the polylines of the reference's own KinoAstar::plan (kino_astar.cpp compiled unmodified, see
+    tests/golden/make_kino_golden.py) on the synthetic terrain: ualm_kino_astar_plan returns them bit for bit -- also where /root/reference and the
+    reference build are absent"""
+    import os
+    from uneven_planner_b200 import front_end
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kino_astar_golden.npz"))
+    view = front_end.MapView(bumps_map, float(gold["min_cnormal"]), float(gold["max_rho"]))
+    off = np.concatenate([[0], np.cumsum(gold["lens"])])
+    nonempty = 0
+    for b in range(len(gold["lens"])):
+        path, _ = front_end.plan(view, gold["starts"][b], gold["goals"][b])
+        want = gold["paths"][off[b]:off[b + 1]]
+        assert path.shape == want.shape and np.array_equal(path, want), b
+        nonempty += len(want) > 0
+    assert nonempty >= 6
